@@ -1,0 +1,1011 @@
+// extern "C" shim of include/gamma_b200.h: owns the device mirror of one RetrievalModel
+// (quantizers, realtime posting pools, raw vectors, deleted bitmap) and sequences the
+// kernels of a Search call on one CUDA stream.  No CPU fallback exists anywhere in here:
+// every data-path step is a kernel launch; the host only moves bytes and keeps list extents.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gamma_b200.h"
+#include "kernels.h"
+
+using namespace gb;
+
+static thread_local std::string g_err;
+static void set_err(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      set_err("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return e_ == cudaErrorMemoryAllocation ? GB200_ENOMEM : GB200_ECUDA;               \
+    }                                                                                    \
+  } while (0)
+#define CKI(expr)                  \
+  do {                             \
+    int r_ = (expr);               \
+    if (r_ != GB200_OK) return r_; \
+  } while (0)
+
+namespace {
+
+struct DevBuf {  // grow-only device scratch
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GB200_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_err("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return GB200_ENOMEM;
+    }
+    cap = want;
+    return GB200_OK;
+  }
+  template <typename T>
+  T *as() { return reinterpret_cast<T *>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline long long roundup32(long long v) { return (v + 31) & ~31LL; }
+
+}  // namespace
+
+struct gb200_index {
+  int kind = 0;  // 0 = IVFPQ, 1 = FLAT
+  gb200_ivfpq_params p{};
+  int dsub = 0, chunk = 0, layout = 0, mode = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  bool trained = false;
+
+  float *d_cent = nullptr, *d_cent_norm = nullptr, *d_pq = nullptr, *d_pq_t = nullptr;
+
+  long long pool_cap = 0, pool_used = 0, pool_live_cap = 0;
+  uint8_t *d_codes = nullptr;
+  int *d_ids = nullptr;
+  float *d_norms = nullptr;
+  std::vector<long long> h_off;
+  std::vector<int> h_len, h_cap;
+  long long *d_off = nullptr;
+  int *d_len = nullptr;
+  std::vector<long long> vid_loc;
+  long long max_vid = -1;
+
+  float *d_raw = nullptr;
+  long long raw_cap = 0, raw_n = 0;
+
+  std::vector<uint32_t> h_deleted;
+  uint32_t *d_deleted = nullptr;
+  long long deleted_words_dev = 0;
+  bool any_deleted = false;
+  bool nodel_valid_dirty = true;       // cached "~deleted" bitmap needs rebuilding
+  DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
+  bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
+
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat;
+  unsigned long long *d_scanned = nullptr;
+  long long last_scanned = 0, launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[4] = {0, 0, 0, 0};
+
+  long long doc_bits() const { return std::max(max_vid + 1, raw_n); }
+};
+
+static int use_device(gb200_index *ix) {
+  CK(cudaSetDevice(ix->p.device));
+  return GB200_OK;
+}
+
+extern "C" {
+
+const char *gb200_last_error(void) { return g_err.c_str(); }
+
+int gb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static int common_create(gb200_index *ix) {
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ix->p.device < 0 || ix->p.device >= ndev) {
+    set_err("device %d not present (%d devices)", ix->p.device, ndev);
+    return GB200_EINVAL;
+  }
+  CK(cudaSetDevice(ix->p.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ix->p.device));
+  if (prop.major < 10) {
+    set_err("device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", ix->p.device, prop.major,
+            prop.minor);
+    return GB200_EUNSUPPORTED;
+  }
+  CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ix->ev[i]));
+  CK(cudaMalloc(&ix->d_scanned, sizeof(unsigned long long)));
+  CK(cudaMemset(ix->d_scanned, 0, sizeof(unsigned long long)));
+  return GB200_OK;
+}
+
+int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
+  if (!p || !out) return GB200_EINVAL;
+  if (p->d <= 0 || p->nlist <= 0 || p->nsubvector <= 0 || p->raw_d <= 0 || p->raw_d > p->d) {
+    set_err("bad ivfpq params");
+    return GB200_EINVAL;
+  }
+  if (p->nbits != 8) {
+    set_err("nbits_per_idx=%d: only 8 is implemented", p->nbits);
+    return GB200_EUNSUPPORTED;
+  }
+  if (p->d % p->nsubvector != 0 || p->nsubvector % 4 != 0) {
+    set_err("need d %% nsubvector == 0 and nsubvector %% 4 == 0 (d=%d M=%d)", p->d, p->nsubvector);
+    return GB200_EUNSUPPORTED;
+  }
+  gb200_index *ix = new gb200_index;
+  ix->kind = 0;
+  ix->p = *p;
+  ix->dsub = p->d / p->nsubvector;
+  int M = p->nsubvector;
+  ix->chunk = (M % 16 == 0) ? 16 : (M % 8 == 0 ? 8 : 4);
+  const char *force = getenv("GB200_FORCE_GENERIC");
+  bool generic = force && force[0] == '1';
+  ix->layout = (M == 32 && !generic) ? LAYOUT_M32_ROT : LAYOUT_PLAIN;
+  ix->mode = ix->layout == LAYOUT_M32_ROT ? 1 : 0;
+  int rc = common_create(ix);
+  if (rc != GB200_OK) {
+    delete ix;
+    return rc;
+  }
+  ix->h_off.assign(p->nlist, 0);
+  ix->h_len.assign(p->nlist, 0);
+  ix->h_cap.assign(p->nlist, 0);
+  if (cudaMalloc(&ix->d_off, sizeof(long long) * p->nlist) != cudaSuccess ||
+      cudaMalloc(&ix->d_len, sizeof(int) * p->nlist) != cudaSuccess) {
+    set_err("alloc list tables");
+    delete ix;
+    return GB200_ENOMEM;
+  }
+  cudaMemset(ix->d_off, 0, sizeof(long long) * p->nlist);
+  cudaMemset(ix->d_len, 0, sizeof(int) * p->nlist);
+  *out = ix;
+  return GB200_OK;
+}
+
+int gb200_flat_create(int device, int raw_d, int metric, gb200_index **out) {
+  if (!out || raw_d <= 0) return GB200_EINVAL;
+  gb200_index *ix = new gb200_index;
+  ix->kind = 1;
+  ix->p.device = device;
+  ix->p.d = raw_d;
+  ix->p.raw_d = raw_d;
+  ix->p.metric = metric;
+  ix->p.store_raw = 1;
+  int rc = common_create(ix);
+  if (rc != GB200_OK) {
+    delete ix;
+    return rc;
+  }
+  *out = ix;
+  return GB200_OK;
+}
+
+int gb200_destroy(gb200_index *ix) {
+  if (!ix) return GB200_OK;
+  cudaSetDevice(ix->p.device);
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  void *ptrs[] = {ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
+                  ix->d_off,  ix->d_len,       ix->d_raw, ix->d_deleted, ix->d_scanned};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
+                    &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
+                    &ix->ws_stage,    &ix->ws_flat};
+  for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < 4; i++)
+    if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+  return GB200_OK;
+}
+
+int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse, const float *pq) {
+  if (!ix || ix->kind != 0 || !coarse || !pq) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  const int d = ix->p.d, nlist = ix->p.nlist, M = ix->p.nsubvector, dsub = ix->dsub;
+  size_t cb = (size_t)nlist * d * sizeof(float), pb = (size_t)M * 256 * dsub * sizeof(float);
+  if (!ix->d_cent) {
+    CK(cudaMalloc(&ix->d_cent, cb));
+    CK(cudaMalloc(&ix->d_cent_norm, (size_t)nlist * sizeof(float)));
+    CK(cudaMalloc(&ix->d_pq, pb));
+    CK(cudaMalloc(&ix->d_pq_t, pb));
+  }
+  CK(cudaMemcpyAsync(ix->d_cent, coarse, cb, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(ix->d_pq, pq, pb, cudaMemcpyHostToDevice, ix->stream));
+  // code-major copy [256][M][dsub] for the table build
+  std::vector<float> t((size_t)M * 256 * dsub);
+  for (int m = 0; m < M; m++)
+    for (int c = 0; c < 256; c++)
+      memcpy(&t[((size_t)c * M + m) * dsub], &pq[((size_t)m * 256 + c) * dsub], dsub * sizeof(float));
+  CK(cudaMemcpyAsync(ix->d_pq_t, t.data(), pb, cudaMemcpyHostToDevice, ix->stream));
+  CK(launch_row_norms(ix->d_cent, nlist, d, ix->d_cent_norm, ix->stream));
+  ix->launches++;
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->trained = true;
+  return GB200_OK;
+}
+
+// ---- posting pools ---------------------------------------------------------------------
+static int pool_reserve(gb200_index *ix, long long need_total) {
+  if (need_total <= ix->pool_cap) return GB200_OK;
+  long long ncap = std::max(need_total, ix->pool_cap * 2);
+  ncap = roundup32(ncap);
+  const int M = ix->p.nsubvector;
+  uint8_t *nc = nullptr;
+  int *ni = nullptr;
+  float *nn = nullptr;
+  CK(cudaMalloc(&nc, (size_t)ncap * M));
+  CK(cudaMalloc(&ni, (size_t)ncap * sizeof(int)));
+  CK(cudaMalloc(&nn, (size_t)ncap * sizeof(float)));
+  if (ix->pool_used > 0) {
+    CK(cudaMemcpyAsync(nc, ix->d_codes, (size_t)ix->pool_used * M, cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaMemcpyAsync(ni, ix->d_ids, (size_t)ix->pool_used * sizeof(int), cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaMemcpyAsync(nn, ix->d_norms, (size_t)ix->pool_used * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+  }
+  CK(cudaStreamSynchronize(ix->stream));
+  if (ix->d_codes) cudaFree(ix->d_codes);
+  if (ix->d_ids) cudaFree(ix->d_ids);
+  if (ix->d_norms) cudaFree(ix->d_norms);
+  ix->d_codes = nc;
+  ix->d_ids = ni;
+  ix->d_norms = nn;
+  ix->pool_cap = ncap;
+  return GB200_OK;
+}
+
+static int sync_list_tables(gb200_index *ix) {
+  CK(cudaMemcpyAsync(ix->d_off, ix->h_off.data(), sizeof(long long) * ix->p.nlist, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * ix->p.nlist, cudaMemcpyHostToDevice, ix->stream));
+  return GB200_OK;
+}
+
+// place n postings (already assigned list/pos) on the device; pos may address existing slots (update in place)
+static int write_postings(gb200_index *ix, long long n, const int *list_no, const int *pos, const int *vid32,
+                          const uint8_t *codes) {
+  const int M = ix->p.nsubvector;
+  size_t b_int = (size_t)n * sizeof(int);
+  size_t total = 3 * b_int + (size_t)n * M;
+  CKI(ix->ws_stage.ensure(total));
+  char *base = ix->ws_stage.as<char>();
+  int *d_list = (int *)base, *d_pos = (int *)(base + b_int), *d_vid = (int *)(base + 2 * b_int);
+  uint8_t *d_aos = (uint8_t *)(base + 3 * b_int);
+  CK(cudaMemcpyAsync(d_list, list_no, b_int, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(d_pos, pos, b_int, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(d_vid, vid32, b_int, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(d_aos, codes, (size_t)n * M, cudaMemcpyHostToDevice, ix->stream));
+  AppendParams A;
+  A.list_no = d_list;
+  A.pos = d_pos;
+  A.vid = d_vid;
+  A.codes_aos = d_aos;
+  A.centroids = ix->d_cent;
+  A.pq = ix->d_pq;
+  A.list_off = ix->d_off;
+  A.codes = ix->d_codes;
+  A.ids = ix->d_ids;
+  A.norms = ix->d_norms;
+  A.n = (int)n;
+  A.d = ix->p.d;
+  A.M = M;
+  A.dsub = ix->dsub;
+  A.chunk = ix->chunk;
+  A.layout = ix->layout;
+  CK(launch_append(A, ix->stream));
+  ix->launches++;
+  return GB200_OK;
+}
+
+static int append_locked(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids,
+                         const uint8_t *codes) {
+  const int nlist = ix->p.nlist, M = ix->p.nsubvector;
+  std::vector<int> inc(nlist, 0);
+  for (int64_t i = 0; i < n; i++) {
+    if (list_no[i] < 0 || list_no[i] >= nlist || vids[i] < 0 || vids[i] > 0x7ffffffeLL) {
+      set_err("append: posting %lld has list %d / vid %lld out of range", (long long)i, list_no[i], (long long)vids[i]);
+      return GB200_EINVAL;
+    }
+    inc[list_no[i]]++;
+  }
+  // grow the lists that overflow: new contiguous regions at the pool tail
+  struct Grow { int list; long long old_off; int old_cap; };
+  std::vector<Grow> grows;
+  long long tail = ix->pool_used;
+  for (int l = 0; l < nlist; l++) {
+    if (!inc[l]) continue;
+    long long need = (long long)ix->h_len[l] + inc[l];
+    if (need > (1LL << GB_SEQ_POS_BITS)) {
+      set_err("list %d would hold %lld postings (> 2^21, bucket_max_size)", l, need);
+      return GB200_EUNSUPPORTED;
+    }
+    if (need > ix->h_cap[l]) {
+      long long ncap = roundup32(std::max(need, (long long)ix->h_cap[l] + ix->h_cap[l] / 2));
+      grows.push_back({l, ix->h_off[l], ix->h_cap[l]});
+      ix->pool_live_cap += ncap - ix->h_cap[l];
+      ix->h_off[l] = tail;
+      ix->h_cap[l] = (int)ncap;
+      tail += ncap;
+    }
+  }
+  if (tail > ix->pool_used) {
+    CKI(pool_reserve(ix, tail));
+    CK(launch_fill_i32(ix->d_ids + ix->pool_used, tail - ix->pool_used, -1, ix->stream));
+    ix->launches++;
+    for (const Grow &g : grows) {
+      int len = ix->h_len[g.list];
+      if (len == 0) continue;
+      long long noff = ix->h_off[g.list];
+      CK(cudaMemcpyAsync(ix->d_codes + (size_t)noff * M, ix->d_codes + (size_t)g.old_off * M,
+                         (size_t)roundup32(len) * M, cudaMemcpyDeviceToDevice, ix->stream));
+      CK(cudaMemcpyAsync(ix->d_ids + noff, ix->d_ids + g.old_off, (size_t)len * sizeof(int),
+                         cudaMemcpyDeviceToDevice, ix->stream));
+      CK(cudaMemcpyAsync(ix->d_norms + noff, ix->d_norms + g.old_off, (size_t)len * sizeof(float),
+                         cudaMemcpyDeviceToDevice, ix->stream));
+    }
+    ix->pool_used = tail;
+  }
+  CK(cudaMemcpyAsync(ix->d_off, ix->h_off.data(), sizeof(long long) * nlist, cudaMemcpyHostToDevice, ix->stream));
+  // positions, in arrival order (== list order == tie-break order)
+  std::vector<int> pos(n), vid32(n);
+  std::vector<int> run(ix->h_len);
+  for (int64_t i = 0; i < n; i++) {
+    pos[i] = run[list_no[i]]++;
+    vid32[i] = (int)vids[i];
+    if (vids[i] > ix->max_vid) ix->max_vid = vids[i];
+    if ((size_t)vids[i] >= ix->vid_loc.size()) ix->vid_loc.resize(std::max<size_t>(vids[i] + 1, ix->vid_loc.size() * 2), -1);
+    ix->vid_loc[vids[i]] = ((long long)list_no[i] << 32) | (unsigned)pos[i];
+  }
+  // stage in slabs so the scratch stays bounded for bulk loads
+  const int64_t SLAB = 1 << 22;
+  for (int64_t s = 0; s < n; s += SLAB) {
+    int64_t m = std::min(SLAB, n - s);
+    CKI(write_postings(ix, m, list_no + s, pos.data() + s, vid32.data() + s, codes + (size_t)s * M));
+    CK(cudaStreamSynchronize(ix->stream));  // staging buffer is reused
+  }
+  ix->h_len = run;  // publish: the scan sees the new length only after the data is in place
+  CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->nodel_valid_dirty = true;
+  return GB200_OK;
+}
+
+int gb200_ivfpq_append(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids,
+                       const uint8_t *codes) {
+  if (!ix || ix->kind != 0 || n < 0 || (n > 0 && (!list_no || !vids || !codes))) return GB200_EINVAL;
+  if (!ix->trained) {
+    set_err("append before set_quantizers");
+    return GB200_ENOTTRAINED;
+  }
+  if (n == 0) return GB200_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  return append_locked(ix, n, list_no, vids, codes);
+}
+
+int gb200_ivfpq_update(gb200_index *ix, int64_t vid, int32_t new_list, const uint8_t *code) {
+  if (!ix || ix->kind != 0 || !code || new_list < 0 || new_list >= ix->p.nlist) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  if (vid < 0 || (size_t)vid >= ix->vid_loc.size() || ix->vid_loc[vid] < 0) return GB200_OK;  // reference: do nothing
+  long long loc = ix->vid_loc[vid];
+  int old_list = (int)(loc >> 32), old_pos = (int)(loc & 0xffffffff);
+  if (old_list == new_list) {
+    int l = new_list, p = old_pos, v = (int)vid;
+    CKI(write_postings(ix, 1, &l, &p, &v, code));
+    CK(cudaStreamSynchronize(ix->stream));
+    return GB200_OK;
+  }
+  // mark the old posting dead: id |= sign bit  (kDelIdxMask analogue)
+  int dead = (int)((unsigned)vid | 0x80000000u);
+  CK(cudaMemcpyAsync(ix->d_ids + ix->h_off[old_list] + old_pos, &dead, sizeof(int), cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  int64_t v64 = vid;
+  return append_locked(ix, 1, &new_list, &v64, code);
+}
+
+int gb200_ivfpq_list_sizes(gb200_index *ix, int64_t *sizes) {
+  if (!ix || ix->kind != 0 || !sizes) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  for (int l = 0; l < ix->p.nlist; l++) sizes[l] = ix->h_len[l];
+  return GB200_OK;
+}
+
+int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t *codes) {
+  if (!ix || ix->kind != 0 || list_no < 0 || list_no >= ix->p.nlist) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  int len = ix->h_len[list_no];
+  if (len == 0) return GB200_OK;
+  const int M = ix->p.nsubvector;
+  CKI(ix->ws_stage.ensure((size_t)len * (M + sizeof(int))));
+  int *d_i = ix->ws_stage.as<int>();
+  uint8_t *d_c = reinterpret_cast<uint8_t *>(d_i + len);
+  CK(launch_gather_list(ix->d_codes, ix->d_ids, ix->h_off[list_no], len, M, ix->chunk, ix->layout, d_c, d_i, ix->stream));
+  ix->launches++;
+  std::vector<int> hi(len);
+  CK(cudaMemcpyAsync(hi.data(), d_i, (size_t)len * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaMemcpyAsync(codes, d_c, (size_t)len * M, cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  for (int i = 0; i < len; i++) {
+    unsigned u = (unsigned)hi[i];
+    ids[i] = (u & 0x80000000u) ? (int64_t)((uint64_t)(u & 0x7fffffffu) | 0x8000000000000000ull) : (int64_t)u;
+  }
+  return GB200_OK;
+}
+
+// ---- raw vectors -----------------------------------------------------------------------
+int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x) {
+  if (!ix || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
+  if (n == 0) return GB200_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  const int rd = ix->p.raw_d;
+  long long need = first_vid + n;
+  if (need > 0x7fffffffLL) return GB200_EUNSUPPORTED;
+  if (need > ix->raw_cap) {
+    long long ncap = std::max(need, ix->raw_cap + ix->raw_cap / 2);
+    float *nr = nullptr;
+    CK(cudaMalloc(&nr, (size_t)ncap * rd * sizeof(float)));
+    if (ix->raw_n > 0)
+      CK(cudaMemcpyAsync(nr, ix->d_raw, (size_t)ix->raw_n * rd * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    if (ix->d_raw) cudaFree(ix->d_raw);
+    ix->d_raw = nr;
+    ix->raw_cap = ncap;
+  }
+  CK(cudaMemcpyAsync(ix->d_raw + (size_t)first_vid * rd, x, (size_t)n * rd * sizeof(float), cudaMemcpyHostToDevice,
+                     ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  if (need > ix->raw_n) ix->raw_n = need;
+  ix->nodel_valid_dirty = true;
+  return GB200_OK;
+}
+
+int64_t gb200_raw_count(gb200_index *ix) { return ix ? ix->raw_n : 0; }
+
+// ---- deleted bitmap ----------------------------------------------------------------------
+static int push_deleted(gb200_index *ix) {
+  long long words = (long long)ix->h_deleted.size();
+  if (words > ix->deleted_words_dev) {
+    if (ix->d_deleted) cudaFree(ix->d_deleted);
+    ix->d_deleted = nullptr;
+    long long cap = words + words / 2 + 1024;
+    CK(cudaMalloc(&ix->d_deleted, (size_t)cap * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ix->d_deleted, 0, (size_t)cap * sizeof(uint32_t), ix->stream));
+    ix->deleted_words_dev = cap;
+  }
+  if (words)
+    CK(cudaMemcpyAsync(ix->d_deleted, ix->h_deleted.data(), (size_t)words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->nodel_valid_dirty = true;
+  return GB200_OK;
+}
+
+int gb200_set_deleted(gb200_index *ix, const int64_t *docids, int64_t n, int deleted) {
+  if (!ix || n < 0 || (n > 0 && !docids)) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  for (int64_t i = 0; i < n; i++) {
+    int64_t doc = docids[i];
+    if (doc < 0 || doc > 0x7ffffffeLL) return GB200_EINVAL;
+    size_t w = (size_t)(doc >> 5);
+    if (w >= ix->h_deleted.size()) ix->h_deleted.resize(std::max(w + 1, ix->h_deleted.size() * 2), 0u);
+    if (deleted)
+      ix->h_deleted[w] |= 1u << (doc & 31);
+    else
+      ix->h_deleted[w] &= ~(1u << (doc & 31));
+  }
+  ix->any_deleted = false;
+  for (uint32_t w : ix->h_deleted)
+    if (w) {
+      ix->any_deleted = true;
+      break;
+    }
+  return push_deleted(ix);
+}
+
+int gb200_upload_deleted_bitmap(gb200_index *ix, const uint8_t *bitmap, int64_t nbits) {
+  if (!ix || nbits < 0 || (nbits > 0 && !bitmap)) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  size_t words = (size_t)((nbits + 31) / 32);
+  ix->h_deleted.assign(words, 0u);
+  // byte[id>>3] & (1 << (id&7))  ==  little-endian u32 word[id>>5] bit (id&31)
+  size_t bytes = (size_t)((nbits + 7) / 8);
+  memcpy(ix->h_deleted.data(), bitmap, bytes);
+  if (nbits & 31) ix->h_deleted[words - 1] &= (1u << (nbits & 31)) - 1u;
+  ix->any_deleted = false;
+  for (uint32_t w : ix->h_deleted)
+    if (w) {
+      ix->any_deleted = true;
+      break;
+    }
+  return push_deleted(ix);
+}
+
+// ---- validity bitmap for one search ---------------------------------------------------------
+// returns device pointer (or nullptr = everything valid) in *out
+static int prepare_valid(gb200_index *ix, const gb200_range_filter *filters, int n_filters, const uint32_t **out) {
+  *out = nullptr;
+  long long bits = roundup32(std::max<long long>(ix->doc_bits(), 32));
+  if (n_filters <= 0) {
+    if (!ix->any_deleted) return GB200_OK;
+    if (ix->nodel_valid_dirty || ix->valid_nodel.cap < (size_t)bits / 8) {
+      CKI(ix->valid_nodel.ensure((size_t)bits / 8));
+      CK(launch_build_valid(ix->d_deleted, (long long)ix->h_deleted.size() * 32, nullptr, 0,
+                            ix->valid_nodel.as<uint32_t>(), bits, ix->stream));
+      ix->launches++;
+      ix->nodel_valid_dirty = false;
+    }
+    *out = ix->valid_nodel.as<uint32_t>();
+    return GB200_OK;
+  }
+  // upload the range bitmaps back to back, then one kernel builds NOT deleted AND all ranges
+  std::vector<DevRangeFilter> desc(n_filters);
+  size_t total = 0;
+  std::vector<size_t> offs(n_filters);
+  for (int f = 0; f < n_filters; f++) {
+    const gb200_range_filter &rf = filters[f];
+    if (!rf.bitmap || rf.max_doc < rf.min_doc || rf.min_aligned > rf.min_doc || rf.min_aligned < 0) {
+      set_err("range filter %d malformed", f);
+      return GB200_EINVAL;
+    }
+    long long max_aligned = ((long long)rf.max_doc / 8 + 1) * 8 - 1;
+    size_t nbytes = (size_t)((max_aligned - rf.min_aligned + 1) / 8);
+    offs[f] = total;
+    total += (nbytes + 15) & ~(size_t)15;
+  }
+  CKI(ix->filt_bytes.ensure(total));
+  CKI(ix->filt_desc.ensure(sizeof(DevRangeFilter) * n_filters));
+  for (int f = 0; f < n_filters; f++) {
+    const gb200_range_filter &rf = filters[f];
+    long long max_aligned = ((long long)rf.max_doc / 8 + 1) * 8 - 1;
+    size_t nbytes = (size_t)((max_aligned - rf.min_aligned + 1) / 8);
+    CK(cudaMemcpyAsync(ix->filt_bytes.as<uint8_t>() + offs[f], rf.bitmap, nbytes, cudaMemcpyHostToDevice, ix->stream));
+    desc[f].bitmap = ix->filt_bytes.as<uint8_t>() + offs[f];
+    desc[f].min_doc = rf.min_doc;
+    desc[f].max_doc = rf.max_doc;
+    desc[f].min_aligned = rf.min_aligned;
+    desc[f].not_in = rf.not_in;
+  }
+  CK(cudaMemcpyAsync(ix->filt_desc.p, desc.data(), sizeof(DevRangeFilter) * n_filters, cudaMemcpyHostToDevice, ix->stream));
+  CKI(ix->valid_filt.ensure((size_t)bits / 8));
+  CK(launch_build_valid(ix->any_deleted ? ix->d_deleted : nullptr, (long long)ix->h_deleted.size() * 32,
+                        ix->filt_desc.as<DevRangeFilter>(), n_filters, ix->valid_filt.as<uint32_t>(), bits, ix->stream));
+  ix->launches++;
+  CK(cudaStreamSynchronize(ix->stream));  // desc/filters host buffers may go away
+  *out = ix->valid_filt.as<uint32_t>();
+  return GB200_OK;
+}
+
+int gb200_set_filters(gb200_index *ix, const gb200_range_filter *filters, int n_filters) {
+  if (!ix) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  if (n_filters <= 0) {
+    ix->dev_filter_active = false;
+    return GB200_OK;
+  }
+  const uint32_t *v = nullptr;
+  CKI(prepare_valid(ix, filters, n_filters, &v));
+  ix->dev_filter_active = true;
+  return GB200_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------
+static int resolve_nprobe(gb200_index *ix, const gb200_search_params *sp, int dflt) {
+  int np = sp->nprobe;
+  if (np <= 0 || np > ix->p.nlist) np = dflt;  // gamma_index_ivfpq.cc:539-545
+  if (np > ix->p.nlist) np = ix->p.nlist;
+  return np;
+}
+
+static int coarse_dev(gb200_index *ix, int n, const float *d_xq, int nprobe, int *d_keys, float *d_cdis) {
+  const int d = ix->p.d, nlist = ix->p.nlist;
+  if (nprobe > 2048) {
+    set_err("nprobe=%d > 2048 not implemented", nprobe);
+    return GB200_EUNSUPPORTED;
+  }
+  CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
+  CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
+  // bound the distance matrix scratch to ~1 GiB by chunking the queries
+  long long rows = std::max<long long>(1, (1LL << 28) / nlist);
+  if (rows > n) rows = n;
+  CKI(ix->ws_dist.ensure((size_t)rows * nlist * sizeof(float)));
+  for (long long r0 = 0; r0 < n; r0 += rows) {
+    int m = (int)std::min<long long>(rows, n - r0);
+    CK(launch_coarse_dist(d_xq + (size_t)r0 * d, ix->ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
+                          ix->ws_dist.as<float>(), ix->stream));
+    CK(launch_coarse_select(ix->ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
+                            d_cdis + (size_t)r0 * nprobe, ix->stream));
+    ix->launches += 2;
+  }
+  ix->launches += 1;
+  return GB200_OK;
+}
+
+// scan + rerank with probes already on the device
+static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, const gb200_search_params *sp, int nprobe,
+                           const int *d_keys, const float *d_cdis, const uint32_t *d_valid, float *d_out_d,
+                           long long *d_out_i) {
+  const int M = ix->p.nsubvector;
+  int R = sp->recall_num < k ? k : sp->recall_num;  // gamma_index_ivfpq.cc:762-765
+  const bool ip = sp->metric == GB200_METRIC_INNER_PRODUCT;
+  if (R > 2048) {
+    set_err("recall_num=%d > 2048 not implemented", R);
+    return GB200_EUNSUPPORTED;
+  }
+  if (nprobe > 2048) return GB200_EUNSUPPORTED;
+  if (sp->has_rank && (!ix->d_raw)) {
+    set_err("has_rank search but no raw vectors uploaded");
+    return GB200_EINVAL;
+  }
+  // splits: enough CTAs for ~2 waves of 148 SMs x 3 resident CTAs, merge buffer <= 8192 keys
+  int S = (148 * 3 * 2 + n - 1) / n;
+  S = std::max(1, std::min(S, nprobe));
+  while (S > 1 && (long long)S * R > 8192) S--;
+  ScanParams P;
+  P.xq = d_xq;
+  P.keys = d_keys;
+  P.coarse_dis = d_cdis;
+  P.centroids = ix->d_cent;
+  P.pq_t = ix->d_pq_t;
+  P.codes = ix->d_codes;
+  P.ids = ix->d_ids;
+  P.norms = ix->d_norms;
+  P.list_off = ix->d_off;
+  P.list_len = ix->d_len;
+  P.valid = d_valid;
+  CKI(ix->ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
+  P.cand = ix->ws_cand.as<u64>();
+  P.scanned = ix->d_scanned;
+  P.n = n;
+  P.d = ix->p.d;
+  P.M = M;
+  P.dsub = ix->dsub;
+  P.nlist = ix->p.nlist;
+  P.nprobe = nprobe;
+  P.S = S;
+  P.R = R;
+  P.cap = scan_buffer_cap(R);
+  P.chunk = ix->chunk;
+  P.max_np_s = (nprobe + S - 1) / S;
+  P.is_ip = ip ? 1 : 0;
+  if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {
+    set_err("scan needs %zu B shared memory (M=%d recall_num=%d): not implemented", scan_smem_bytes(P, ix->mode), M, R);
+    return GB200_EUNSUPPORTED;
+  }
+  CK(cudaMemsetAsync(ix->d_scanned, 0, sizeof(unsigned long long), ix->stream));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
+  CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));
+  RerankParams Q;
+  Q.cand = P.cand;
+  Q.keys = d_keys;
+  Q.list_off = ix->d_off;
+  Q.ids = ix->d_ids;
+  Q.xq = d_xq;
+  Q.raw = ix->d_raw;
+  Q.nraw = ix->raw_n;
+  Q.out_dist = d_out_d;
+  Q.out_ids = d_out_i;
+  Q.n = n;
+  Q.S = S;
+  Q.R = R;
+  Q.k = k;
+  Q.nprobe = nprobe;
+  Q.raw_d = ix->p.raw_d;
+  Q.xq_stride = ix->p.d;
+  Q.has_rank = sp->has_rank ? 1 : 0;
+  Q.is_ip = ip ? 1 : 0;
+  Q.min_score = sp->min_score;
+  Q.max_score = sp->max_score;
+  CK(launch_rerank(Q, ix->stream));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[3], ix->stream));
+  ix->launches += 2;
+  return GB200_OK;
+}
+
+static int finish_profile(gb200_index *ix) {
+  unsigned long long sc = 0;
+  CK(cudaMemcpyAsync(&sc, ix->d_scanned, sizeof(sc), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->last_scanned = (long long)sc;
+  if (ix->profiling) {
+    cudaEventElapsedTime(&ix->stage_ms[0], ix->ev[0], ix->ev[1]);
+    cudaEventElapsedTime(&ix->stage_ms[1], ix->ev[1], ix->ev[2]);
+    cudaEventElapsedTime(&ix->stage_ms[2], ix->ev[2], ix->ev[3]);
+    cudaEventElapsedTime(&ix->stage_ms[3], ix->ev[0], ix->ev[3]);
+  }
+  return GB200_OK;
+}
+
+static int check_search_args(gb200_index *ix, int n, const void *xq, int k, const gb200_search_params *sp,
+                             const void *D, const void *I) {
+  if (!ix || n < 0 || !sp || (n > 0 && (!xq || !D || !I))) return GB200_EINVAL;
+  if (k <= 0) {  // reference logs a warning and returns without touching the outputs (gamma_index_ivfpq.cc:753-756)
+    set_err("topK must be > 0");
+    return GB200_EINVAL;
+  }
+  if (sp->metric != GB200_METRIC_INNER_PRODUCT && sp->metric != GB200_METRIC_L2) return GB200_EINVAL;
+  return GB200_OK;
+}
+
+static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, int k,
+                             const gb200_search_params *sp, const gb200_range_filter *filters, int n_filters,
+                             bool use_installed_filter, const int64_t *keys_h, const float *cdis_h, int nprobe_pre,
+                             float *D, int64_t *I, bool out_on_dev) {
+  if (n == 0) return GB200_OK;
+  if (!ix->trained) {
+    set_err("IVFPQ search on an untrained index");
+    return GB200_ENOTTRAINED;
+  }
+  const int d = ix->p.d;
+  int nprobe = keys_h ? nprobe_pre : resolve_nprobe(ix, sp, ix->p.nprobe > 0 ? ix->p.nprobe : 80);
+  if (nprobe <= 0) return GB200_EINVAL;
+  const float *d_xq = xq;
+  if (!xq_on_dev) {
+    CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
+    CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    d_xq = ix->ws_xq.as<float>();
+  }
+  const uint32_t *d_valid = nullptr;
+  if (use_installed_filter && ix->dev_filter_active)
+    d_valid = ix->valid_filt.as<uint32_t>();
+  else
+    CKI(prepare_valid(ix, filters, n_filters, &d_valid));
+  CKI(ix->ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
+  CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
+  if (keys_h) {
+    std::vector<int> k32((size_t)n * nprobe);
+    for (size_t i = 0; i < k32.size(); i++) k32[i] = (keys_h[i] < 0 || keys_h[i] >= ix->p.nlist) ? -1 : (int)keys_h[i];
+    CK(cudaMemcpyAsync(ix->ws_keys.p, k32.data(), k32.size() * sizeof(int), cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaMemcpyAsync(ix->ws_cdis.p, cdis_h, (size_t)n * nprobe * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+  } else {
+    CKI(coarse_dev(ix, n, d_xq, nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>()));
+  }
+  float *d_D = D;
+  long long *d_I = reinterpret_cast<long long *>(I);
+  if (!out_on_dev) {
+    CKI(ix->ws_out_d.ensure((size_t)n * k * sizeof(float)));
+    CKI(ix->ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+    d_D = ix->ws_out_d.as<float>();
+    d_I = ix->ws_out_i.as<long long>();
+  }
+  CKI(scan_rerank_dev(ix, n, d_xq, k, sp, nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>(), d_valid, d_D, d_I));
+  if (!out_on_dev) {
+    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    CKI(finish_profile(ix));
+  }
+  return GB200_OK;
+}
+
+int gb200_ivfpq_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
+                       const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
+  CKI(check_search_args(ix, n, xq, k, sp, D, I));
+  if (ix->kind != 0) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  return ivfpq_search_impl(ix, n, xq, false, k, sp, filters, n_filters, false, nullptr, nullptr, 0, D, I, false);
+}
+
+int gb200_ivfpq_search_preassigned(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
+                                   const gb200_range_filter *filters, int n_filters, const int64_t *keys,
+                                   const float *coarse_dis, int nprobe, float *D, int64_t *I) {
+  CKI(check_search_args(ix, n, xq, k, sp, D, I));
+  if (ix->kind != 0 || !keys || !coarse_dis || nprobe <= 0) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  return ivfpq_search_impl(ix, n, xq, false, k, sp, filters, n_filters, false, keys, coarse_dis, nprobe, D, I, false);
+}
+
+int gb200_ivfpq_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp,
+                           float *D_dev, int64_t *I_dev, void *stream) {
+  CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
+  if (ix->kind != 0) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  // order after the caller's stream, run on ours, and make the caller's stream wait for us
+  cudaStream_t cs = (cudaStream_t)stream;
+  cudaEvent_t e;
+  CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventRecord(e, cs));
+  CK(cudaStreamWaitEvent(ix->stream, e, 0));
+  int rc = ivfpq_search_impl(ix, n, xq_dev, true, k, sp, nullptr, 0, true, nullptr, nullptr, 0, D_dev, I_dev, true);
+  if (rc == GB200_OK) {
+    CK(cudaEventRecord(e, ix->stream));
+    CK(cudaStreamWaitEvent(cs, e, 0));
+  }
+  cudaEventDestroy(e);
+  return rc;
+}
+
+int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, float *coarse_dis, int64_t *keys) {
+  if (!ix || ix->kind != 0 || n < 0 || nprobe <= 0 || nprobe > ix->p.nlist || !xq || !coarse_dis || !keys)
+    return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n == 0) return GB200_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  const int d = ix->p.d;
+  CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
+  CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  CKI(ix->ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
+  CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
+  CKI(coarse_dev(ix, n, ix->ws_xq.as<float>(), nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>()));
+  std::vector<int> k32((size_t)n * nprobe);
+  CK(cudaMemcpyAsync(k32.data(), ix->ws_keys.p, k32.size() * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaMemcpyAsync(coarse_dis, ix->ws_cdis.p, (size_t)n * nprobe * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  for (size_t i = 0; i < k32.size(); i++) keys[i] = k32[i];
+  return GB200_OK;
+}
+
+// ---- flat ----------------------------------------------------------------------------------------
+static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, int k, const gb200_search_params *sp,
+                     const gb200_range_filter *filters, int n_filters, bool use_installed_filter, float *D, int64_t *I,
+                     bool out_on_dev) {
+  if (n == 0) return GB200_OK;
+  const int d = ix->p.raw_d;
+  if (k > 2048) {
+    set_err("flat k=%d > 2048 not implemented", k);
+    return GB200_EUNSUPPORTED;
+  }
+  const float *d_xq = xq;
+  if (!xq_on_dev) {
+    CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
+    CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    d_xq = ix->ws_xq.as<float>();
+  }
+  const uint32_t *d_valid = nullptr;
+  if (use_installed_filter && ix->dev_filter_active)
+    d_valid = ix->valid_filt.as<uint32_t>();
+  else
+    CKI(prepare_valid(ix, filters, n_filters, &d_valid));
+  float *d_D = D;
+  long long *d_I = reinterpret_cast<long long *>(I);
+  if (!out_on_dev) {
+    CKI(ix->ws_out_d.ensure((size_t)n * k * sizeof(float)));
+    CKI(ix->ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+    d_D = ix->ws_out_d.as<float>();
+    d_I = ix->ws_out_i.as<long long>();
+  }
+  FlatParams F;
+  F.xq = d_xq;
+  F.raw = ix->d_raw;
+  F.valid = d_valid;
+  F.N = ix->raw_n;
+  F.out_dist = d_D;
+  F.out_ids = d_I;
+  F.n = n;
+  F.d = d;
+  F.k = k;
+  F.is_ip = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
+  F.min_score = sp->min_score;
+  F.max_score = sp->max_score;
+  F.nsplit = flat_exact_splits(ix->raw_n, n);
+  while (F.nsplit > 1 && (long long)F.nsplit * k > 8192) F.nsplit--;
+  CKI(ix->ws_flat.ensure((size_t)n * F.nsplit * k * sizeof(u64)));
+  F.scratch = ix->ws_flat.as<u64>();
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
+  CK(launch_flat_exact(F, ix->stream));
+  ix->launches += 2;
+  if (ix->profiling) {
+    CK(cudaEventRecord(ix->ev[2], ix->stream));
+    CK(cudaEventRecord(ix->ev[3], ix->stream));
+  }
+  if (!out_on_dev) {
+    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    CKI(finish_profile(ix));
+  }
+  return GB200_OK;
+}
+
+int gb200_flat_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
+                      const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
+  CKI(check_search_args(ix, n, xq, k, sp, D, I));
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  if (!ix->d_raw || ix->raw_n == 0) {  // empty store: all slots unfilled
+    for (long long i = 0; i < (long long)n * k; i++) {
+      D[i] = sp->metric == GB200_METRIC_INNER_PRODUCT ? -FLT_MAX : FLT_MAX;
+      I[i] = -1;
+    }
+    return GB200_OK;
+  }
+  return flat_impl(ix, n, xq, false, k, sp, filters, n_filters, false, D, I, false);
+}
+
+int gb200_flat_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp,
+                          float *D_dev, int64_t *I_dev, void *stream) {
+  CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  if (!ix->d_raw || ix->raw_n == 0) return GB200_EINVAL;
+  cudaStream_t cs = (cudaStream_t)stream;
+  cudaEvent_t e;
+  CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventRecord(e, cs));
+  CK(cudaStreamWaitEvent(ix->stream, e, 0));
+  int rc = flat_impl(ix, n, xq_dev, true, k, sp, nullptr, 0, true, D_dev, I_dev, true);
+  if (rc == GB200_OK) {
+    CK(cudaEventRecord(e, ix->stream));
+    CK(cudaStreamWaitEvent(cs, e, 0));
+  }
+  cudaEventDestroy(e);
+  return rc;
+}
+
+// ---- accounting ---------------------------------------------------------------------------------
+int64_t gb200_mem_bytes(gb200_index *ix) {
+  if (!ix) return 0;
+  std::lock_guard<std::mutex> g(ix->mu);
+  int64_t b = 0;
+  if (ix->kind == 0) {
+    b += (int64_t)ix->p.nlist * ix->p.d * 4 + (int64_t)ix->p.nlist * 4 + 2LL * ix->p.nsubvector * 256 * ix->dsub * 4;
+    b += ix->pool_cap * (ix->p.nsubvector + 8) + (int64_t)ix->p.nlist * 12;
+  }
+  b += ix->raw_cap * ix->p.raw_d * 4;
+  b += ix->deleted_words_dev * 4;
+  return b;
+}
+int64_t gb200_last_scanned_postings(gb200_index *ix) { return ix ? ix->last_scanned : 0; }
+int64_t gb200_launch_count(gb200_index *ix) { return ix ? ix->launches : 0; }
+int gb200_last_stage_ms(gb200_index *ix, float *out4) {
+  if (!ix || !out4) return GB200_EINVAL;
+  for (int i = 0; i < 4; i++) out4[i] = ix->stage_ms[i];
+  return GB200_OK;
+}
+int gb200_sync(gb200_index *ix) {
+  if (!ix) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  CKI(use_device(ix));
+  return finish_profile(ix);
+}
+int gb200_set_profiling(gb200_index *ix, int enable) {
+  if (!ix) return GB200_EINVAL;
+  ix->profiling = enable != 0;
+  return GB200_OK;
+}
+
+}  // extern "C"

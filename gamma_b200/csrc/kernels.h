@@ -1,0 +1,109 @@
+// Host-visible launchers of the gamma_b200 kernels (internal; the public surface is
+// include/gamma_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gb {
+
+typedef unsigned long long u64;
+
+// scan-order field of a candidate key: (probe_rank << 21) | position_in_list
+#define GB_SEQ_POS_BITS 21  // bucket_max_size default 1,280,000 < 2^21 (gamma_index_ivfpq.h:706)
+#define GB_SEQ_POS_MASK ((1u << GB_SEQ_POS_BITS) - 1u)
+
+// posting-mirror layouts (how a 32-posting block of codes is laid out in HBM)
+//   0: chunk-major, chunk = largest of {16,8,4} dividing M: byte b of posting i at
+//      ((b/chunk)*32 + i)*chunk + b%chunk
+//   1: M == 32, chunk 16, bytes pre-rotated per lane: stored byte s of posting i = code[(i + s) % 32]
+enum { LAYOUT_PLAIN = 0, LAYOUT_M32_ROT = 1 };
+
+struct ScanParams {
+  const float *xq;          // [n][d]
+  const int *keys;          // [n][nprobe] probed lists, ascending coarse distance, -1 = none
+  const float *coarse_dis;  // [n][nprobe]
+  const float *centroids;   // [nlist][d]
+  const float *pq_t;        // [256][M][dsub] code-major PQ codebook
+  const uint8_t *codes;     // posting pool (layout above)
+  const int *ids;           // [pool] vid, -1 = padding / moved (kDelIdxMask)
+  const float *norms;       // [pool] t(p) (L2 only)
+  const long long *list_off;// [nlist] first posting of the list (multiple of 32)
+  const int *list_len;      // [nlist]
+  const uint32_t *valid;    // validity bitmap or nullptr (everything valid)
+  u64 *cand;                // [n][S][R] surviving keys (unsorted), GB_KEY_MAX padded
+  unsigned long long *scanned;  // += postings walked (may be nullptr)
+  int n, d, M, dsub, nlist, nprobe, S, R, cap, chunk, max_np_s, is_ip;
+};
+size_t scan_smem_bytes(const ScanParams &P, int mode);
+int scan_buffer_cap(int R);
+cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);
+
+// K0 — device-side append into the posting mirror (+ t(p) for L2)
+struct AppendParams {
+  const int *list_no;       // [n]
+  const int *pos;           // [n] position inside the list
+  const int *vid;           // [n]
+  const uint8_t *codes_aos; // [n][M]
+  const float *centroids;   // [nlist][d]
+  const float *pq;          // [M][256][dsub]
+  const long long *list_off;
+  uint8_t *codes;
+  int *ids;
+  float *norms;
+  int n, d, M, dsub, chunk, layout;
+};
+cudaError_t launch_append(const AppendParams &P, cudaStream_t st);
+cudaError_t launch_fill_i32(int *p, long long n, int v, cudaStream_t st);
+// read a list back in reference AoS form (test hook)
+cudaError_t launch_gather_list(const uint8_t *codes, const int *ids, long long off, int len, int M,
+                               int chunk, int layout, uint8_t *out_codes, int *out_ids, cudaStream_t st);
+
+// K1 — coarse quantiser: dist[n][nlist] = |q|^2 + |c|^2 - 2 q.c (clamped at 0), then top-nprobe
+cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st);
+cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,
+                               const float *cent_norm, int n, int nlist, int d, float *dist,
+                               cudaStream_t st);
+cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys,
+                                 float *coarse_dis, cudaStream_t st);
+
+// K3 — merge the per-split survivors, optional exact re-rank, score window, top-k
+struct RerankParams {
+  const u64 *cand;          // [n][S][R]
+  const int *keys;          // [n][nprobe]
+  const long long *list_off;
+  const int *ids;
+  const float *xq;          // [n][raw_d] (raw query, rerank uses raw_d)
+  const float *raw;         // [nraw][raw_d]
+  long long nraw;
+  float *out_dist;          // [n][k]
+  long long *out_ids;       // [n][k]
+  int n, S, R, k, nprobe, raw_d, xq_stride, has_rank, is_ip;
+  float min_score, max_score;
+};
+cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st);
+
+// K4 — flat scan over the raw vectors
+struct FlatParams {
+  const float *xq;          // [n][d]
+  const float *raw;         // [N][d]
+  const uint32_t *valid;    // or nullptr
+  long long N;
+  float *out_dist;
+  long long *out_ids;
+  int n, d, k, is_ip;
+  float min_score, max_score;
+  u64 *scratch;             // [n][nsplit][kpad]
+  int nsplit;
+};
+cudaError_t launch_flat_exact(const FlatParams &P, cudaStream_t st);
+int flat_exact_splits(long long N, int n);
+
+// validity bitmap = NOT deleted AND all range filters
+struct DevRangeFilter {
+  const uint8_t *bitmap;  // device bytes
+  int min_doc, max_doc, min_aligned, not_in;
+};
+cudaError_t launch_build_valid(const uint32_t *deleted, long long deleted_bits, const DevRangeFilter *filters,
+                               int n_filters, uint32_t *valid, long long nbits, cudaStream_t st);
+
+}  // namespace gb

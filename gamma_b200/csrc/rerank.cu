@@ -1,0 +1,170 @@
+// K3 — per-query merge of the scan's survivors, optional exact re-rank on the raw vectors,
+// score window and final top-k.  Replaces compute_dis (index/impl/gamma_index_ivfpq.cc:642-697):
+//   has_rank : for every recall candidate dis = fvec_L2sqr / fvec_inner_product(xi, raw[vid], raw_d),
+//              keep if min_score <= dis <= max_score, k-heap, heap_reorder          (:646-680)
+//   !has_rank: heap_reorder(recall_num); copy the first k entries passing the window (:681-696)
+// and the vid lookup the scan deferred (ids[list_off + pos]).
+//
+// exact_distance() reproduces the summation order of faiss' AVX kernels
+// (faiss utils/distances_simd.cpp:366-431): 8 strided partial sums (mul then add, unfused),
+// hi/lo halves added, optional 4-wide and masked tails (fused), then two horizontal adds —
+// so re-ranked distances are bit-identical to the CPU engine built with the same flags.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gb {
+
+constexpr int RR_THREADS = 128;
+
+// 8 consecutive lanes (an "octet") cooperate on one candidate; returns the result in every lane of the octet
+template <bool IP>
+__device__ __forceinline__ float exact_distance_octet(const float *__restrict__ q, const float *__restrict__ y,
+                                                      int d, int sub /*0..7*/) {
+  float s = 0.f;
+  int d8 = d & ~7;
+  for (int i = sub; i < d8; i += 8) {
+    float a = q[i], b = __ldg(y + i);
+    if (IP) {
+      s = __fadd_rn(s, __fmul_rn(a, b));
+    } else {
+      float t = __fsub_rn(a, b);
+      s = __fadd_rn(s, __fmul_rn(t, t));
+    }
+  }
+  // msum2 = hi + lo
+  float other = __shfl_down_sync(GB_FULL, s, 4, 8);
+  float t4 = __fadd_rn(other, s);  // valid in sub 0..3
+  int rem = d - d8;
+  if (rem >= 4) {
+    if (sub < 4) {
+      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
+    }
+    d8 += 4;
+    rem -= 4;
+  }
+  if (rem > 0) {
+    if (sub < rem) {
+      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
+    }
+  }
+  // hadd, hadd: (t0 + t1) + (t2 + t3)
+  float n1 = __shfl_xor_sync(GB_FULL, t4, 1, 8);
+  float p = __fadd_rn(t4, n1);  // lanes 0,1: t0+t1 ; lanes 2,3: t2+t3
+  float n2 = __shfl_xor_sync(GB_FULL, p, 2, 8);
+  float r = __fadd_rn(p, n2);
+  return __shfl_sync(GB_FULL, r, 0, 8);
+}
+
+template <bool IP>
+__global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int p2_all, int p2_r) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  u64 *keys = reinterpret_cast<u64 *>(smem);                      // [p2_all]
+  u64 *keys2 = keys + p2_all;                                     // [p2_r]
+  int *vids = reinterpret_cast<int *>(keys2 + p2_r);              // [p2_r]
+  float *qs = reinterpret_cast<float *>(vids + p2_r);             // [raw_d]
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int total = P.S * P.R;
+  const u64 *cand = P.cand + (size_t)q * total;
+  for (int i = tid; i < p2_all; i += RR_THREADS) keys[i] = i < total ? cand[i] : GB_KEY_MAX;
+  if (P.has_rank)
+    for (int i = tid; i < P.raw_d; i += RR_THREADS) qs[i] = P.xq[(size_t)q * P.xq_stride + i];
+  __syncthreads();
+  block_bitonic_sort(keys, p2_all);  // ascending: best candidates first, scan order among equals
+
+  // recall set = first R finite keys; resolve vids
+  for (int i = tid; i < p2_r; i += RR_THREADS) {
+    int vid = -1;
+    if (i < P.R) {
+      u64 k = keys[i];
+      if (k != GB_KEY_MAX) {
+        uint32_t seq = (uint32_t)k;
+        int rank = seq >> GB_SEQ_POS_BITS, pos = seq & GB_SEQ_POS_MASK;
+        int list = P.keys[(size_t)q * P.nprobe + rank];
+        vid = P.ids[P.list_off[list] + pos];
+      }
+    }
+    vids[i] = vid;
+  }
+  __syncthreads();
+
+  float *od = P.out_dist + (size_t)q * P.k;
+  long long *oi = P.out_ids + (size_t)q * P.k;
+  const float neutral = IP ? -3.402823466e38f : 3.402823466e38f;
+
+  if (P.has_rank) {
+    // exact distances, 8 lanes per candidate
+    const int sub = tid & 7, oct = tid >> 3;
+    const int n_oct = RR_THREADS / 8;
+    for (int base = 0; base < p2_r; base += n_oct) {
+      int i = base + oct;
+      int vid = i < p2_r ? vids[i] : -1;
+      bool have = vid >= 0 && (long long)vid < P.nraw;
+      const float *y = P.raw + (size_t)(have ? vid : 0) * P.raw_d;
+      float dis = exact_distance_octet<IP>(qs, y, have ? P.raw_d : 0, sub);
+      if (sub == 0 && i < p2_r) {
+        bool ok = have && dis <= P.max_score && dis >= P.min_score;  // IsSimilarScoreValid
+        keys2[i] = ok ? (((u64)dist_to_key32<IP>(dis) << 32) | (uint32_t)i) : GB_KEY_MAX;
+      }
+    }
+    __syncthreads();
+    block_bitonic_sort(keys2, p2_r);
+    for (int j = tid; j < P.k; j += RR_THREADS) {
+      u64 k = j < p2_r ? keys2[j] : GB_KEY_MAX;
+      if (k != GB_KEY_MAX) {
+        od[j] = key32_to_dist<IP>((uint32_t)(k >> 32));
+        oi[j] = vids[(uint32_t)k];
+      } else {
+        od[j] = neutral;
+        oi[j] = -1;
+      }
+    }
+  } else {
+    // ADC distances are final: window filter in sorted order, first k
+    if (tid < 32) {
+      int filled = 0;
+      for (int base = 0; base < p2_r && filled < P.k; base += 32) {
+        int i = base + tid;
+        bool ok = false;
+        float dis = 0.f;
+        if (i < p2_r && vids[i] >= 0) {
+          dis = key32_to_dist<IP>((uint32_t)(keys[i] >> 32));
+          ok = dis <= P.max_score && dis >= P.min_score;
+        }
+        unsigned m = __ballot_sync(GB_FULL, ok);
+        int slot = filled + __popc(m & ((1u << tid) - 1u));
+        if (ok && slot < P.k) {
+          od[slot] = dis;
+          oi[slot] = vids[i];
+        }
+        filled += __popc(m);
+      }
+      if (filled > P.k) filled = P.k;
+      for (int j = filled + tid; j < P.k; j += 32) {
+        od[j] = neutral;
+        oi[j] = -1;
+      }
+    }
+  }
+}
+
+cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st) {
+  int p2_all = next_pow2(P.S * P.R);
+  int p2_r = next_pow2(P.R);
+  size_t smem = (size_t)(p2_all + p2_r) * sizeof(u64) + (size_t)p2_r * sizeof(int) + (size_t)P.raw_d * sizeof(float);
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[P.is_ip]) {
+    cudaError_t e = P.is_ip ? cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[P.is_ip] = smem;
+  }
+  if (P.is_ip)
+    rerank_kernel<true><<<P.n, RR_THREADS, smem, st>>>(P, p2_all, p2_r);
+  else
+    rerank_kernel<false><<<P.n, RR_THREADS, smem, st>>>(P, p2_all, p2_r);
+  return cudaGetLastError();
+}
+
+}  // namespace gb

@@ -1,0 +1,175 @@
+/*
+ * gamma_b200.h — C ABI of the B200-native Gamma search hot path.
+ *
+ * This is the drop-in boundary BELOW the reference's RetrievalModel plugin
+ * interface (/root/reference/index/retrieval_model.h:218-310): the C++ plugin
+ * classes in gamma_b200/plugin/ ("B200IVFPQ", "B200FLAT", registered with
+ * REGISTER_MODEL) are thin hosts that forward to these entry points, exactly
+ * where the reference's own models call into faiss.  Plain pointers and sizes
+ * only — no C++/torch types — so Go (cgo), Python (ctypes) or C++ can bind it.
+ *
+ * Conventions (reference: search/error_code.h:17-25, retrieval_model.h:228-301):
+ *   - every function returns 0 on success, a negative GB200_E* code on failure;
+ *     no exception ever crosses this boundary;
+ *   - pointers are HOST pointers unless the parameter name ends in _dev;
+ *   - output buffers are caller-allocated; unfilled result slots are id = -1 and
+ *     distance = FLT_MAX (L2) / -FLT_MAX (InnerProduct), the neutral heap value
+ *     the reference leaves there (faiss utils/ordered_key_value.h:49-69);
+ *   - there is NO CPU fallback: if no sm_100 device is usable, create fails.
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef GAMMA_B200_H_
+#define GAMMA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_OK 0
+#define GB200_EINVAL (-1)      /* bad argument (reference: -1 "bad input")            */
+#define GB200_ENOTTRAINED (-2) /* quantizers not set (reference Search returns -2)     */
+#define GB200_ECUDA (-3)       /* CUDA runtime error; see gb200_last_error()           */
+#define GB200_ENOMEM (-4)      /* device/host allocation failed                        */
+#define GB200_EUNSUPPORTED (-5)/* parameter outside what the kernels implement         */
+
+/* DistanceComputeType values of index/retrieval_model.h:20 */
+#define GB200_METRIC_INNER_PRODUCT 0
+#define GB200_METRIC_L2 1
+
+typedef struct gb200_index gb200_index; /* opaque: one RetrievalModel's device state */
+
+/* Model parameters: IVFPQModelParams (index/impl/gamma_index_ivfpq.h:675-887) reduced
+ * to what the search path needs.  nbits_per_idx must be 8, by_residual is always true,
+ * the coarse quantizer is always IndexFlatL2 (gamma_index_ivfpq.cc:147,179).          */
+typedef struct gb200_ivfpq_params {
+  int device;      /* CUDA device ordinal                                              */
+  int d;           /* index dimension (d_ after support_indivisible_nsubvector pad)    */
+  int raw_d;       /* raw vector dimension (re-rank / flat use this)                   */
+  int nlist;       /* ncentroids                                                       */
+  int nsubvector;  /* M                                                                */
+  int nbits;       /* nbits_per_idx (8)                                                */
+  int metric;      /* index default metric, GB200_METRIC_*                             */
+  int nprobe;      /* index default nprobe (IVFPQModelParams::nprobe, default 80)      */
+  int store_raw;   /* 1: keep raw vectors on device (needed for has_rank and FLAT)     */
+} gb200_ivfpq_params;
+
+/* Per-call search parameters: IVFPQRetrievalParameters / FlatRetrievalParameters
+ * (gamma_index_ivfpq.h:629-673, gamma_index_flat.h:38-64) + the fields of
+ * GammaSearchCondition the models read (common/gamma_common_data.h:84-93).           */
+typedef struct gb200_search_params {
+  int metric;        /* GB200_METRIC_* (retrieval_params metric_type)                 */
+  int nprobe;        /* <=0 or >nlist: index default (gamma_index_ivfpq.cc:539-545)   */
+  int recall_num;    /* raised to k if smaller (gamma_index_ivfpq.cc:762-765)         */
+  int has_rank;      /* 1: exact re-rank of the recall set (compute_dis :646-680)     */
+  float min_score;   /* IsSimilarScoreValid window (gamma_common_data.h:95-97)        */
+  float max_score;
+} gb200_search_params;
+
+/* One range-filter bitmap: RangeQueryResult (table/range_query_result.h:24-160).
+ * bit (doc - min_aligned) of `bitmap` set  <=>  doc passes; docs outside [min,max]
+ * fail (or pass when not_in).  A search passes all filters (MultiRangeQueryResults::Has,
+ * :169-179).  n_filters == 0 means "no range filter" (range_query_result == nullptr).   */
+typedef struct gb200_range_filter {
+  int min_doc, max_doc; /* min_, max_                                                  */
+  int min_aligned;      /* (min_/8)*8                                                  */
+  int not_in;           /* b_not_in_                                                   */
+  const uint8_t *bitmap;/* ((max_aligned-min_aligned+1)/8) bytes, util/bitmap.cc:25-27 */
+} gb200_range_filter;
+
+const char *gb200_last_error(void);
+int gb200_device_count(void);
+
+/* ---- lifecycle: RetrievalModel ctor/Init/dtor (retrieval_model.h:220-233) ---------- */
+int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out);
+int gb200_flat_create(int device, int raw_d, int metric, gb200_index **out);
+int gb200_destroy(gb200_index *ix);
+
+/* ---- trained state: result of GammaIVFPQIndex::Indexing -> faiss::IndexIVFPQ::train
+ * (gamma_index_ivfpq.cc:272-354).  coarse: nlist x d f32 (IndexFlatL2::xb);
+ * pq: M x 256 x dsub f32 (ProductQuantizer::centroids).                               */
+int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse_centroids,
+                               const float *pq_centroids);
+
+/* ---- postings: RTInvertIndex::AddKeys / RealTimeMemData::AddKeys
+ * (realtime/realtime_invert_index.cc:43-71, realtime_mem_data.cc:264-303).
+ * n postings; posting i goes to the END of list list_no[i] (append order is list
+ * order, which is the tie-break order of the scan); vids < 2^31; codes n x M bytes.   */
+int gb200_ivfpq_append(gb200_index *ix, int64_t n, const int32_t *list_no,
+                       const int64_t *vids, const uint8_t *codes);
+/* RealTimeMemData::Update (realtime_mem_data.cc:305-327): same list -> overwrite the
+ * code in place; other list -> old posting gets kDelIdxMask (dead), new one appended.   */
+int gb200_ivfpq_update(gb200_index *ix, int64_t vid, int32_t new_list_no, const uint8_t *code);
+/* list_len[l] as the scan sees it (retrieve_idx_pos_, realtime_invert_index.cc:77-81)  */
+int gb200_ivfpq_list_sizes(gb200_index *ix, int64_t *sizes /* nlist */);
+/* read one list back in the REFERENCE layout (ids with kDelIdxMask bit 63, AoS codes);
+ * test hook mirroring RealTimeMemData::RetrieveCodes (realtime_mem_data.h:95-96).      */
+int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t *codes);
+
+/* ---- raw vectors: the read side of VectorReader::Gets / RawVector::GetVectorHeader
+ * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are
+ * implicit = first_vid .. first_vid+n-1; re-upload of an existing range = UpdateToStore. */
+int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x);
+int64_t gb200_raw_count(gb200_index *ix);
+
+/* ---- deleted-docs bitmap: bitmap::BitmapManager::Set/Unset (util/bitmap_manager.cc),
+ * bit = 1 => deleted; consulted by GammaSearchCondition::IsValid (:99-108).            */
+int gb200_set_deleted(gb200_index *ix, const int64_t *docids, int64_t n, int deleted);
+int gb200_upload_deleted_bitmap(gb200_index *ix, const uint8_t *bitmap, int64_t nbits);
+
+/* ---- search: RetrievalModel::Search (retrieval_model.h:282-284).
+ * GammaIVFPQIndex::Search (gamma_index_ivfpq.cc:514-566): coarse quantizer, ADC scan of
+ * the nprobe lists with the validity filter inside the scan, recall_num selection,
+ * optional exact re-rank, score window, top-k.  xq: n x d f32; out: n x k.             */
+int gb200_ivfpq_search(gb200_index *ix, int n, const float *xq, int k,
+                       const gb200_search_params *sp, const gb200_range_filter *filters,
+                       int n_filters, float *distances, int64_t *labels);
+/* GammaIVFPQIndex::search_preassigned (gamma_index_ivfpq.cc:701-890): probes given.
+ * keys n x nprobe (i64, -1 = none), coarse_dis n x nprobe.                             */
+int gb200_ivfpq_search_preassigned(gb200_index *ix, int n, const float *xq, int k,
+                                   const gb200_search_params *sp,
+                                   const gb200_range_filter *filters, int n_filters,
+                                   const int64_t *keys, const float *coarse_dis, int nprobe,
+                                   float *distances, int64_t *labels);
+/* coarse stage alone: quantizer->search (gamma_index_ivfpq.cc:560).                    */
+int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe,
+                       float *coarse_dis, int64_t *keys);
+/* GammaFLATIndex::Search (gamma_index_flat.cc:118-300) over the uploaded raw vectors;
+ * also the brute_force_search / untrained fallback of the IVFPQ model (:529-537).      */
+int gb200_flat_search(gb200_index *ix, int n, const float *xq, int k,
+                      const gb200_search_params *sp, const gb200_range_filter *filters,
+                      int n_filters, float *distances, int64_t *labels);
+
+/* ---- device-resident variants (queries/results already in HBM; stream = cudaStream_t
+ * as void*).  Used by bench.py's device-timed leg and by the multi-GPU driver so the
+ * per-rank top-k can feed ncclAllGather without a host round trip.                     */
+int gb200_ivfpq_search_dev(gb200_index *ix, int n, const float *xq_dev, int k,
+                           const gb200_search_params *sp, float *distances_dev,
+                           int64_t *labels_dev, void *stream);
+int gb200_flat_search_dev(gb200_index *ix, int n, const float *xq_dev, int k,
+                          const gb200_search_params *sp, float *distances_dev,
+                          int64_t *labels_dev, void *stream);
+/* install a per-index "valid docs" filter for the *_dev calls (same semantics as the
+ * filters argument above); n_filters = 0 clears it.                                    */
+int gb200_set_filters(gb200_index *ix, const gb200_range_filter *filters, int n_filters);
+
+/* ---- accounting: RetrievalModel::GetTotalMemBytes (retrieval_model.h:287) + bench ---- */
+int64_t gb200_mem_bytes(gb200_index *ix);
+/* postings the last IVFPQ search scanned (sum over (query,probe) of list length) and the
+ * number of kernels it launched — bench.py's algorithmic-bytes and gpu_launches.        */
+int64_t gb200_last_scanned_postings(gb200_index *ix);
+int64_t gb200_launch_count(gb200_index *ix);
+/* device time (ms, CUDA events on the search stream) of the stages of the last search:
+ * out[0]=coarse, out[1]=scan, out[2]=merge/rerank, out[3]=total.                        */
+int gb200_last_stage_ms(gb200_index *ix, float *out4);
+int gb200_set_profiling(gb200_index *ix, int enable);
+/* wait for the index's stream (after *_dev calls) and refresh the counters above.          */
+int gb200_sync(gb200_index *ix);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMMA_B200_H_ */

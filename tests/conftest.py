@@ -1,0 +1,117 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def has_gpu():
+    try:
+        from gamma_b200 import api
+        return api.lib().gb200_device_count() > 0
+    except Exception:
+        return False
+
+
+# ----------------------------------------------------------------------------------------------
+# result comparison: ids must agree except where the reference's own ordering is a floating-point
+# (near-)tie; distances must agree to `rtol` relative.
+# ----------------------------------------------------------------------------------------------
+def compare_topk(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-6):
+    """Returns dict(n_id_mismatch_unexplained, max_rel_err, n_slots).  A differing id at slot j is
+    'explained' when it is a near-tie swap: the id we returned sits in the reference list at a
+    distance within tolerance of slot j's, or (boundary tie) it is absent from the reference list but
+    its distance is within tolerance of the reference's last filled slot."""
+    D_ref, I_ref, D, I = map(np.asarray, (D_ref, I_ref, D, I))
+    n, k = I_ref.shape
+    bad = 0
+    max_rel = 0.0
+    for q in range(n):
+        dr, ir, dd, ii = D_ref[q], I_ref[q], D[q], I[q]
+        filled_ref = ir >= 0
+        filled = ii >= 0
+        nfr, nf = int(filled_ref.sum()), int(filled.sum())
+        if nfr != nf:
+            bad += abs(nfr - nf)
+        m = min(nfr, nf)
+        if m == 0:
+            continue
+        scale = np.maximum(np.abs(dr[:m]), atol / rtol)
+        rel = np.abs(dr[:m] - dd[:m]) / scale
+        max_rel = max(max_rel, float(rel.max()))
+        for j in range(m):
+            if ir[j] == ii[j]:
+                continue
+            tol = rtol * max(abs(float(dr[j])), abs(float(dd[j]))) + atol
+            where = np.nonzero(ir[:nfr] == ii[j])[0]
+            if where.size and abs(float(dr[where[0]]) - float(dd[j])) <= tol and abs(float(dr[where[0]]) - float(dr[j])) <= 2 * tol:
+                continue  # near-tie swap inside the list
+            if where.size == 0 and abs(float(dd[j]) - float(dr[nfr - 1])) <= 2 * tol and nfr == k:
+                continue  # tie at the k boundary
+            bad += 1
+    return dict(n_id_mismatch_unexplained=bad, max_rel_err=max_rel, n_slots=int(n * k))
+
+
+def assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-6, max_bad_frac=0.0):
+    r = compare_topk(D_ref, I_ref, D, I, rtol, atol)
+    assert r["max_rel_err"] <= rtol * 1.0001 + 1e-12, r
+    assert r["n_id_mismatch_unexplained"] <= max_bad_frac * r["n_slots"], r
+    return r
+
+
+# ----------------------------------------------------------------------------------------------
+# small reference-built indexes shared by the GPU parity tests
+# ----------------------------------------------------------------------------------------------
+class RefFixture:
+    """A reference (oracle/_ref) IVFPQ index over seeded synthetic data + everything needed to
+    mirror it into the device library."""
+
+    def __init__(self, N, d, nlist, M, metric, nq=64, n_clusters=64, seed_shift=0):
+        from gamma_b200 import synth
+        from oracle import ref
+        self.N, self.d, self.nlist, self.M, self.metric = N, d, nlist, M, metric
+        normalize = metric != "L2"
+        self.xb = synth.mixture(N, d, synth.SEED_BASE + seed_shift, n_clusters=n_clusters, normalize=normalize)
+        self.xq = synth.mixture(nq, d, synth.SEED_QUERY + seed_shift, n_clusters=n_clusters, normalize=normalize)
+        self.model_json = json.dumps({"ncentroids": nlist, "nsubvector": M, "metric_type": metric, "nprobe": 8})
+        self.ref = ref.RefIndex(d, "IVFPQ", self.model_json, indexing_size=N, bitmap_bits=max(N * 2, 1024))
+        self.ref.add_raw(self.xb)
+        self.ref.indexing()
+        self.ref.add_to_index()
+        self.centroids = self.ref.centroids()
+        self.pq = self.ref.pq_centroids()
+        self.lists = self.ref.lists()
+
+    def mirror(self, device=0, raw=True):
+        """Build the device index from the reference's trained state and postings (list order kept)."""
+        from gamma_b200 import api
+        ix = api.B200IVFPQ(device)
+        assert ix.Init(self.model_json, self.d) == 0, api.lib().gb200_last_error()
+        ix.set_quantizers(self.centroids, self.pq)
+        list_no = np.concatenate([np.full(len(ids), l, np.int32) for l, (ids, _) in enumerate(self.lists)])
+        vids = np.concatenate([ids for ids, _ in self.lists])
+        codes = np.concatenate([c for _, c in self.lists])
+        # feed in vid order like the engine's AddRTVecsToIndex loop would (per-list order is preserved)
+        order = np.argsort(vids, kind="stable")
+        assert ix.append(list_no[order], vids[order], codes[order]) == 0, api.lib().gb200_last_error()
+        if raw:
+            ix.upload_raw(self.xb)
+        return ix
+
+
+_FIXTURE_CACHE = {}
+
+
+def get_ref_fixture(key, **kw):
+    if key not in _FIXTURE_CACHE:
+        _FIXTURE_CACHE[key] = RefFixture(**kw)
+    return _FIXTURE_CACHE[key]

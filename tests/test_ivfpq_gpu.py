@@ -1,0 +1,208 @@
+"""GPU parity tests of the IVFPQ hot path against the compiled reference engine (oracle/_ref):
+same trained quantizers, same postings in the same list order, same queries, same filters.
+
+Parity contract: ids identical except where the reference ordering is a
+floating-point near-tie; ADC distances within 1e-4 relative; re-ranked (exact) distances
+bit-identical because exact_distance reproduces faiss' AVX summation order.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import assert_topk_parity, compare_topk, get_ref_fixture
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def fx_l2_m32():
+    return get_ref_fixture("l2_m32", N=40000, d=128, nlist=128, M=32, metric="L2", nq=96, n_clusters=128)
+
+
+def fx_l2_m16():
+    return get_ref_fixture("l2_m16", N=20000, d=64, nlist=64, M=16, metric="L2", nq=48, n_clusters=64)
+
+
+def fx_ip_m32():
+    return get_ref_fixture("ip_m32", N=30000, d=128, nlist=96, M=32, metric="InnerProduct", nq=64, n_clusters=96)
+
+
+def rj(nprobe, recall_num, metric):
+    return json.dumps({"nprobe": nprobe, "recall_num": recall_num, "metric_type": metric})
+
+
+@pytest.mark.parametrize("fx", [fx_l2_m32, fx_l2_m16, fx_ip_m32])
+def test_posting_mirror_roundtrip(fx):
+    f = fx()
+    ix = f.mirror(raw=False)
+    sizes = ix.list_sizes()
+    assert int(sizes.sum()) == f.N
+    for l in [0, 1, f.nlist // 2, f.nlist - 1]:
+        ids, codes = ix.get_list(l)
+        rids, rcodes = f.lists[l]
+        assert np.array_equal(ids, rids)  # bit-exact list order
+        assert np.array_equal(codes, rcodes)  # bit-exact codes through the blocked/rotated layout
+
+
+@pytest.mark.parametrize("fx", [fx_l2_m32, fx_l2_m16])
+def test_coarse_quantizer_matches_reference(fx):
+    f = fx()
+    ix = f.mirror(raw=False)
+    nprobe = 16
+    cd_ref, k_ref = f.ref.coarse(f.xq, nprobe)
+    cd, k = ix.coarse(f.xq, nprobe)
+    r = compare_topk(cd_ref, k_ref, cd, k, rtol=1e-4, atol=1e-4)
+    assert r["n_id_mismatch_unexplained"] == 0, r
+    assert r["max_rel_err"] <= 1e-4, r
+    assert np.all(np.diff(cd, axis=1) >= 0)  # ascending coarse distance
+
+
+@pytest.mark.parametrize("fx,metric", [(fx_l2_m32, "L2"), (fx_l2_m16, "L2"), (fx_ip_m32, "InnerProduct")])
+def test_adc_scan_preassigned_no_rank(fx, metric):
+    """ADC scan + recall selection in isolation: probes taken from the reference's own coarse stage
+    (search_preassigned), has_rank off so returned distances are the ADC sums."""
+    f = fx()
+    ix = f.mirror()
+    nprobe, R = 12, 50
+    cd_ref, k_ref = f.ref.coarse(f.xq, nprobe)
+    D_ref, I_ref = f.ref.search(f.xq, R, rj(nprobe, R, metric), has_rank=False, keys=k_ref, coarse_dis=cd_ref)
+    rc, D, I = ix.Search(f.xq, R, nprobe=nprobe, recall_num=R, metric=metric, has_rank=False, keys=k_ref,
+                         coarse_dis=cd_ref)
+    assert rc == 0
+    r = assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
+    assert ix.last_scanned_postings() > 0
+
+
+@pytest.mark.parametrize("fx,metric", [(fx_l2_m32, "L2"), (fx_l2_m16, "L2"), (fx_ip_m32, "InnerProduct")])
+def test_full_search_with_rerank(fx, metric):
+    f = fx()
+    ix = f.mirror()
+    nprobe, R, k = 16, 100, 10
+    D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, metric), has_rank=True)
+    rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric=metric, has_rank=True)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+    same = I_ref == I
+    # exact re-rank reproduces the AVX summation order: bit-identical distances where ids agree
+    assert np.array_equal(D_ref[same], D[same])
+    assert same.mean() > 0.995
+
+
+def test_filters_and_deletions_inside_the_scan():
+    from gamma_b200 import synth
+    f = fx_l2_m32()
+    ix = f.mirror()
+    N = f.N
+    field = synth.filter_field(N)
+    pass_flags = (field < 30).astype(np.uint8)
+    dele = synth.deleted_docs(N, 0.01)
+    for doc in dele:
+        f.ref.delete(int(doc))
+    try:
+        ix.set_deleted(dele, True)
+        filt = [(0, N - 1, False, pass_flags)]
+        nprobe, R, k = 16, 100, 10
+        D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, "L2"), has_rank=True, filters=filt)
+        rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=True, filters=filt)
+        assert rc == 0
+        got = I[I >= 0]
+        assert np.all(pass_flags[got] == 1) and not np.isin(got, dele).any()
+        assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+        # a second, partial-range NOT-IN filter on top (b_not_in_ and min/max clipping semantics)
+        lo, hi = 1003, N // 2 + 5
+        flags2 = (np.arange(lo, hi + 1) % 3 == 0).astype(np.uint8)
+        filt2 = filt + [(lo, hi, True, flags2)]
+        D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, "L2"), has_rank=False, filters=filt2)
+        rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=False, filters=filt2)
+        assert rc == 0
+        assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
+        # deletions only (no range filter)
+        D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, "L2"), has_rank=True)
+        rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=True)
+        assert not np.isin(I[I >= 0], dele).any()
+        assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+    finally:
+        pass  # fixture is cached with the deletions applied; later tests re-apply the same set
+
+
+def test_score_window_and_unfilled_slots():
+    f = fx_l2_m16()
+    ix = f.mirror()
+    nprobe, R, k = 8, 40, 20
+    D0, _ = f.ref.search(f.xq, k, rj(nprobe, R, "L2"), has_rank=True)
+    lo, hi = float(np.percentile(D0[:, 0], 50)), float(np.percentile(D0[:, 5], 50))
+    for has_rank in (True, False):
+        D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, "L2"), has_rank=has_rank, min_score=lo, max_score=hi)
+        rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=has_rank, min_score=lo,
+                             max_score=hi)
+        assert rc == 0
+        assert (I == -1).any()  # the window leaves unfilled slots
+        filled = I >= 0
+        assert np.array_equal(filled, I_ref >= 0) or compare_topk(D_ref, I_ref, D, I)["n_id_mismatch_unexplained"] == 0
+        assert np.all(D[~filled] == FLT_MAX)  # heap neutral value for L2
+        assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4 if not has_rank else 1e-6, atol=1e-5 if not has_rank else 0.0)
+
+
+def test_k_larger_than_recall_and_few_candidates():
+    f = fx_l2_m16()
+    ix = f.mirror()
+    # recall_num < k  => recall_num = k (gamma_index_ivfpq.cc:762-765); nprobe=1 => fewer than k candidates for some
+    D_ref, I_ref = f.ref.search(f.xq, 64, rj(1, 10, "L2"), has_rank=True)
+    rc, D, I = ix.Search(f.xq, 64, nprobe=1, recall_num=10, metric="L2", has_rank=True)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+
+
+def test_error_codes_match_reference_convention():
+    f = fx_l2_m16()
+    ix = f.mirror(raw=False)
+    rc, _, _ = ix.Search(f.xq, 10, nprobe=4, recall_num=20, has_rank=True)  # has_rank without raw vectors
+    assert rc < 0
+    from gamma_b200 import api
+    fresh = api.B200IVFPQ(0)
+    assert fresh.Init(f.model_json, f.d) == 0
+    rc, _, _ = fresh.Search(f.xq, 10)
+    assert rc == -2  # untrained: reference GammaEngine::Search returns -2 when not indexed
+
+
+def test_realtime_append_and_update_visible_to_next_search():
+    """Postings appended after a search are seen by the next one (RTInvertIndex::AddKeys semantics);
+    Update to another list kills the old posting (kDelIdxMask) and appends the new one."""
+    f = fx_l2_m16()
+    from gamma_b200 import api
+    ix = api.B200IVFPQ(0)
+    assert ix.Init(f.model_json, f.d) == 0
+    ix.set_quantizers(f.centroids, f.pq)
+    list_no = np.concatenate([np.full(len(ids), l, np.int32) for l, (ids, _) in enumerate(f.lists)])
+    vids = np.concatenate([ids for ids, _ in f.lists])
+    codes = np.concatenate([c for _, c in f.lists])
+    order = np.argsort(vids, kind="stable")
+    list_no, vids, codes = list_no[order], vids[order], codes[order]
+    half = f.N // 2
+    ix.upload_raw(f.xb)
+    # chunks of 1000 like AddRTVecsToIndex (vector_manager.cc:280-382)
+    for s in range(0, half, 1000):
+        assert ix.append(list_no[s:s + 1000], vids[s:s + 1000], codes[s:s + 1000]) == 0
+    rc, D1, I1 = ix.Search(f.xq, 10, nprobe=8, recall_num=50, metric="L2", has_rank=True)
+    assert rc == 0 and I1.max() < half
+    for s in range(half, f.N, 1000):
+        assert ix.append(list_no[s:s + 1000], vids[s:s + 1000], codes[s:s + 1000]) == 0
+    D_ref, I_ref = f.ref.search(f.xq, 10, rj(8, 50, "L2"), has_rank=True)
+    rc, D2, I2 = ix.Search(f.xq, 10, nprobe=8, recall_num=50, metric="L2", has_rank=True)
+    assert_topk_parity(D_ref, I_ref, D2, I2, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+    for l in [0, f.nlist - 1]:
+        ids, cds = ix.get_list(l)
+        assert np.array_equal(ids, f.lists[l][0]) and np.array_equal(cds, f.lists[l][1])
+    # Update: move vid v to another list with a new code
+    v = int(I2[0, 0])
+    old_list = int(list_no[np.nonzero(vids == v)[0][0]])
+    new_list = (old_list + 1) % f.nlist
+    new_code = codes[np.nonzero(vids == v)[0][0]].copy()
+    assert ix.update(v, new_list, new_code) == 0
+    ids_old, _ = ix.get_list(old_list)
+    dead = ids_old[(ids_old & 0x7fffffff) == v]
+    assert dead.size == 1 and dead[0] < 0  # kDelIdxMask bit set
+    ids_new, codes_new = ix.get_list(new_list)
+    assert ids_new[-1] == v and np.array_equal(codes_new[-1], new_code)
