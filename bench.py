@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric on B200.
+
+metric  : QPS @ recall@10 (d=128, 10M vecs, nprobe=32, batch=1024) — BASELINE.json
+workload: IVFPQ d=128 nlist=16384 PQ32x8, 10M synthetic vectors, nprobe=32, recall_num=100,
+          exact re-rank on, k=10, L2 (SURVEY.md §8d "headline shape").  `--workload c3` = PQ64x8 +
+          range-filter bitmap + 1 % deletions, `--workload c2` = 1M/nlist 4096/nprobe 16/batch 256.
+step    : one Search of one batch (coarse quantiser + ADC scan + select + re-rank + top-k).
+value   : device-timed (CUDA events), queries resident in HBM, L2 flushed between steps.
+e2e     : the same Search through the public host C-ABI call with pinned HOST buffers
+          (H2D of the queries and D2H of the results inside the timed region).
+roofline: ADC scan kernel, algorithmic bytes = scanned postings x (code_size + 4)  (SURVEY §8d).
+cpu_baseline / --impl reference: the reference's own CPU engine (oracle/_ref = unmodified
+          GammaIVFPQIndex over faiss 1.7.1, compiled by oracle/Makefile) searching the SAME index on
+          the host cores, on a bounded sample of the batch.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torch.distributed.run
+(one rank per GPU, index replicated, queries sharded: every rank searches its own batch, then an
+NCCL all-gather of the per-rank top-k — weak scaling, global batch = N x 1024).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, d, nlist, M, nprobe, batch, filter
+    "headline": dict(N=10_000_000, d=128, nlist=16384, M=32, nprobe=32, batch=1024, filt=False,
+                     desc="IVFPQ d=128 nlist=16384 PQ32x8 10M vecs nprobe=32 batch=1024 recall_num=100 rerank k=10 L2"),
+    "c3": dict(N=10_000_000, d=128, nlist=16384, M=64, nprobe=32, batch=1024, filt=True,
+               desc="IVFPQ d=128 nlist=16384 PQ64x8 10M vecs nprobe=32 batch=1024 + range-filter bitmap (30% pass) + 1% deleted"),
+    "c2": dict(N=1_000_000, d=128, nlist=4096, M=32, nprobe=16, batch=256, filt=False,
+               desc="IVFPQ d=128 nlist=4096 PQ32x8 1M vecs nprobe=16 batch=256"),
+}
+K_TOP, RECALL_NUM = 10, 100
+METRIC = "QPS @ recall@10 (d=128, 10M vecs, nprobe=32, batch=1024)"
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_dataset(w, scale):
+    from gamma_b200 import synth
+    N = max(int(w["N"] * scale), 50 * 256)
+    nlist = w["nlist"] if scale == 1.0 else max(64, int(w["nlist"] * scale))
+    t = time.time()
+    xb = synth.base_vectors(N, w["d"])
+    xq_all = synth.query_vectors(w["batch"] * 8, w["d"])
+    log("synthetic data N=%d d=%d in %.1fs" % (N, w["d"], time.time() - t))
+    return N, nlist, xb, xq_all
+
+
+def build_index_state(w, N, nlist, xb, device, dist_ctx):
+    """rank 0 trains + encodes on its GPU (torch, setup only), other ranks receive the result."""
+    import torch
+    from gamma_b200 import builder
+    rank, world = dist_ctx
+    M, d = w["M"], w["d"]
+    if rank == 0:
+        t = time.time()
+        coarse, pq, list_no, codes = builder.build_ivfpq(xb, nlist, M, device=device)
+        log("trained + encoded in %.1fs" % (time.time() - t))
+    if world > 1:
+        import torch.distributed as dist
+        dev = torch.device(device)
+        tc = torch.from_numpy(coarse).to(dev) if rank == 0 else torch.empty(nlist, d, device=dev)
+        tp = torch.from_numpy(pq).to(dev) if rank == 0 else torch.empty(M, 256, d // M, device=dev)
+        tl = torch.from_numpy(list_no).to(dev) if rank == 0 else torch.empty(N, dtype=torch.int32, device=dev)
+        tcd = torch.from_numpy(codes).to(dev) if rank == 0 else torch.empty(N, M, dtype=torch.uint8, device=dev)
+        for t_ in (tc, tp, tl, tcd):
+            dist.broadcast(t_, 0)
+        coarse, pq, list_no, codes = tc.cpu().numpy(), tp.cpu().numpy(), tl.cpu().numpy(), tcd.cpu().numpy()
+    return coarse, pq, list_no, codes
+
+
+def make_filter(w, N):
+    from gamma_b200 import synth
+    if not w["filt"]:
+        return [], None
+    flags = (synth.filter_field(N) < 30).astype(np.uint8)
+    dele = synth.deleted_docs(N, 0.01)
+    return [(0, N - 1, False, flags)], dele
+
+
+def ground_truth(xb_t, xq_t, k, valid_mask_t=None, chunk=1 << 20):
+    import torch
+    n = xq_t.shape[0]
+    best_d = torch.full((n, k), float("inf"), device=xq_t.device)
+    best_i = torch.full((n, k), -1, dtype=torch.int64, device=xq_t.device)
+    qn = (xq_t * xq_t).sum(1, keepdim=True)
+    for s in range(0, xb_t.shape[0], chunk):
+        xs = xb_t[s:s + chunk]
+        dist = qn + (xs * xs).sum(1)[None, :] - 2.0 * (xq_t @ xs.t())
+        if valid_mask_t is not None:
+            dist = dist.masked_fill(~valid_mask_t[s:s + chunk][None, :], float("inf"))
+        d, i = dist.topk(k, dim=1, largest=False)
+        cat_d = torch.cat([best_d, d], 1)
+        cat_i = torch.cat([best_i, i + s], 1)
+        sel = cat_d.topk(k, dim=1, largest=False)
+        best_d, best_i = sel.values, torch.gather(cat_i, 1, sel.indices)
+    return best_i
+
+
+def recall_at_k(I, gt):
+    hit = 0
+    for a, b in zip(I, gt):
+        hit += len(set(int(x) for x in a if x >= 0) & set(int(x) for x in b))
+    return hit / float(gt.shape[0] * gt.shape[1])
+
+
+def build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele):
+    from oracle import ref
+    t = time.time()
+    model_json = json.dumps({"ncentroids": nlist, "nsubvector": w["M"], "metric_type": "L2", "nprobe": w["nprobe"]})
+    wd = tempfile.mkdtemp(prefix="oref_bench_")
+    r = ref.RefIndex(w["d"], "IVFPQ", model_json, indexing_size=N, bitmap_bits=max(2 * N, 1024), work_dir=wd)
+    r._own_dir = True
+    for s in range(0, N, 1 << 20):
+        r.add_raw(xb[s:s + (1 << 20)])
+    r.set_trained(coarse, pq)
+    r.inject_postings(list_no, np.arange(N, dtype=np.int64), codes)
+    if dele is not None:
+        for doc in dele:
+            r.delete(int(doc))
+    log("reference CPU engine loaded with the same index in %.1fs" % (time.time() - t))
+    return r
+
+
+def time_reference(r, w, xq, filters, n_queries, reps, warm=1):
+    from oracle import ref
+    cores = ref.max_threads()
+    rj = json.dumps({"nprobe": w["nprobe"], "recall_num": RECALL_NUM, "metric_type": "L2", "parallel_on_queries": 1})
+    q = xq[:n_queries]
+    times = []
+    I = None
+    for it in range(warm + reps):
+        t = time.perf_counter()
+        D, I = r.search(q, K_TOP, rj, has_rank=True, filters=filters)
+        dt = time.perf_counter() - t
+        if it >= warm:
+            times.append(dt)
+    return n_queries / float(np.median(times)), cores, times, I
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="dev only: shrink N and nlist (result not valid)")
+    ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample of the batch for the CPU engine")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # rank 0 alone runs and prints the reference arm
+
+    import torch
+    have_gpu = torch.cuda.is_available()
+    if args.impl == "ours" and not have_gpu:
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    device = "cuda:%d" % local if have_gpu else "cpu"
+    if have_gpu:
+        torch.cuda.set_device(local)
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    N, nlist, xb, xq_all = build_dataset(w, args.scale)
+    dist_ctx = (rank, world) if args.impl == "ours" else (0, 1)
+    coarse, pq, list_no, codes = build_index_state(w, N, nlist, xb, device, dist_ctx)
+    filters, dele = make_filter(w, N)
+    n = w["batch"]
+    # every rank gets its own batch of fresh queries (weak scaling); rank r uses slice r
+    xq = np.ascontiguousarray(xq_all[(rank % 8) * n:(rank % 8 + 1) * n])
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        r = build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele)
+        nq = min(args.cpu_queries, n)
+        qps_list = []
+        from oracle import ref
+        cores = ref.max_threads()
+        rj = json.dumps({"nprobe": w["nprobe"], "recall_num": RECALL_NUM, "metric_type": "L2", "parallel_on_queries": 1})
+        for it in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            r.search(xq[:nq], K_TOP, rj, has_rank=True, filters=filters)
+            dt = time.perf_counter() - t
+            if it >= args.warmup:
+                qps_list.append(dt)
+        ms = 1e3 * float(np.mean(qps_list))
+        val = nq / (ms / 1e3)
+        out = dict(metric=METRIC, value=val, unit="queries/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                   data="synthetic", impl="reference",
+                   config=dict(workload=w["desc"], N=N, nlist=nlist, queries_per_step=nq, scaled_down=args.scale != 1.0),
+                   cpu_baseline=dict(value=val, unit="queries/s", cores=cores, kind="reference",
+                                     sample="%d of the %d-query batch per step, %d steps, OpenMP over queries" % (nq, n, args.steps)),
+                   e2e=dict(value=val, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(out), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    from gamma_b200 import api
+    t = time.time()
+    model_json = json.dumps({"ncentroids": nlist, "nsubvector": w["M"], "metric_type": "L2", "nprobe": w["nprobe"]})
+    ix = api.B200IVFPQ(local)
+    rc = ix.Init(model_json, w["d"])
+    if rc != 0:
+        raise SystemExit("gb200 create failed: %s" % api.lib().gb200_last_error().decode())
+    ix.set_quantizers(coarse, pq)
+    rc = ix.append(list_no, np.arange(N, dtype=np.int64), codes)
+    assert rc == 0, api.lib().gb200_last_error()
+    for s in range(0, N, 1 << 21):
+        ix.upload_raw(xb[s:s + (1 << 21)], first_vid=s)
+    if dele is not None:
+        ix.set_deleted(dele, True)
+    if filters:
+        ix.set_filters(filters)
+    log("device mirror built in %.1fs, %.2f GB" % (time.time() - t, ix.GetTotalMemBytes() / 1e9))
+
+    dev = torch.device(device)
+    xq_d = torch.from_numpy(xq).to(dev)
+    D_d = torch.empty(n, K_TOP, dtype=torch.float32, device=dev)
+    I_d = torch.empty(n, K_TOP, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        import torch.distributed as dist
+        D_all = torch.empty(world * n, K_TOP, dtype=torch.float32, device=dev)
+        I_all = torch.empty(world * n, K_TOP, dtype=torch.int64, device=dev)
+
+    def step_dev():
+        rc_ = ix.search_dev(xq_d.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
+                            nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
+        assert rc_ == 0, api.lib().gb200_last_error()
+        if world > 1:
+            dist.all_gather_into_tensor(D_all, D_d)
+            dist.all_gather_into_tensor(I_all, I_d)
+
+    # correctness side: recall@10 vs exact ground truth (and the raw result for the CPU cross-check)
+    step_dev()
+    torch.cuda.synchronize()
+    I_ours = I_d.cpu().numpy().copy()
+    valid_mask = None
+    if filters:
+        vm = filters[0][3].astype(bool).copy()
+        vm[dele] = False
+        valid_mask = torch.from_numpy(vm).to(dev)
+    xb_t = torch.from_numpy(xb[: min(N, 10_000_000)]).to(dev) if N <= 12_000_000 else None
+    rec_ours = None
+    if xb_t is not None:
+        gt = ground_truth(xb_t, xq_d, K_TOP, valid_mask).cpu().numpy()
+        rec_ours = recall_at_k(I_ours, gt)
+        del xb_t
+        torch.cuda.empty_cache()
+    log("recall@10 (ours) = %s" % rec_ours)
+
+    # ---- device-timed region: per-step CUDA events, L2 flushed between steps (untimed)
+    ix.set_profiling(True)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step_dev()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ix.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    scan_ms, stage_acc = [], dict(coarse=0.0, scan=0.0, rerank=0.0, total=0.0)
+    scanned = 0
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        evs[i][0].record(stream)
+        step_dev()
+        evs[i][1].record(stream)
+        ix.sync()  # host sync so the per-stage event times of this step can be read
+        st = ix.last_stage_ms()
+        scan_ms.append(st["scan"])
+        for k_ in stage_acc:
+            stage_acc[k_] += st[k_] / args.steps
+        scanned = ix.last_scanned_postings()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = ix.launch_count() - launches0
+    if world > 1:
+        launches += 2 * args.steps  # the two NCCL all-gathers per step
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * args.steps / (total_ms / 1e3)
+
+    # back-to-back, no flush (informational)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_noflush = e0.elapsed_time(e1) / args.steps
+
+    # ---- e2e: public host call, pinned host buffers, H2D + D2H inside the timed region
+    xq_pin = torch.from_numpy(xq).pin_memory()
+    D_pin = torch.empty(n, K_TOP, dtype=torch.float32).pin_memory()
+    I_pin = torch.empty(n, K_TOP, dtype=torch.int64).pin_memory()
+    sp = api._Base._sp("L2", w["nprobe"], RECALL_NUM, True, -api.FLT_MAX, api.FLT_MAX)
+    farr, fkeep = api.make_filters(filters)
+
+    def step_host():
+        rc_ = api.lib().gb200_ivfpq_search(ix.h, n, xq_pin.data_ptr(), K_TOP, ctypes.byref(sp),
+                                           ctypes.cast(farr, ctypes.c_void_p), len(filters), D_pin.data_ptr(),
+                                           I_pin.data_ptr())
+        assert rc_ == 0, api.lib().gb200_last_error()
+
+    for _ in range(args.warmup):
+        step_host()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = world * n * args.steps / float(te.item())
+    assert np.array_equal(I_pin.numpy(), I_ours), "host-API result differs from device-API result"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (ADC scan)
+    peak, peak_src = measured_peaks()
+    code_size = w["M"]
+    alg_bytes = scanned * (code_size + 4)
+    scan_avg_ms = float(np.mean(scan_ms))
+    achieved = alg_bytes / (scan_avg_ms / 1e3) / 1e9
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    kernel="ivfpq_scan_kernel", algorithmic_bytes_per_launch=alg_bytes,
+                    scanned_postings_per_launch=scanned, kernel_ms=scan_avg_ms, peak_source=peak_src,
+                    stage_ms=stage_acc)
+    tr = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- CPU baseline: reference engine, same index, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele)
+            nq = min(args.cpu_queries, n)
+            qps, cores, times, I_cpu = time_reference(r, w, xq, filters, nq, reps=3)
+            agree = float((I_cpu == I_ours[:nq]).mean())
+            cpu = dict(value=qps, unit="queries/s", cores=cores, kind="reference",
+                       sample="first %d queries of the batch, median of 3 runs after 1 warm-up, parallel_on_queries=1" % nq,
+                       ids_identical_frac=agree)
+            if rec_ours is not None:
+                cpu["recall_at_10"] = recall_at_k(I_cpu, gt[:nq])
+            r.close()
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            cpu = dict(value=None, unit="queries/s", cores=None, kind="reference", sample="failed: %r" % (e,))
+
+    out = dict(metric=METRIC, value=value, unit="queries/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+               data="synthetic",
+               config=dict(workload=w["desc"], N=N, nlist=nlist, M=w["M"], nprobe=w["nprobe"], batch_per_gpu=n,
+                           global_batch=world * n, k=K_TOP, recall_num=RECALL_NUM, has_rank=True,
+                           parallelism="query-sharded x%d, index replicated, NCCL all-gather of top-k" % world,
+                           l2="256 MB flush write between steps (untimed); per-step CUDA events",
+                           ms_per_step_back_to_back_no_flush=ms_noflush, scaled_down=args.scale != 1.0),
+               roofline=roofline, cpu_baseline=cpu,
+               e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * w["d"] * 4),
+                        d2h_bytes_per_step=int(n * K_TOP * 12)),
+               gpu_launches=int(launches), clocks=clocks, recall_at_10=rec_ours)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,8 +25,16 @@ def available():
 def lib():
     global _lib
     if _lib is None:
-        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")  # BLAS inside OpenMP oversubscribes
+        # BLAS threads inside OpenMP regions oversubscribe (10x slowdown on 8 cores,
+        # a stall on the 128-core GPU host); idle OpenMP workers must sleep, not spin.
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+        os.environ.setdefault("GOMP_SPINCOUNT", "0")
         _lib = C.CDLL(LIB_PATH)
+        try:
+            _lib.openblas_set_num_threads(1)
+        except AttributeError:
+            pass
         _lib.oref_open.restype = C.c_void_p
         _lib.oref_open.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_long]
         _lib.oref_close.argtypes = [C.c_void_p]
@@ -43,6 +51,8 @@ def lib():
         _lib.oref_list_size.argtypes = [C.c_void_p, C.c_long]
         _lib.oref_get_list.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
         _lib.oref_coarse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oref_set_trained.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oref_inject_postings.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oref_search.argtypes = [
             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_float, C.c_float,
             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -88,8 +98,27 @@ class RefIndex:
         rc = lib().oref_add_raw(self.h, x.shape[0], x.ctypes.data)
         assert rc == 0, rc
 
-    def indexing(self):
-        rc = lib().oref_indexing(self.h)
+    def indexing(self, threads=16):
+        """train; k-means on small data degrades badly with >100 OpenMP threads, so cap them here"""
+        prev = max_threads()
+        set_threads(min(prev, threads))
+        try:
+            rc = lib().oref_indexing(self.h)
+        finally:
+            set_threads(prev)
+        assert rc == 0, rc
+
+    def set_trained(self, coarse, pq):
+        coarse = np.ascontiguousarray(coarse, dtype=np.float32)
+        pq = np.ascontiguousarray(pq, dtype=np.float32)
+        rc = lib().oref_set_trained(self.h, coarse.ctypes.data, pq.ctypes.data)
+        assert rc == 0, rc
+
+    def inject_postings(self, list_no, vids, codes):
+        ln = np.ascontiguousarray(list_no, dtype=np.int32)
+        v = np.ascontiguousarray(vids, dtype=np.int64)
+        c = np.ascontiguousarray(codes, dtype=np.uint8)
+        rc = lib().oref_inject_postings(self.h, ln.size, ln.ctypes.data, v.ctypes.data, c.ctypes.data)
         assert rc == 0, rc
 
     def add_to_index(self, upto=-1, chunk=10000):

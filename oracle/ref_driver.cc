@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -225,6 +226,50 @@ int oref_get_list(void *h, long list_no, int64_t *ids, uint8_t *codes) {
 int oref_coarse(void *h, int n, const float *xq, int nprobe, float *cdis, int64_t *keys) {
   OracleRef *o = (OracleRef *)h;
   o->ivfpq->quantizer->search(n, xq, nprobe, cdis, (faiss::Index::idx_t *)keys);
+  return 0;
+}
+
+// Install an externally trained state, leaving the index exactly as GammaIVFPQIndex::Load does
+// (gamma_index_ivfpq.cc:993-1048): quantizer holds the nlist centroids, pq.centroids set,
+// is_trained, precomputed table recomputed (use_precomputed_table = 0; precompute_table()).
+// Lets the bench give the reference CPU engine the SAME index the GPU path searches.
+int oref_set_trained(void *h, const float *coarse, const float *pq) {
+  OracleRef *o = (OracleRef *)h;
+  GammaIVFPQIndex *ix = o->ivfpq;
+  if (!ix) return -1;
+  ix->quantizer->reset();
+  ix->quantizer->add(ix->nlist, coarse);
+  ix->quantizer->is_trained = true;
+  memcpy(ix->pq.centroids.data(), pq, sizeof(float) * ix->pq.centroids.size());
+  ix->is_trained = true;
+  ix->use_precomputed_table = 0;
+  if (ix->by_residual) ix->precompute_table();
+  return 0;
+}
+
+// Postings straight into the realtime inverted lists: the second half of GammaIVFPQIndex::Add
+// (gamma_index_ivfpq.cc:474-500) with the codes given instead of computed.  Postings must come in
+// vid order so that list order equals the engine's.
+int oref_inject_postings(void *h, long n, const int *list_no, const int64_t *vids, const uint8_t *codes) {
+  OracleRef *o = (OracleRef *)h;
+  GammaIVFPQIndex *ix = o->ivfpq;
+  if (!ix) return -1;
+  const size_t cs = ix->code_size;
+  const long CH = 100000;
+  for (long s = 0; s < n; s += CH) {
+    long e = s + CH < n ? s + CH : n;
+    std::map<int, std::vector<long>> new_keys;
+    std::map<int, std::vector<uint8_t>> new_codes;
+    for (long i = s; i < e; i++) {
+      int key = list_no[i];
+      new_keys[key].push_back((long)vids[i]);
+      std::vector<uint8_t> &c = new_codes[key];
+      c.insert(c.end(), codes + i * cs, codes + (i + 1) * cs);
+    }
+    if (!ix->rt_invert_index_ptr_->AddKeys(new_keys, new_codes)) return -2;
+  }
+  ix->indexed_vec_count_ += (int)n;
+  o->model->indexed_count_ += (int)n;
   return 0;
 }
 
