@@ -26,6 +26,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// dynamic shared memory at file scope so PTX can name it: its shared-window address is a link-time
+// constant that ptxas folds into the LDS immediate (no per-lookup base add).
+extern __shared__ __align__(16) unsigned char gb_scan_smem[];
+
 namespace gb {
 
 constexpr int SCAN_THREADS = 256;
@@ -66,35 +70,42 @@ __device__ __forceinline__ float adc_generic(const float *lut, const uint8_t *co
   return acc;
 }
 
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
+template <int IMM>
+__device__ __forceinline__ float lds_lut(uint32_t off) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  // address = gb_scan_smem (constant) + off + IMM ; the table is the first thing in dynamic smem
+  asm("{\n\t.reg .u32 a;\n\tmov.u32 a, gb_scan_smem;\n\tadd.u32 a, a, %1;\n\tld.shared.f32 %0, [a+%2];\n\t}"
+      : "=f"(v)
+      : "r"(off), "n"(IMM));
   return v;
 }
 
 // M = 32 conflict-free ADC (see header comment).  lut_lane = shared byte address of the table
 // + lane*4 folded into the PRMT operand; w[0..7] = the posting's 32 pre-rotated code bytes.
-__device__ __forceinline__ float adc_m32(uint32_t lut_saddr, uint32_t lane4, const uint32_t (&w)[8]) {
+template <int S>
+__device__ __forceinline__ void adc_m32_word(uint32_t word, uint32_t lane4, float &a0, float &a1, float &a2, float &a3) {
+  // (code_byte << 8) | lane4 : selector nibbles [3]=5 (zero) [2]=5 (zero) [1]=byte j [0]=4 (lane4)
+  a0 += lds_lut<4 * (S + 0)>(__byte_perm(word, lane4, 0x5504));
+  a1 += lds_lut<4 * (S + 1)>(__byte_perm(word, lane4, 0x5514));
+  a2 += lds_lut<4 * (S + 2)>(__byte_perm(word, lane4, 0x5524));
+  a3 += lds_lut<4 * (S + 3)>(__byte_perm(word, lane4, 0x5534));
+}
+__device__ __forceinline__ float adc_m32(uint32_t lane4, const uint32_t (&w)[8]) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-  for (int s = 0; s < 32; s += 4) {
-    uint32_t word = w[s >> 2];
-    // (code_byte << 8) | lane4 : selector nibbles [3]=5 (zero) [2]=5 (zero) [1]=byte j [0]=4 (lane4)
-    uint32_t o0 = __byte_perm(word, lane4, 0x5504);
-    uint32_t o1 = __byte_perm(word, lane4, 0x5514);
-    uint32_t o2 = __byte_perm(word, lane4, 0x5524);
-    uint32_t o3 = __byte_perm(word, lane4, 0x5534);
-    a0 += lds_f32(lut_saddr + o0 + 4 * (s + 0));
-    a1 += lds_f32(lut_saddr + o1 + 4 * (s + 1));
-    a2 += lds_f32(lut_saddr + o2 + 4 * (s + 2));
-    a3 += lds_f32(lut_saddr + o3 + 4 * (s + 3));
-  }
+  adc_m32_word<0>(w[0], lane4, a0, a1, a2, a3);
+  adc_m32_word<4>(w[1], lane4, a0, a1, a2, a3);
+  adc_m32_word<8>(w[2], lane4, a0, a1, a2, a3);
+  adc_m32_word<12>(w[3], lane4, a0, a1, a2, a3);
+  adc_m32_word<16>(w[4], lane4, a0, a1, a2, a3);
+  adc_m32_word<20>(w[5], lane4, a0, a1, a2, a3);
+  adc_m32_word<24>(w[6], lane4, a0, a1, a2, a3);
+  adc_m32_word<28>(w[7], lane4, a0, a1, a2, a3);
   return (a0 + a1) + (a2 + a3);
 }
 
 template <bool IP, int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char *smem = gb_scan_smem;
   const int q = blockIdx.y;
   const int split = blockIdx.x;
   const int tid = threadIdx.x;
@@ -203,7 +214,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) 
 
   const int total_blocks = blk_prefix[np_s];
   const int rounds = (total_blocks + SCAN_WARPS * SCAN_U - 1) / (SCAN_WARPS * SCAN_U);
-  const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(lut);
   const uint32_t lane4 = lane * 4;
   const int prune_limit = P.cap - SCAN_ROUND_POSTINGS;
   int cur = 0;  // probe cursor (monotone per warp)
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) 
           ok = ok && id >= 0;
           if (ok && P.valid) ok = bitmap_test(P.valid, id);
           uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          dis += adc_m32(lut_saddr, lane4, w);
+          dis += adc_m32(lane4, w);
         } else {
           if (ok) id = ldg_nc_s32(P.ids + pidx);
           ok = ok && id >= 0;
