@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="dev only: shrink N and nlist (result not valid)")
     ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample of the batch for the CPU engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variants", default="", help="dev only: ';'-separated ENV=VAL[,ENV=VAL] sets to time after the main run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -384,6 +385,30 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     ms_noflush = e0.elapsed_time(e1) / args.steps
+
+    # ---- dev: tuning-knob sweep (stderr only, never part of the JSON line)
+    for var in [v for v in args.variants.split(";") if v]:
+        kv = dict(x.split("=") for x in var.split(","))
+        for k_, v_ in kv.items():
+            os.environ[k_] = v_
+        for _ in range(3):
+            step_dev()
+        torch.cuda.synchronize()
+        sc = []
+        t_ev = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            step_dev()
+            b_.record(stream)
+            ix.sync()
+            sc.append(ix.last_stage_ms()["scan"])
+            t_ev.append(a_.elapsed_time(b_))
+        ok_ = bool(np.array_equal(I_d.cpu().numpy(), I_ours))
+        log("variant %s: ms/step %.4f scan %.4f same_ids=%s" % (var, float(np.mean(t_ev)), float(np.mean(sc)), ok_))
+        for k_ in kv:
+            os.environ.pop(k_, None)
 
     # ---- e2e: public host call, pinned host buffers, H2D + D2H inside the timed region
     xq_pin = torch.from_numpy(xq).pin_memory()

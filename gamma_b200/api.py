@@ -45,6 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_sync",
+    "gb200_debug_select",
 ]
 
 
@@ -91,8 +92,22 @@ def lib():
         L.gb200_last_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.gb200_sync.argtypes = [C.c_void_p]
+        L.gb200_debug_select.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p]
         _lib = L
     return _lib
+
+
+def debug_select(keys, R, cap, batch, threads=256, device=0):
+    """test hook: the R smallest of `keys` (u64) through the kernels' streaming selection primitive"""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.empty(R, np.uint64)
+    n_out = C.c_int(0)
+    rc = lib().gb200_debug_select(device, keys.ctypes.data, keys.size, R, cap, batch, threads, out.ctypes.data,
+                                  C.byref(n_out))
+    if rc != 0:
+        raise RuntimeError("gb200_debug_select rc=%d %s" % (rc, lib().gb200_last_error().decode()))
+    return out[:n_out.value]
 
 
 class GammaB200Error(RuntimeError):

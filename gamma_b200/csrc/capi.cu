@@ -105,8 +105,9 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut;
   unsigned long long *d_scanned = nullptr;
+  unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
   bool profiling = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -224,7 +225,7 @@ int gb200_destroy(gb200_index *ix) {
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 4; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
@@ -677,6 +678,7 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   }
   // splits: enough CTAs for ~2 waves of 148 SMs x 3 resident CTAs, merge buffer <= 8192 keys
   int S = (148 * 3 * 2 + n - 1) / n;
+  if (const char *es = getenv("GB200_SCAN_SPLITS")) S = atoi(es);  // tuning knob
   S = std::max(1, std::min(S, nprobe));
   while (S > 1 && (long long)S * R > 8192) S--;
   ScanParams P;
@@ -694,6 +696,16 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   CKI(ix->ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
   P.cand = ix->ws_cand.as<u64>();
   P.scanned = ix->d_scanned;
+  P.timing = nullptr;
+  if (const char *tm = getenv("GB200_SCAN_TIMING")) {
+    if (tm[0] == '1') {
+      if (!ix->d_timing) {
+        CK(cudaMalloc(&ix->d_timing, 8 * sizeof(unsigned long long)));
+      }
+      CK(cudaMemsetAsync(ix->d_timing, 0, 8 * sizeof(unsigned long long), ix->stream));
+      P.timing = ix->d_timing;
+    }
+  }
   P.n = n;
   P.d = ix->p.d;
   P.M = M;
@@ -706,12 +718,31 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   P.chunk = ix->chunk;
   P.max_np_s = (nprobe + S - 1) / S;
   P.is_ip = ip ? 1 : 0;
+  {
+    const char *fs = getenv("GB200_SCAN_FORCE_SYM");
+    P.force_sym = (fs && fs[0] == '1') ? 1 : 0;
+    const char *nt = getenv("GB200_SCAN_NO_TMA");
+    P.no_tma = (nt && nt[0] == '1') ? 1 : 0;
+    const char *th = getenv("GB200_SCAN_THREADS");
+    P.m32_threads = th ? atoi(th) : 256;
+  }
   if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d): not implemented", scan_smem_bytes(P, ix->mode), M, R);
     return GB200_EUNSUPPORTED;
   }
   CK(cudaMemsetAsync(ix->d_scanned, 0, sizeof(unsigned long long), ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
+  P.lut_g = nullptr;
+  if (ix->mode == 1) {
+    if (ix->p.d > 1024) {
+      set_err("M=32 kernel: d=%d > 1024 not implemented", ix->p.d);
+      return GB200_EUNSUPPORTED;
+    }
+    CKI(ix->ws_lut.ensure((size_t)n * 65536));
+    CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
+    ix->launches++;
+    P.lut_g = ix->ws_lut.as<float>();
+  }
   CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));
   RerankParams Q;
@@ -743,6 +774,16 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
 
 static int finish_profile(gb200_index *ix) {
   unsigned long long sc = 0;
+  if (ix->d_timing && getenv("GB200_SCAN_TIMING")) {
+    unsigned long long t[8];
+    CK(cudaMemcpyAsync(t, ix->d_timing, sizeof(t), cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    double n = t[7] ? (double)t[7] : 1.0;
+    fprintf(stderr,
+            "[gb200 scan timing] ctas %llu | per-CTA cycles: table %.0f setup %.0f loop %.0f (in-loop prunes %.0f, %0.2f prunes, "
+            "%.1f sync points) final %.0f\n",
+            t[7], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n, t[6] / n, t[3] / n);
+  }
   CK(cudaMemcpyAsync(&sc, ix->d_scanned, sizeof(sc), cudaMemcpyDeviceToHost, ix->stream));
   CK(cudaStreamSynchronize(ix->stream));
   ix->last_scanned = (long long)sc;
@@ -974,6 +1015,29 @@ int gb200_flat_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, co
   }
   cudaEventDestroy(e);
   return rc;
+}
+
+// ---- test hook -------------------------------------------------------------------------------------
+int gb200_debug_select(int device, const uint64_t *keys, int n, int R, int cap, int batch, int threads,
+                       uint64_t *out, int *out_n) {
+  if (!keys || !out || !out_n || n <= 0 || R <= 0 || cap < 512 || batch <= 0 || batch > cap - R ||
+      cap > 16 * threads || threads % 32 != 0 || threads > 1024)
+    return GB200_EINVAL;
+  CK(cudaSetDevice(device));
+  u64 *d_keys = nullptr, *d_out = nullptr;
+  int *d_n = nullptr;
+  CK(cudaMalloc(&d_keys, (size_t)n * 8));
+  CK(cudaMalloc(&d_out, (size_t)R * 8));
+  CK(cudaMalloc(&d_n, 4));
+  CK(cudaMemcpy(d_keys, keys, (size_t)n * 8, cudaMemcpyHostToDevice));
+  CK(launch_select_selftest(d_keys, n, R, cap, batch, threads, d_out, d_n, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out_n, d_n, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, d_out, (size_t)(*out_n) * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_keys);
+  cudaFree(d_out);
+  cudaFree(d_n);
+  return GB200_OK;
 }
 
 // ---- accounting ---------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const floa
 constexpr int CS_THREADS = 256;
 constexpr int CS_PER_ROUND = 4;  // elements per thread per round
 
+template <int PER>
 __global__ void __launch_bounds__(CS_THREADS) coarse_select_kernel(const float *__restrict__ dist, int nlist,
                                                                     int nprobe, int cap, int *__restrict__ keys,
                                                                     float *__restrict__ coarse_dis) {
@@ -107,9 +108,9 @@ __global__ void __launch_bounds__(CS_THREADS) coarse_select_kernel(const float *
       topr.append_warp(pass, key);
     }
     int over = *((volatile int *)topr.cnt) > prune_limit;
-    if (__syncthreads_or(over)) topr.prune_collective();
+    if (__syncthreads_or(over)) topr.prune_collective<PER>();
   }
-  topr.prune_collective();
+  topr.prune_collective<PER>();
   const int n_out = min(*((volatile int *)topr.cnt), nprobe);
   const int np2 = next_pow2(nprobe);
   for (int i = n_out + threadIdx.x; i < np2; i += CS_THREADS) buf[i] = GB_KEY_MAX;
@@ -130,13 +131,17 @@ cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe
   while (cap < need) cap <<= 1;
   if (cap < next_pow2(nprobe)) cap = next_pow2(nprobe);
   size_t smem = (size_t)cap * sizeof(u64) + (4 + 64) * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
+  if (cap <= 4 * CS_THREADS) {
+    coarse_select_kernel<4><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
+  } else {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(coarse_select_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    coarse_select_kernel<16><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   }
-  coarse_select_kernel<<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   return cudaGetLastError();
 }
 

@@ -76,11 +76,9 @@ __device__ __forceinline__ float ldg_nc_f32(const void *p) {
 //
 //   * append(): a candidate whose key is below the current threshold tau is pushed
 //     into an UNSORTED shared-memory buffer (one warp-aggregated atomicAdd);
-//   * prune(): when the buffer cannot take another round, the whole CTA finds the
-//     R-th smallest key by MSB-first bisection over the 64-bit key space
-//     (count-below per step: register compares + one warp REDUX + one barrier —
-//     almost no shared-memory/LSU traffic, which the ADC lookups need), compacts
-//     the survivors to the front and tightens tau.
+//   * prune(): when the buffer is (nearly) full the whole CTA finds the R-th smallest key
+//     with a register-resident radix select (see prune_impl), compacts the survivors to
+//     the front and tightens tau.
 //   No sorting network runs during the scan; only the final <=R survivors are sorted
 //   where an order is required.
 // Keys are unique (seq is unique per posting), so a separating threshold exists.
@@ -119,71 +117,175 @@ struct BlockTopR {
     }
   }
 
-  // collective: number of buffered keys strictly below t
-  __device__ __forceinline__ int count_below(u64 t, int n, int parity) {
-    int c = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (buf[i] < t);
-    c = __reduce_add_sync(GB_FULL, c);
-    int nw = (blockDim.x + 31) >> 5;
-    int *part = warp_part + parity * 32;
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  // collective: keep only the R smallest keys (no-op when <= R are buffered), tighten tau.
+  //
+  // Radix select on registers: every thread pulls its share of the buffer into registers (the
+  // buffer then doubles as scratch), the CTA narrows [min,max] of the distance word by a 256-bin
+  // shared-memory histogram per pass (power-of-two bins => exact integer boundaries) until the bin
+  // holding the R-th key has <= 64 members, ranks those 64 by brute force, and compacts.  Equal
+  // distance words fall through to a second stage on the scan-order word.  About a dozen barriers
+  // and ~2 passes in practice, versus 64 barrier-separated bisection steps.  PER = keys held per thread: cap <= PER * blockDim.x
+  // (the launchers pick 4 when the buffer has <= 4 keys per thread, else 16).
+  template <int PER>
+  __device__ __forceinline__ void prune_collective() {
     __syncthreads();
-    int tot = 0;
-    for (int w = 0; w < nw; w++) tot += part[w];
-    return tot;
-  }
-
-  // collective: keep only the `keep` smallest keys (keep = min(R, count)), set tau.
-  __device__ void prune_collective() {
-    __syncthreads();
-    int n = min(*((volatile int *)cnt), cap);
+    const int n = min(*((volatile int *)cnt), cap);
     if (n <= R) {  // nothing to drop (uniform decision)
       __syncthreads();
       return;
     }
-    // Find the smallest t with count(key < t) >= R, bit by bit: t = prefix with the
-    // undecided low bits zero; invariant count(key < lo) < R.  After 64 steps lo is the
-    // R-th smallest key itself, so count(key <= lo) == R because keys are unique.
-    u64 lo = 0;
-    int parity = 0;
-    for (int bit = 63; bit >= 0; --bit) {
-      u64 cand = lo | (1ull << bit);
-      int c = count_below(cand, n, parity);
-      parity ^= 1;
-      if (c < R) {
-        lo = cand;  // R-th smallest is >= cand
-      } else if (c == R) {
-        // cand separates exactly R keys: done early.
-        lo = cand - 1;  // keys <= lo are the survivors
-        break;
-      }
-    }
-    // survivors: key <= lo  (exactly R of them when the loop ran to the end: lo == R-th key)
-    // compact in two phases through registers (buffer is read fully before being rewritten)
-    const int PER = 16;  // cap <= PER * blockDim.x is guaranteed by the launcher
-    u64 mine[PER];
-    unsigned keep = 0;
+    const int tid = threadIdx.x, bd = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (bd + 31) >> 5;
+    u64 k[PER];
 #pragma unroll
     for (int j = 0; j < PER; j++) {
-      int i = threadIdx.x + j * blockDim.x;
-      mine[j] = 0;
-      if (i < n) {
-        mine[j] = buf[i];
-        if (mine[j] <= lo) keep |= (1u << j);
-      }
+      int i = tid + j * bd;
+      k[j] = i < n ? buf[i] : GB_KEY_MAX;
     }
+    __syncthreads();  // buf is scratch from here until the compaction
+    int *hist = reinterpret_cast<int *>(buf);          // [256]
+    volatile int *var = hist + 256;                    // [16]: 0 bin, 1 below, 2 in-bin, 4 ncand, 6..7 t*
+    u64 *cand = buf + 160;                             // [64] at byte 1280
+    int stage = 0;      // 0: distance word, 1: scan-order word among keys whose distance word == fixed_hi
+    uint32_t fixed_hi = 0, lo = 0, hi = 0;
+    int base = 0;       // keys known to be strictly below the current range
+    u64 tstar = 0;
+    bool resolved = false;
+
+    auto in_scope = [&](u64 key) -> bool {
+      return key != GB_KEY_MAX && (stage == 0 || (uint32_t)(key >> 32) == fixed_hi);
+    };
+    auto word = [&](u64 key) -> uint32_t { return stage == 0 ? (uint32_t)(key >> 32) : (uint32_t)key; };
+    auto minmax = [&]() {  // collective: lo/hi = min/max word over keys in scope
+      uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (in_scope(k[j])) {
+          uint32_t w = word(k[j]);
+          mn = min(mn, w);
+          mx = max(mx, w);
+        }
+      mn = __reduce_min_sync(GB_FULL, mn);
+      mx = __reduce_max_sync(GB_FULL, mx);
+      if (lane == 0) {
+        hist[wid] = (int)mn;
+        hist[32 + wid] = (int)mx;
+      }
+      __syncthreads();
+      mn = 0xffffffffu;
+      mx = 0u;
+      for (int w = 0; w < nw; w++) {
+        mn = min(mn, (uint32_t)hist[w]);
+        mx = max(mx, (uint32_t)hist[32 + w]);
+      }
+      lo = mn;
+      hi = mx;
+      __syncthreads();
+    };
+
+    minmax();
+    for (;;) {
+      if (lo == hi) {
+        if (stage == 0) {  // every remaining key has the same distance word: decide on scan order
+          stage = 1;
+          fixed_hi = lo;
+          minmax();
+          continue;
+        }
+        tstar = ((u64)fixed_hi << 32) | lo;  // keys are unique: a single key is left
+        resolved = true;
+        break;
+      }
+      const uint32_t range = hi - lo;
+      const int shift = max(0, (32 - __clz(range)) - 8);  // (range >> shift) < 256
+      if (tid < 256) hist[tid] = 0;
+      if (tid == 0) var[4] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (in_scope(k[j])) {
+          uint32_t w = word(k[j]);
+          if (w >= lo && w <= hi) atomicAdd(&hist[(w - lo) >> shift], 1);
+        }
+      __syncthreads();
+      if (wid == 0) {  // locate the bin that holds rank `need` (1-based) inside the range
+        int c[8], s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          c[t] = hist[lane * 8 + t];
+          s += c[t];
+        }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(GB_FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int excl = incl - s, need = R - base;
+        if (excl < need && need <= incl) {
+          int run = excl;
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            if (need > run && need <= run + c[t]) {
+              var[0] = lane * 8 + t;
+              var[1] = run;
+              var[2] = c[t];
+            }
+            run += c[t];
+          }
+        }
+      }
+      __syncthreads();
+      const int b = var[0], below = var[1], cb = var[2];
+      base += below;
+      const uint32_t nlo = lo + ((uint32_t)b << shift);
+      const uint32_t nhi = shift == 0 ? nlo : min(hi, nlo + ((1u << shift) - 1u));
+      lo = nlo;
+      hi = nhi;
+      __syncthreads();  // scratch is reused by the next pass / the gather
+      if (cb <= 64) break;
+    }
+    if (!resolved) {
+      // gather the <= 64 keys of the final range and rank them by brute force
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (in_scope(k[j])) {
+          uint32_t w = word(k[j]);
+          if (w >= lo && w <= hi) {
+            int sidx = atomicAdd((int *)&var[4], 1);
+            if (sidx < 64) cand[sidx] = k[j];
+          }
+        }
+      __syncthreads();
+      const int nc = min((int)var[4], 64), need = R - base;
+      if (wid == 0) {
+        for (int i = lane; i < nc; i += 32) {
+          const u64 c = cand[i];
+          int r = 0;
+          for (int j = 0; j < nc; j++) r += cand[j] < c;
+          if (r == need - 1) *reinterpret_cast<volatile u64 *>(var + 6) = c;
+        }
+      }
+      __syncthreads();
+      tstar = *reinterpret_cast<volatile u64 *>(var + 6);
+    }
+    // survivors: key <= t*  (exactly R of them)
+    unsigned keep = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+      if (k[j] != GB_KEY_MAX && k[j] <= tstar) keep |= (1u << j);
     __syncthreads();
-    if (threadIdx.x == 0) *cnt = 0;
+    if (tid == 0) *cnt = 0;
     __syncthreads();
     if (keep) {
       int o = atomicAdd(cnt, __popc(keep));
 #pragma unroll
       for (int j = 0; j < PER; j++)
-        if ((keep >> j) & 1u) buf[o++] = mine[j];
+        if ((keep >> j) & 1u) buf[o++] = k[j];
     }
-    if (threadIdx.x == 0) *tau = lo + 1;  // admit only strictly better than the R-th
+    if (tid == 0) *tau = tstar + 1;  // admit only strictly better than the R-th
     __syncthreads();
   }
+
 };
 
 // In-place bitonic sort (ascending) of n = power of two u64 keys in shared memory. collective.

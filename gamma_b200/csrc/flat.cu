@@ -52,7 +52,7 @@ __device__ __forceinline__ float exact_distance_octet_f(const float *__restrict_
   return __shfl_sync(GB_FULL, r, 0, 8);
 }
 
-template <bool IP>
+template <bool IP, int PER>
 __global__ void __launch_bounds__(FL_THREADS) flat_exact_kernel(FlatParams P, int cap, int kpad) {
   extern __shared__ __align__(16) unsigned char smem[];
   u64 *buf = reinterpret_cast<u64 *>(smem);
@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(FL_THREADS) flat_exact_kernel(FlatParams P, in
       topr.append_warp(pass, key);
     }
     int over = *((volatile int *)topr.cnt) > prune_limit;
-    if (__syncthreads_or(over)) topr.prune_collective();
+    if (__syncthreads_or(over)) topr.prune_collective<PER>();
   }
-  topr.prune_collective();
+  topr.prune_collective<PER>();
   const int n_out = min(*((volatile int *)topr.cnt), P.k);
   u64 *out = P.scratch + ((size_t)q * P.nsplit + split) * kpad;
   for (int i = tid; i < kpad; i += FL_THREADS) out[i] = i < n_out ? buf[i] : GB_KEY_MAX;
@@ -135,19 +135,23 @@ cudaError_t launch_flat_exact(const FlatParams &P, cudaStream_t st) {
   if (p2 < next_pow2(P.k)) p2 = next_pow2(P.k);
   size_t smem2 = (size_t)p2 * sizeof(u64);
   if (smem > 200 * 1024 || smem2 > 200 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e;
-  if (P.is_ip) {
-    if (smem > 48 * 1024) { e = cudaFuncSetAttribute(flat_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; }
-    if (smem2 > 48 * 1024) { e = cudaFuncSetAttribute(flat_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); if (e) return e; }
-    flat_exact_kernel<true><<<dim3(P.nsplit, P.n), FL_THREADS, smem, st>>>(P, cap, kpad);
-    flat_merge_kernel<true><<<P.n, 256, smem2, st>>>(P, kpad, p2);
-  } else {
-    if (smem > 48 * 1024) { e = cudaFuncSetAttribute(flat_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; }
-    if (smem2 > 48 * 1024) { e = cudaFuncSetAttribute(flat_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); if (e) return e; }
-    flat_exact_kernel<false><<<dim3(P.nsplit, P.n), FL_THREADS, smem, st>>>(P, cap, kpad);
-    flat_merge_kernel<false><<<P.n, 256, smem2, st>>>(P, kpad, p2);
-  }
-  return cudaGetLastError();
+  auto run = [&](auto exact, auto merge) -> cudaError_t {
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e) return e;
+    }
+    if (smem2 > 48 * 1024) {
+      e = cudaFuncSetAttribute(merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e) return e;
+    }
+    exact<<<dim3(P.nsplit, P.n), FL_THREADS, smem, st>>>(P, cap, kpad);
+    merge<<<P.n, 256, smem2, st>>>(P, kpad, p2);
+    return cudaGetLastError();
+  };
+  const bool big = cap > 4 * FL_THREADS;
+  if (P.is_ip) return big ? run(flat_exact_kernel<true, 16>, flat_merge_kernel<true>) : run(flat_exact_kernel<true, 4>, flat_merge_kernel<true>);
+  return big ? run(flat_exact_kernel<false, 16>, flat_merge_kernel<false>) : run(flat_exact_kernel<false, 4>, flat_merge_kernel<false>);
 }
 
 }  // namespace gb

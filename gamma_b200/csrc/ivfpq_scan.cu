@@ -32,10 +32,13 @@ extern __shared__ __align__(16) unsigned char gb_scan_smem[];
 
 namespace gb {
 
+// generic kernel: lock-step rounds of SCAN_U blocks per warp
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_U = 2;  // 32-posting blocks per warp per round
 constexpr int SCAN_ROUND_POSTINGS = SCAN_WARPS * SCAN_U * 32;
+// M = 32 kernel: 12 warps, 3 CTAs per SM (36 resident warps), sync point every M32_U blocks per warp
+constexpr int M32_U = 8;
 
 struct ProbeInfo {
   long long off;  // first posting of the list in the pools
@@ -70,114 +73,60 @@ __device__ __forceinline__ float adc_generic(const float *lut, const uint8_t *co
   return acc;
 }
 
-template <int IMM>
-__device__ __forceinline__ float lds_lut(uint32_t off) {
-  float v;
-  // address = gb_scan_smem (constant) + off + IMM ; the table is the first thing in dynamic smem
-  asm("{\n\t.reg .u32 a;\n\tmov.u32 a, gb_scan_smem;\n\tadd.u32 a, a, %1;\n\tld.shared.f32 %0, [a+%2];\n\t}"
-      : "=f"(v)
-      : "r"(off), "n"(IMM));
-  return v;
-}
 
-// M = 32 conflict-free ADC (see header comment).  lut_lane = shared byte address of the table
-// + lane*4 folded into the PRMT operand; w[0..7] = the posting's 32 pre-rotated code bytes.
-template <int S>
-__device__ __forceinline__ void adc_m32_word(uint32_t word, uint32_t lane4, float &a0, float &a1, float &a2, float &a3) {
-  // (code_byte << 8) | lane4 : selector nibbles [3]=5 (zero) [2]=5 (zero) [1]=byte j [0]=4 (lane4)
-  a0 += lds_lut<4 * (S + 0)>(__byte_perm(word, lane4, 0x5504));
-  a1 += lds_lut<4 * (S + 1)>(__byte_perm(word, lane4, 0x5514));
-  a2 += lds_lut<4 * (S + 2)>(__byte_perm(word, lane4, 0x5524));
-  a3 += lds_lut<4 * (S + 3)>(__byte_perm(word, lane4, 0x5534));
-}
-__device__ __forceinline__ float adc_m32(uint32_t lane4, const uint32_t (&w)[8]) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  adc_m32_word<0>(w[0], lane4, a0, a1, a2, a3);
-  adc_m32_word<4>(w[1], lane4, a0, a1, a2, a3);
-  adc_m32_word<8>(w[2], lane4, a0, a1, a2, a3);
-  adc_m32_word<12>(w[3], lane4, a0, a1, a2, a3);
-  adc_m32_word<16>(w[4], lane4, a0, a1, a2, a3);
-  adc_m32_word<20>(w[5], lane4, a0, a1, a2, a3);
-  adc_m32_word<24>(w[6], lane4, a0, a1, a2, a3);
-  adc_m32_word<28>(w[7], lane4, a0, a1, a2, a3);
-  return (a0 + a1) + (a2 + a3);
-}
+// ---------------------------------------------------------------------------------------------
+// shared-memory carve-up, identical for both kernels (host mirrors it in scan_smem_bytes):
+//   [lut][buf u64 cap][qs d floats][probe infos][blk prefix][misc 68 ints][mbar 2 x u64]
+// ---------------------------------------------------------------------------------------------
+struct ScanSmem {
+  float *lut;
+  u64 *buf;
+  float *qs;
+  ProbeInfo *pinfo;
+  int *blk_prefix;
+  int *misc;
+  unsigned long long *mbar;
+};
 
-template <bool IP, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) {
-  unsigned char *smem = gb_scan_smem;
-  const int q = blockIdx.y;
-  const int split = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int M = P.M, d = P.d, dsub = P.dsub;
-
-  // ---- carve shared memory
-  float *lut = reinterpret_cast<float *>(smem);
-  size_t o = scan_lut_bytes(M, MODE);
-  u64 *buf = reinterpret_cast<u64 *>(smem + o);
+__device__ __forceinline__ ScanSmem carve(unsigned char *smem, const ScanParams &P, int mode) {
+  ScanSmem S;
+  S.lut = reinterpret_cast<float *>(smem);
+  size_t o = scan_lut_bytes(P.M, mode);
+  S.buf = reinterpret_cast<u64 *>(smem + o);
   o += (size_t)P.cap * sizeof(u64);
-  float *qs = reinterpret_cast<float *>(smem + o);
-  o += (size_t)((d + 3) & ~3) * sizeof(float);
-  const int np_s = (P.nprobe - split + P.S - 1) / P.S;  // my probes: split, split+S, ...
-  ProbeInfo *pinfo = reinterpret_cast<ProbeInfo *>(smem + ((o + 15) & ~(size_t)15));
-  o = ((o + 15) & ~(size_t)15) + (size_t)P.max_np_s * sizeof(ProbeInfo);
-  int *blk_prefix = reinterpret_cast<int *>(smem + o);
+  S.qs = reinterpret_cast<float *>(smem + o);
+  o += (size_t)((P.d + 3) & ~3) * sizeof(float);
+  o = (o + 15) & ~(size_t)15;
+  S.pinfo = reinterpret_cast<ProbeInfo *>(smem + o);
+  o += (size_t)P.max_np_s * sizeof(ProbeInfo);
+  S.blk_prefix = reinterpret_cast<int *>(smem + o);
   o += (size_t)(P.max_np_s + 1) * sizeof(int);
-  int *misc = reinterpret_cast<int *>(smem + ((o + 7) & ~(size_t)7));
-  // misc: [0..1] tau (u64), [2] cnt, [4..67] warp_part
-  BlockTopR topr;
-  topr.buf = buf;
-  topr.tau = reinterpret_cast<u64 *>(misc);
-  topr.cnt = misc + 2;
-  topr.warp_part = misc + 4;
-  topr.cap = P.cap;
-  topr.R = P.R;
+  o = (o + 7) & ~(size_t)7;
+  S.misc = reinterpret_cast<int *>(smem + o);  // [0..1] tau (u64), [2] cnt, [4..67] warp_part, [68..70] round flags
+  o += (4 + 64 + 4) * sizeof(int);
+  S.mbar = reinterpret_cast<unsigned long long *>(smem + o);
+  return S;
+}
 
-  // ---- query to shared
-  const float *xq = P.xq + (size_t)q * d;
-  for (int i = tid; i < d; i += SCAN_THREADS) qs[i] = xq[i];
-  if (tid == 0) {
-    *topr.cnt = 0;
-    *topr.tau = GB_KEY_MAX;
-  }
-  __syncthreads();
+size_t scan_smem_bytes(const ScanParams &P, int mode) {
+  size_t o = scan_lut_bytes(P.M, mode);
+  o += (size_t)P.cap * sizeof(u64);
+  o += (size_t)((P.d + 3) & ~3) * sizeof(float);
+  o = ((o + 15) & ~(size_t)15) + (size_t)P.max_np_s * sizeof(ProbeInfo);
+  o += (size_t)(P.max_np_s + 1) * sizeof(int);
+  o = ((o + 7) & ~(size_t)7) + (4 + 64 + 4) * sizeof(int);
+  o += 2 * sizeof(unsigned long long);
+  return o;
+}
 
-  // ---- per-query lookup table: q_m . cb[m][c]   (x -2 for L2)
-  // pq_t is code-major [256][M][dsub]: lanes over m read consecutive dsub-float groups.
-  {
-    const float scale = IP ? 1.f : -2.f;
-    const int total = 256 * M;
-    for (int e = tid; e < total; e += SCAN_THREADS) {
-      int c = e / M, m = e - c * M;
-      const float *cb = P.pq_t + (size_t)e * dsub;
-      const float *qm = qs + m * dsub;
-      float ip = 0.f;
-      if ((dsub & 3) == 0) {
-        for (int j = 0; j < dsub; j += 4) {
-          float4 v = __ldg(reinterpret_cast<const float4 *>(cb + j));
-          ip = fmaf(qm[j], v.x, ip);
-          ip = fmaf(qm[j + 1], v.y, ip);
-          ip = fmaf(qm[j + 2], v.z, ip);
-          ip = fmaf(qm[j + 3], v.w, ip);
-        }
-      } else {
-        for (int j = 0; j < dsub; j++) ip = fmaf(qm[j], __ldg(cb + j), ip);
-      }
-      float v = scale * ip;
-      if (MODE == 1) {
-        lut[c * 64 + m] = v;
-        lut[c * 64 + 32 + m] = v;
-      } else {
-        lut[m * 257 + c] = v;
-      }
-    }
-  }
-
-  // ---- my probes: list extents, dis0, block prefix
-  long long my_postings = 0;
-  for (int j = tid; j < np_s; j += SCAN_THREADS) {
+// my probes (split, split+S, ...): list extents, dis0, prefix of 32-posting blocks.  collective.
+template <bool IP>
+__device__ __forceinline__ int setup_probes(const ScanParams &P, const ScanSmem &S, const float *q_glob, int q,
+                                            int split) {
+  const int tid = threadIdx.x;
+  const int d = P.d;
+  const int np_s = (P.nprobe - split + P.S - 1) / P.S;
+  for (int j = tid; j < np_s; j += blockDim.x) {
     int p = split + j * P.S;
     int key = P.keys[(size_t)q * P.nprobe + p];
     ProbeInfo pi;
@@ -188,69 +137,104 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) 
     if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
       pi.off = P.list_off[key];
       pi.len = P.list_len[key];
-      if (IP) {
+      if (IP) {  // dis0 = <q, centroid>  (precompute_list_tables_IP, gamma_index_ivfpq.h:216-230)
         const float *cen = P.centroids + (size_t)key * d;
         float s = 0.f;
-        for (int i = 0; i < d; i++) s = fmaf(qs[i], __ldg(cen + i), s);
+        for (int i = 0; i < d; i++) s = fmaf(__ldg(q_glob + i), __ldg(cen + i), s);
         pi.dis0 = s;
       } else {
         pi.dis0 = P.coarse_dis[(size_t)q * P.nprobe + p];
       }
     }
-    pinfo[j] = pi;
+    S.pinfo[j] = pi;
   }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
+    long long my_postings = 0;
     for (int j = 0; j < np_s; j++) {
-      blk_prefix[j] = acc;
-      acc += (pinfo[j].len + 31) >> 5;
-      my_postings += pinfo[j].len;
+      S.blk_prefix[j] = acc;
+      acc += (S.pinfo[j].len + 31) >> 5;
+      my_postings += S.pinfo[j].len;
     }
-    blk_prefix[np_s] = acc;
+    S.blk_prefix[np_s] = acc;
     if (P.scanned) atomicAdd(P.scanned, (unsigned long long)my_postings);
   }
   __syncthreads();
+  return S.blk_prefix[np_s];
+}
 
-  const int total_blocks = blk_prefix[np_s];
+__device__ __forceinline__ BlockTopR make_topr(const ScanSmem &S, const ScanParams &P) {
+  BlockTopR t;
+  t.buf = S.buf;
+  t.tau = reinterpret_cast<u64 *>(S.misc);
+  t.cnt = S.misc + 2;
+  t.warp_part = S.misc + 4;
+  t.cap = P.cap;
+  t.R = P.R;
+  return t;
+}
+
+template <int PER>
+__device__ __forceinline__ void write_survivors(BlockTopR &topr, const ScanParams &P, int q, int split) {
+  topr.prune_collective<PER>();  // leaves min(cnt, R) survivors
+  const int n_out = min(*((volatile int *)topr.cnt), P.R);
+  u64 *out = P.cand + ((size_t)q * P.S + split) * P.R;
+  for (int i = threadIdx.x; i < P.R; i += blockDim.x) out[i] = i < n_out ? topr.buf[i] : GB_KEY_MAX;
+}
+
+// =============================================================================================
+// generic kernel: any M % 4 == 0, classic [M][257] table, lanes = postings (bank conflicts random)
+// =============================================================================================
+template <bool IP, int PER>
+__global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_generic_kernel(ScanParams P) {
+  const int q = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = P.M, d = P.d, dsub = P.dsub;
+  ScanSmem S = carve(gb_scan_smem, P, 0);
+  BlockTopR topr = make_topr(S, P);
+  const float *xq = P.xq + (size_t)q * d;
+  for (int i = tid; i < d; i += SCAN_THREADS) S.qs[i] = xq[i];
+  if (tid == 0) {
+    *topr.cnt = 0;
+    *topr.tau = GB_KEY_MAX;
+  }
+  __syncthreads();
+  {  // per-query table  q_m . cb[m][c]  (x -2 for L2); pq_t is code-major [256][M][dsub]
+    const float scale = IP ? 1.f : -2.f;
+    const int total = 256 * M;
+    for (int e = tid; e < total; e += SCAN_THREADS) {
+      int c = e / M, m = e - c * M;
+      const float *cb = P.pq_t + (size_t)e * dsub;
+      const float *qm = S.qs + m * dsub;
+      float ip = 0.f;
+      for (int j = 0; j < dsub; j++) ip = fmaf(qm[j], __ldg(cb + j), ip);
+      S.lut[m * 257 + c] = scale * ip;
+    }
+  }
+  const int total_blocks = setup_probes<IP>(P, S, xq, q, split);
   const int rounds = (total_blocks + SCAN_WARPS * SCAN_U - 1) / (SCAN_WARPS * SCAN_U);
-  const uint32_t lane4 = lane * 4;
   const int prune_limit = P.cap - SCAN_ROUND_POSTINGS;
-  int cur = 0;  // probe cursor (monotone per warp)
-
+  int cur = 0;
   for (int r = 0; r < rounds; r++) {
 #pragma unroll
     for (int u = 0; u < SCAN_U; u++) {
       int g = (r * SCAN_U + u) * SCAN_WARPS + warp;
       if (g < total_blocks) {  // warp-uniform
-        while (g >= blk_prefix[cur + 1]) cur++;
-        const ProbeInfo pi = pinfo[cur];
-        const int b = g - blk_prefix[cur];
+        while (g >= S.blk_prefix[cur + 1]) cur++;
+        const ProbeInfo pi = S.pinfo[cur];
+        const int b = g - S.blk_prefix[cur];
         const int pos = b * 32 + lane;
         const long long pidx = pi.off + pos;
         bool ok = pos < pi.len;
         int id = -1;
         float dis = pi.dis0;
-        if (MODE == 1) {
-          // 32-posting block = 2 chunks of 512 B: chunk j of posting `lane` at (j*32 + lane)*16
-          const uint8_t *blk = P.codes + (size_t)(pi.off + (long long)b * 32) * 32;
-          uint4 c0 = ldg_nc_v4(blk + lane * 16);
-          uint4 c1 = ldg_nc_v4(blk + 512 + lane * 16);
-          if (ok) id = ldg_nc_s32(P.ids + pidx);
-          if (!IP) dis += ok ? ldg_nc_f32(P.norms + pidx) : 0.f;
-          ok = ok && id >= 0;
-          if (ok && P.valid) ok = bitmap_test(P.valid, id);
-          uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          dis += adc_m32(lane4, w);
-        } else {
-          if (ok) id = ldg_nc_s32(P.ids + pidx);
-          ok = ok && id >= 0;
-          if (ok && P.valid) ok = bitmap_test(P.valid, id);
-          if (ok) {
-            if (!IP) dis += ldg_nc_f32(P.norms + pidx);
-            long long blk_base = (pi.off + (long long)b * 32) * (long long)M;
-            dis += adc_generic<IP>(lut, P.codes, blk_base, lane, M, P.chunk);
-          }
+        if (ok) id = ldg_nc_s32(P.ids + pidx);
+        ok = ok && id >= 0;
+        if (ok && P.valid) ok = bitmap_test(P.valid, id);
+        if (ok) {
+          if (!IP) dis += ldg_nc_f32(P.norms + pidx);
+          long long blk_base = (pi.off + (long long)b * 32) * (long long)M;
+          dis += adc_generic<IP>(S.lut, P.codes, blk_base, lane, M, P.chunk);
         }
         uint32_t seq = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) | (uint32_t)pos;
         u64 key = ((u64)dist_to_key32<IP>(dis) << 32) | seq;
@@ -259,51 +243,359 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_kernel(ScanParams P) 
       }
     }
     int over = *((volatile int *)topr.cnt) > prune_limit;
-    if (__syncthreads_or(over)) topr.prune_collective();
+    if (__syncthreads_or(over)) topr.prune_collective<PER>();
   }
-  topr.prune_collective();  // leaves min(cnt, R) survivors
-
-  const int n_out = min(*((volatile int *)topr.cnt), P.R);
-  u64 *out = P.cand + ((size_t)q * P.S + split) * P.R;
-  for (int i = tid; i < P.R; i += SCAN_THREADS) out[i] = i < n_out ? buf[i] : GB_KEY_MAX;
+  write_survivors<PER>(topr, P, q, split);
 }
 
-size_t scan_smem_bytes(const ScanParams &P, int mode) {
-  size_t o = scan_lut_bytes(P.M, mode);
-  o += (size_t)P.cap * sizeof(u64);
-  o += (size_t)((P.d + 3) & ~3) * sizeof(float);
-  o = ((o + 15) & ~(size_t)15) + (size_t)P.max_np_s * sizeof(ProbeInfo);
-  o += (size_t)(P.max_np_s + 1) * sizeof(int);
-  o = ((o + 7) & ~(size_t)7) + (4 + 64) * sizeof(int);
-  return o;
+// =============================================================================================
+// M = 32 kernel: conflict-free table, TMA-staged codebook, software-pipelined posting loads
+// =============================================================================================
+// ---- mbarrier / TMA bulk-copy wrappers (cp.async.bulk -> UBLKCP in SASS)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct Pre {  // one prefetched 32-posting block, per lane
+  uint4 c0, c1;
+  int id;        // vid, < 0 = padding / dead / beyond the list end
+  float nrm;     // t(p)  (L2 only) — consumed one block later, never at load time
+  float base;    // dis0 of the list
+  uint32_t seq;  // (probe rank << 21) | position ; 0xffffffff = no block
+};
+
+// LDS addressing of the table.  RAW: the table's shared-window address is the constant
+// GB_SMEM_RESERVED (dynamic shared memory starts right after the 1 KB the driver reserves per CTA on
+// sm_90+, cudaDevAttrReservedSharedMemoryPerBlock), so "prmt + const + 4*s" is the complete address and
+// the lookup is PRMT + LDS + FADD.  The kernel verifies the assumption at run time and otherwise takes
+// the SYM path (address through the symbol: one extra integer add per lookup).
+#define GB_SMEM_RESERVED 1024
+template <bool RAW, int S0>
+__device__ __forceinline__ float lut_at(uint32_t off) {
+  if (RAW) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(GB_SMEM_RESERVED + 4 * S0));
+    return v;
+  } else {
+    return *reinterpret_cast<const float *>(gb_scan_smem + off + 4 * S0);
+  }
+}
+template <bool RAW, int S0>
+__device__ __forceinline__ void adc_m32_word(uint32_t word, uint32_t lane4, float &a0, float &a1, float &a2,
+                                             float &a3) {
+  // selector nibbles [3]=5 (zero) [2]=5 (zero) [1]=code byte j [0]=4 (lane4)
+  a0 += lut_at<RAW, S0 + 0>(__byte_perm(word, lane4, 0x5504));
+  a1 += lut_at<RAW, S0 + 1>(__byte_perm(word, lane4, 0x5514));
+  a2 += lut_at<RAW, S0 + 2>(__byte_perm(word, lane4, 0x5524));
+  a3 += lut_at<RAW, S0 + 3>(__byte_perm(word, lane4, 0x5534));
+}
+template <bool RAW>
+__device__ __forceinline__ float adc_m32(uint32_t lane4, const uint4 &c0, const uint4 &c1) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  adc_m32_word<RAW, 0>(c0.x, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 4>(c0.y, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 8>(c0.z, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 12>(c0.w, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 16>(c1.x, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 20>(c1.y, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 24>(c1.z, lane4, a0, a1, a2, a3);
+  adc_m32_word<RAW, 28>(c1.w, lane4, a0, a1, a2, a3);
+  return (a0 + a1) + (a2 + a3);
+}
+
+// main loop of the M = 32 kernel.
+//  * every warp owns a CONTIGUOUS range of the query's 32-posting blocks: per-list state lives in
+//    registers, a new list costs one shared-memory read; selection does not depend on the order in which
+//    warps see postings (ties are broken by seq);
+//  * the next block's codes/id/t(p) are in flight while the current block is looked up;
+//  * warps run free for up to M32_U blocks between CTA-wide sync points.  A warp whose append does not fit
+//    in the candidate buffer keeps the unwritten candidates in registers ("stalled"), asks for a prune
+//    at the sync point and retries afterwards — so no headroom has to be reserved per round.
+template <bool IP, bool HAS_VALID, bool RAW, int M32_WARPS, int PER>
+__device__ __forceinline__ void scan_loop_m32(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
+                                              int total_blocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane4 = lane * 4;
+  const int per_warp = (total_blocks + M32_WARPS - 1) / M32_WARPS;
+  const int w0 = min(total_blocks, warp * per_warp);
+  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
+  const int soft_limit = P.cap - M32_WARPS * 32;
+  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
+
+  int pj = 0;
+  if (left > 0)  // blk_prefix[pj] <= w0 < blk_prefix[pj + 1]; terminates because w0 < total_blocks
+    while (S.blk_prefix[pj + 1] <= w0) pj++;
+  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
+  uint32_t seq0 = 0;
+  float dis0 = 0.f;
+  const uint8_t *cptr = nullptr;
+  const int *iptr = nullptr;
+  const float *nptr = nullptr;
+  auto open_list = [&](int j, int b_start) {
+    const ProbeInfo pi = S.pinfo[j];
+    bl = ((pi.len + 31) >> 5) - b_start;
+    dis0 = pi.dis0;
+    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
+    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
+    const long long first = pi.off + (long long)b_start * 32;
+    cptr = P.codes + (size_t)first * 32 + lane * 16;
+    iptr = P.ids + first + lane;
+    nptr = P.norms + first + lane;
+  };
+  if (left > 0) open_list(pj, w0 - S.blk_prefix[pj]);
+
+  auto load_block = [&]() -> Pre {
+    Pre x;
+    x.seq = 0xffffffffu;
+    x.id = -1;
+    x.base = 0.f;
+    x.nrm = 0.f;
+    x.c0 = make_uint4(0, 0, 0, 0);
+    x.c1 = x.c0;
+    if (left > 0) {  // warp-uniform
+      while (bl == 0) open_list(++pj, 0);
+      // 32-posting block = 2 chunks of 512 B: chunk j of posting `lane` at (j*32 + lane)*16
+      x.c0 = ldg_nc_v4(cptr);
+      x.c1 = ldg_nc_v4(cptr + 512);
+      x.seq = seq0;
+      x.base = dis0;
+      if (len > 0) {
+        x.id = ldg_nc_s32(iptr);
+        if (!IP) x.nrm = ldg_nc_f32(nptr);
+      }
+      cptr += 1024;
+      iptr += 32;
+      nptr += 32;
+      seq0 += 32;
+      len -= 32;
+      bl--;
+      left--;
+    }
+    return x;
+  };
+
+  // append what passes; returns true when some lane of the warp could not be written (buffer full)
+  u64 skey = 0;
+  bool spend = false;
+  auto try_append = [&](bool pass, u64 key) -> bool {
+    const unsigned m = __ballot_sync(GB_FULL, pass);
+    if (m == 0) return false;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
+    base = __shfl_sync(GB_FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    bool pending = pass;
+    if (pass && slot < topr.cap) {
+      topr.buf[slot] = key;
+      pending = false;
+    }
+    spend = pending;
+    skey = key;
+    return __any_sync(GB_FULL, pending);
+  };
+
+  Pre nxt = load_block();
+  bool stalled = false;
+  int round = 0;
+  for (;;) {
+    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
+    int done = 0;
+    while (!stalled && done < M32_U && nxt.seq != 0xffffffffu) {  // warp-uniform
+      const Pre cur = nxt;
+      nxt = load_block();
+      uint32_t vw = 0xffffffffu;
+      if (HAS_VALID) vw = cur.id >= 0 ? __ldg(P.valid + (cur.id >> 5)) : 0u;  // latency hidden by the lookups
+      const uint32_t tau_hi = (uint32_t)(topr.threshold() >> 32);
+      const float dis = (cur.base + cur.nrm) + adc_m32<RAW>(lane4, cur.c0, cur.c1);
+      bool ok = cur.id >= 0;
+      if (HAS_VALID) ok = ok && ((vw >> (cur.id & 31)) & 1u);
+      const uint32_t k32 = dist_to_key32<IP>(dis);
+      bool pass = ok && (dis == dis) && k32 <= tau_hi;  // cheap pre-test on the distance word
+      if (__any_sync(GB_FULL, pass)) {
+        const u64 key = ((u64)k32 << 32) | cur.seq;
+        stalled = try_append(pass && key < topr.threshold(), key);
+      }
+      done++;
+    }
+    const bool more = stalled || nxt.seq != 0xffffffffu;
+    const bool over = stalled || *((volatile int *)topr.cnt) > soft_limit;
+    const int slot = round % 3;
+    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
+    __syncthreads();
+    const int v = flags[slot];
+    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
+    round++;
+    if (v & 1) {
+      long long tp0 = clock64();
+      topr.prune_collective<PER>();
+      if (P.timing && threadIdx.x == 0) {
+        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
+        atomicAdd(P.timing + 5, 1ull);
+      }
+    }
+    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
+    if (!(v & 2)) break;
+  }
+}
+
+#define GB_TICK(slot)                                                   \
+  if (P.timing && threadIdx.x == 0) {                                   \
+    long long t_now = clock64();                                        \
+    atomicAdd(P.timing + (slot), (unsigned long long)(t_now - t_last)); \
+    t_last = t_now;                                                     \
+  }
+
+template <bool IP, int M32_THREADS, int PER>
+__global__ void __launch_bounds__(M32_THREADS, PER == 4 ? 3 : 1) ivfpq_scan_m32_kernel(ScanParams P) {
+  constexpr int M32_WARPS = M32_THREADS / 32;
+  long long t_last = clock64();
+  const int q = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int d = P.d;
+  ScanSmem S = carve(gb_scan_smem, P, 1);
+  BlockTopR topr = make_topr(S, P);
+  const float *xq = P.xq + (size_t)q * d;
+  if (tid == 0) {
+    *topr.cnt = 0;
+    *topr.tau = GB_KEY_MAX;
+    S.misc[68] = S.misc[69] = S.misc[70] = 0;
+    mbar_init(&S.mbar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- the query's lookup table [256][64] (built once per query by lut_build_kernel, L2-resident) is
+  // pulled into shared memory by four 16 KB TMA bulk copies; the probe setup below overlaps the transfer.
+  if (tid == 0) {
+    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
+    mbar_expect_tx(&S.mbar[0], 65536u);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
+  }
+  const int total_blocks = setup_probes<IP>(P, S, xq, q, split);
+  GB_TICK(1);  // probe setup
+  mbar_wait(&S.mbar[0], 0);
+  GB_TICK(0);  // wait for the table
+  const bool raw_ok = smem_u32(gb_scan_smem) == GB_SMEM_RESERVED && !P.force_sym;  // CTA-uniform
+  if (P.valid) {
+    if (raw_ok) scan_loop_m32<IP, true, true, M32_WARPS, PER>(P, S, topr, total_blocks);
+    else scan_loop_m32<IP, true, false, M32_WARPS, PER>(P, S, topr, total_blocks);
+  } else {
+    if (raw_ok) scan_loop_m32<IP, false, true, M32_WARPS, PER>(P, S, topr, total_blocks);
+    else scan_loop_m32<IP, false, false, M32_WARPS, PER>(P, S, topr, total_blocks);
+  }
+  GB_TICK(2);  // scan loop incl. in-loop prunes
+  write_survivors<PER>(topr, P, q, split);
+  GB_TICK(3);  // final prune + write
+  if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
+}
+
+// K2a — per-query lookup tables for the M = 32 kernel: lut_g[q][c][m] = lut_g[q][c][32 + m] =
+// scale * <q_m, cb[m][c]>  (scale = -2 for L2, +1 for InnerProduct): QueryTables::init_query /
+// ProductQuantizer::compute_inner_prod_table (gamma_index_ivfpq.h:148-168, faiss ProductQuantizer.cpp:504-530).
+__global__ void __launch_bounds__(256) lut_build_m32_kernel(const float *__restrict__ xq, const float *__restrict__ pq_t,
+                                                            float *__restrict__ lut_g, int d, int dsub, float scale) {
+  __shared__ float qs[1024];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < d; i += 256) qs[(i % dsub) * 32 + (i / dsub)] = xq[(size_t)q * d + i];
+  __syncthreads();
+  float *out = lut_g + (size_t)q * 16384;
+  if (dsub == 4) {
+    float q0 = qs[lane], q1 = qs[32 + lane], q2 = qs[64 + lane], q3 = qs[96 + lane];
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+      const int e = tid + i * 256;
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(pq_t) + e);
+      float ip = q0 * v.x;
+      ip = fmaf(q1, v.y, ip);
+      ip = fmaf(q2, v.z, ip);
+      ip = fmaf(q3, v.w, ip);
+      const int c = e >> 5;
+      out[c * 64 + lane] = scale * ip;
+      out[c * 64 + 32 + lane] = scale * ip;
+    }
+  } else {
+    for (int e = tid; e < 8192; e += 256) {
+      const float *cb = pq_t + (size_t)e * dsub;
+      float ip = 0.f;
+      for (int j = 0; j < dsub; j++) ip = fmaf(qs[j * 32 + lane], __ldg(cb + j), ip);
+      const int c = e >> 5;
+      out[c * 64 + lane] = scale * ip;
+      out[c * 64 + 32 + lane] = scale * ip;
+    }
+  }
+}
+
+cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
+                                 cudaStream_t st) {
+  if (d > 1024) return cudaErrorInvalidValue;
+  lut_build_m32_kernel<<<n, 256, 0, st>>>(xq, pq_t, lut_g, d, dsub, is_ip ? 1.f : -2.f);
+  return cudaGetLastError();
 }
 
 int scan_buffer_cap(int R) {
-  // room for R survivors + one full round of admissions
+  // room for R survivors + one full round of admissions (generic kernel's lock-step rounds)
   int need = R + SCAN_ROUND_POSTINGS;
   int cap = 1024;
   while (cap < need) cap <<= 1;
   return cap;  // <= 16 * SCAN_THREADS = 4096 (BlockTopR::prune_collective register budget)
 }
 
-template <bool IP, int MODE>
-static cudaError_t launch_one(const ScanParams &P, cudaStream_t st) {
-  size_t smem = scan_smem_bytes(P, MODE);
-  static size_t configured[2][2] = {{0, 0}, {0, 0}};
-  if (smem > configured[IP][MODE]) {
-    cudaError_t e = cudaFuncSetAttribute(ivfpq_scan_kernel<IP, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <typename K>
+static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int threads, size_t *configured,
+                                 cudaStream_t st) {
+  size_t smem = scan_smem_bytes(P, mode);
+  if (smem > *configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[IP][MODE] = smem;
+    *configured = smem;
   }
   dim3 grid(P.S, P.n);
-  ivfpq_scan_kernel<IP, MODE><<<grid, SCAN_THREADS, smem, st>>>(P);
+  kernel<<<grid, threads, smem, st>>>(P);
   return cudaGetLastError();
 }
 
+template <int T, int PER>
+static cudaError_t launch_m32(const ScanParams &P, cudaStream_t st) {
+  static size_t conf[2] = {0, 0};
+  return P.is_ip ? launch_kernel(ivfpq_scan_m32_kernel<true, T, PER>, P, 1, T, &conf[0], st)
+                 : launch_kernel(ivfpq_scan_m32_kernel<false, T, PER>, P, 1, T, &conf[1], st);
+}
+
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
-  if (P.is_ip) return mode == 1 ? launch_one<true, 1>(P, st) : launch_one<true, 0>(P, st);
-  return mode == 1 ? launch_one<false, 1>(P, st) : launch_one<false, 0>(P, st);
+  static size_t conf[4] = {0, 0, 0, 0};
+  if (mode == 1) {
+    if (P.cap > 4 * 256) return launch_m32<256, 16>(P, st);  // large recall_num: 16 keys per thread in the select
+    switch (P.m32_threads) {
+      case 384: return launch_m32<384, 4>(P, st);
+      case 320: return launch_m32<320, 4>(P, st);
+      default: return launch_m32<256, 4>(P, st);
+    }
+  }
+  if (P.cap > 4 * SCAN_THREADS)
+    return P.is_ip ? launch_kernel(ivfpq_scan_generic_kernel<true, 16>, P, 0, SCAN_THREADS, &conf[0], st)
+                   : launch_kernel(ivfpq_scan_generic_kernel<false, 16>, P, 0, SCAN_THREADS, &conf[1], st);
+  return P.is_ip ? launch_kernel(ivfpq_scan_generic_kernel<true, 4>, P, 0, SCAN_THREADS, &conf[2], st)
+                 : launch_kernel(ivfpq_scan_generic_kernel<false, 4>, P, 0, SCAN_THREADS, &conf[3], st);
 }
 
 }  // namespace gb

@@ -24,6 +24,7 @@ struct ScanParams {
   const float *coarse_dis;  // [n][nprobe]
   const float *centroids;   // [nlist][d]
   const float *pq_t;        // [256][M][dsub] code-major PQ codebook
+  const float *lut_g;       // M = 32 kernel: [n][256][64] per-query tables from launch_lut_build_m32
   const uint8_t *codes;     // posting pool (layout above)
   const int *ids;           // [pool] vid, -1 = padding / moved (kDelIdxMask)
   const float *norms;       // [pool] t(p) (L2 only)
@@ -32,11 +33,17 @@ struct ScanParams {
   const uint32_t *valid;    // validity bitmap or nullptr (everything valid)
   u64 *cand;                // [n][S][R] surviving keys (unsorted), GB_KEY_MAX padded
   unsigned long long *scanned;  // += postings walked (may be nullptr)
+  unsigned long long *timing;   // optional [8] phase cycle counters (GB200_SCAN_TIMING=1), else nullptr
   int n, d, M, dsub, nlist, nprobe, S, R, cap, chunk, max_np_s, is_ip;
+  int m32_threads;          // tuning: CTA size of the M = 32 kernel (256 / 320 / 384)
+  int no_tma;               // tuning: build the table with plain LDG instead of TMA-staged chunks
+  int force_sym;            // debug: take the symbol-addressed LDS path even when the raw one is valid
 };
 size_t scan_smem_bytes(const ScanParams &P, int mode);
 int scan_buffer_cap(int R);
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);
+cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
+                                 cudaStream_t st);
 
 // K0 — device-side append into the posting mirror (+ t(p) for L2)
 struct AppendParams {
@@ -97,6 +104,10 @@ struct FlatParams {
 };
 cudaError_t launch_flat_exact(const FlatParams &P, cudaStream_t st);
 int flat_exact_splits(long long N, int n);
+
+// test hook: BlockTopR selection on caller-provided keys (single CTA)
+cudaError_t launch_select_selftest(const u64 *keys, int n, int R, int cap, int batch, int threads, u64 *out, int *out_n,
+                                   cudaStream_t st);
 
 // validity bitmap = NOT deleted AND all range filters
 struct DevRangeFilter {

@@ -169,6 +169,13 @@ int gb200_set_profiling(gb200_index *ix, int enable);
 /* wait for the index's stream (after *_dev calls) and refresh the counters above.          */
 int gb200_sync(gb200_index *ix);
 
+/* ---- test hook (not used by the plugin): run the streaming top-R selection primitive the scan
+ * kernels use (append + radix-select prune, one CTA of `threads`) on caller-provided 64-bit keys fed
+ * in batches, return the R smallest (unordered).  Lets tests check the k-select against a host
+ * sort in isolation — the role faiss' own Heap tests play for heap_replace_top.                  */
+int gb200_debug_select(int device, const uint64_t *keys, int n, int R, int cap, int batch, int threads,
+                       uint64_t *out, int *out_n);
+
 #ifdef __cplusplus
 }
 #endif

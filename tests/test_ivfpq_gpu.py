@@ -206,3 +206,20 @@ def test_realtime_append_and_update_visible_to_next_search():
     assert dead.size == 1 and dead[0] < 0  # kDelIdxMask bit set
     ids_new, codes_new = ix.get_list(new_list)
     assert ids_new[-1] == v and np.array_equal(codes_new[-1], new_code)
+
+
+@pytest.mark.parametrize("fx,metric", [(fx_l2_m32, "L2"), (fx_l2_m16, "L2")])
+def test_large_recall_num_uses_the_wide_select(fx, metric):
+    """recall_num = 600 (> 512): candidate buffer of 2048 keys, 16-keys-per-thread radix select."""
+    f = fx()
+    ix = f.mirror()
+    nprobe, R, k = 24, 600, 50
+    cd_ref, k_ref = f.ref.coarse(f.xq, nprobe)
+    D_ref, I_ref = f.ref.search(f.xq, k, rj(nprobe, R, metric), has_rank=True, keys=k_ref, coarse_dis=cd_ref)
+    rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric=metric, has_rank=True, keys=k_ref, coarse_dis=cd_ref)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+    D_ref, I_ref = f.ref.search(f.xq, R, rj(nprobe, R, metric), has_rank=False, keys=k_ref, coarse_dis=cd_ref)
+    rc, D, I = ix.Search(f.xq, R, nprobe=nprobe, recall_num=R, metric=metric, has_rank=False, keys=k_ref, coarse_dis=cd_ref)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
