@@ -1,0 +1,200 @@
+// Drop-in proof: the reference's own model ("IVFPQ"/"FLAT") and the B200 plugin ("B200IVFPQ"/"B200FLAT")
+// are obtained from the SAME reflector (index/reflector.h:50-57, exactly what VectorManager does,
+// vector/vector_manager.cc:161-195), fed the same RawVector / deleted bitmap / Add / Update / Delete
+// stream, and searched with the same GammaSearchCondition; outputs are compared.
+// Built by `make -C oracle plugin` against the unmodified reference sources; runs on the GPU box.
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <random>
+#include <string>
+#include <vector>
+
+#include "b200_models.h"
+#include "common/gamma_common_data.h"
+#include "index/reflector.h"
+#include "table/range_query_result.h"
+#include "util/bitmap_manager.h"
+#include "vector/raw_vector_factory.h"
+
+#include <faiss/IndexFlat.h>
+
+INITIALIZE_EASYLOGGINGPP
+using namespace tig_gamma;
+
+static void quiet() {
+  el::Configurations conf;
+  conf.setToDefault();
+  conf.setGlobally(el::ConfigurationType::Enabled, "false");
+  el::Loggers::reconfigureAllLoggers(conf);
+  el::Loggers::setDefaultConfigurations(conf, true);
+}
+
+struct Cmp {
+  long slots = 0, same_id = 0, filled_mismatch = 0;
+  double max_rel = 0;
+};
+
+static Cmp compare(int n, int k, const float *D0, const int64_t *I0, const float *D1, const int64_t *I1) {
+  Cmp c;
+  for (long i = 0; i < (long)n * k; i++) {
+    c.slots++;
+    if (I0[i] == I1[i]) {
+      c.same_id++;
+      if (I0[i] >= 0) {
+        double rel = fabs((double)D0[i] - D1[i]) / fmax(fabs((double)D0[i]), 1e-6);
+        if (rel > c.max_rel) c.max_rel = rel;
+      }
+    }
+    if ((I0[i] < 0) != (I1[i] < 0)) c.filled_mismatch++;
+  }
+  return c;
+}
+
+int main(int argc, char **argv) {
+  quiet();
+  const int N = argc > 1 ? atoi(argv[1]) : 60000, d = 128, nlist = 256, M = 32, nq = 128, k = 10;
+  omp_set_num_threads(16);
+  std::mt19937 rng(123);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::vector<float> centres(256 * d), xb((size_t)N * d), xq((size_t)nq * d);
+  for (auto &v : centres) v = nd(rng);
+  auto sample = [&](float *out) {
+    int c = rng() % 256;
+    for (int j = 0; j < d; j++) out[j] = centres[c * d + j] + 0.3f * nd(rng);
+  };
+  for (int i = 0; i < N; i++) sample(&xb[(size_t)i * d]);
+  for (int i = 0; i < nq; i++) sample(&xq[(size_t)i * d]);
+
+  utils::make_dir("/tmp/b200_plugin_parity");
+  utils::make_dir("/tmp/b200_plugin_parity/vectors");
+  VectorMetaInfo *meta = new VectorMetaInfo("gamma", d, VectorValueType::FLOAT);
+  meta->with_io_ = false;
+  StoreParams sp(meta->AbsoluteName());
+  bitmap::BitmapManager *bm = new bitmap::BitmapManager();
+  bm->Init(4 * N);
+  RawVector *raw = RawVectorFactory::Create(meta, VectorStorageType::MemoryOnly, "/tmp/b200_plugin_parity/vectors", sp, bm);
+  if (!raw || raw->Init("gamma", false, false)) return 2;
+
+  const char *json = "{\"ncentroids\":256,\"nsubvector\":32,\"metric_type\":\"L2\",\"nprobe\":16}";
+  RetrievalModel *cpu = reflector().GetNewModel("IVFPQ");
+  RetrievalModel *gpu = reflector().GetNewModel("B200IVFPQ");
+  RetrievalModel *cpu_flat = reflector().GetNewModel("FLAT");
+  RetrievalModel *gpu_flat = reflector().GetNewModel("B200FLAT");
+  if (!cpu || !gpu || !cpu_flat || !gpu_flat) {
+    printf("{\"error\":\"reflector did not return the models\"}\n");
+    return 3;
+  }
+  for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat}) m->vector_ = raw;
+  if (cpu->Init(json, N) || gpu->Init(json, N)) return 4;
+  if (cpu_flat->Init("{\"metric_type\":\"L2\"}", N) || gpu_flat->Init("{\"metric_type\":\"L2\"}", N)) return 4;
+
+  // the engine adds to the store first (AddToStore), trains once indexing_size docs exist, then feeds the index
+  const int first = N - 5000;
+  for (int i = 0; i < first; i++) raw->Add(i, &xb[(size_t)i * d]);
+  if (cpu->Indexing()) return 5;
+  {  // same trained state for both (what Dump/Load would give): copy quantizers into the plugin's embedded CPU model
+    GammaIVFPQIndex *c = dynamic_cast<GammaIVFPQIndex *>(cpu), *g = dynamic_cast<GammaIVFPQIndex *>(gpu);
+    faiss::IndexFlat *cf = dynamic_cast<faiss::IndexFlat *>(c->quantizer);
+    g->quantizer->reset();
+    g->quantizer->add(c->nlist, cf->xb.data());
+    g->quantizer->is_trained = true;
+    g->pq.centroids = c->pq.centroids;
+    g->is_trained = true;
+    g->use_precomputed_table = 0;
+    g->precompute_table();
+  }
+  if (gpu->Indexing()) return 5;
+  auto feed = [&](int from, int to) {
+    for (int s = from; s < to; s += 1000) {  // AddRTVecsToIndex chunks (vector_manager.cc:280-382)
+      int n = std::min(1000, to - s);
+      ScopeVectors h;
+      std::vector<int> lens;
+      raw->GetVectorHeader(s, n, h, lens);
+      int off = 0;
+      for (size_t j = 0; j < h.Size(); j++) {
+        for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat})
+          if (!m->Add(lens[j], h.Get(j))) exit(6);
+        off += lens[j];
+      }
+    }
+  };
+  feed(0, first);
+
+  PerfTool perf;
+  auto search = [&](RetrievalModel *m, const char *rjson, bool has_rank, MultiRangeQueryResults *mr, float lo, float hi,
+                    std::vector<float> &D, std::vector<int64_t> &I) {
+    GammaSearchCondition cond(&perf);
+    cond.topn = k;
+    cond.has_rank = has_rank;
+    cond.range_query_result = mr;
+    cond.Init(lo, hi, bm, raw);
+    cond.retrieval_params_ = m->Parse(rjson);
+    D.assign((size_t)nq * k, 0.f);
+    I.assign((size_t)nq * k, -1);
+    return m->Search(&cond, nq, (const uint8_t *)xq.data(), k, D.data(), I.data());
+  };
+  const float FMAX = std::numeric_limits<float>::max();
+  std::vector<float> D0, D1;
+  std::vector<int64_t> I0, I1;
+  int fails = 0;
+  auto report = [&](const char *name, double min_same, double max_rel) {
+    Cmp c = compare(nq, k, D0.data(), I0.data(), D1.data(), I1.data());
+    double same = (double)c.same_id / c.slots;
+    bool ok = same >= min_same && c.max_rel <= max_rel && c.filled_mismatch == 0;
+    printf("{\"case\":\"%s\",\"ids_identical\":%.5f,\"max_rel_err_where_same\":%.3g,\"filled_mismatch\":%ld,\"ok\":%s}\n", name,
+           same, c.max_rel, c.filled_mismatch, ok ? "true" : "false");
+    if (!ok) fails++;
+  };
+  const char *rj = "{\"nprobe\":16,\"recall_num\":100,\"metric_type\":\"L2\"}";
+  search(cpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, true, nullptr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_rerank", 0.995, 1e-6);
+  search(cpu, rj, false, nullptr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, false, nullptr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_adc", 0.98, 1e-4);
+
+  // realtime: add the rest, delete some docs, update one, filter by a range bitmap
+  for (int i = first; i < N; i++) raw->Add(i, &xb[(size_t)i * d]);
+  feed(first, N);
+  std::vector<int64_t> dele;
+  for (int i = 0; i < N; i += 97) dele.push_back(i);
+  for (int64_t v : dele) bm->Set((uint32_t)v);
+  for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat}) m->Delete(dele);
+  {
+    std::vector<int64_t> ids(1, 4242);
+    std::vector<const uint8_t *> vecs(1, (const uint8_t *)&xb[(size_t)(N - 1) * d]);
+    raw->UpdateToStore(4242, (uint8_t *)vecs[0], d * sizeof(float));
+    for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat}) m->Update(ids, vecs);
+  }
+  MultiRangeQueryResults mr;
+  {
+    RangeQueryResult r;
+    r.SetRange(1000, N - 777);
+    r.Resize();
+    int cnt = 0;
+    for (int doc = 1000; doc <= N - 777; doc++)
+      if ((doc * 2654435761u >> 7) % 10 < 3) {
+        r.Set(doc - r.MinAligned());
+        cnt++;
+      }
+    r.SetDocNum(cnt);
+    mr.Add(std::move(r));
+  }
+  search(cpu, rj, true, &mr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, true, &mr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_rerank_filter_delete_update", 0.995, 1e-6);
+  const char *fj = "{\"metric_type\":\"L2\",\"parallel_on_queries\":0}";
+  search(cpu_flat, fj, true, &mr, -FMAX, FMAX, D0, I0);
+  search(gpu_flat, fj, true, &mr, -FMAX, FMAX, D1, I1);
+  report("flat_filter_delete_update", 1.0, 0.0);
+  float lo = D0[3], hi = D0[7];
+  search(cpu_flat, fj, true, nullptr, lo, hi, D0, I0);
+  search(gpu_flat, fj, true, nullptr, lo, hi, D1, I1);
+  report("flat_score_window", 1.0, 0.0);
+  printf("{\"plugin_parity\":\"%s\",\"gpu_mem_bytes\":%ld}\n", fails ? "FAIL" : "PASS", gpu->GetTotalMemBytes());
+  return fails ? 1 : 0;
+}

@@ -90,6 +90,13 @@ class RefFixture:
         self.centroids = self.ref.centroids()
         self.pq = self.ref.pq_centroids()
         self.lists = self.ref.lists()
+        self.deleted = []  # docs deleted in the (cached, shared) reference index; mirror() replays them
+
+    def delete(self, docs):
+        for doc in docs:
+            if int(doc) not in self.deleted:
+                self.ref.delete(int(doc))
+                self.deleted.append(int(doc))
 
     def mirror(self, device=0, raw=True):
         """Build the device index from the reference's trained state and postings (list order kept)."""
@@ -105,6 +112,8 @@ class RefFixture:
         assert ix.append(list_no[order], vids[order], codes[order]) == 0, api.lib().gb200_last_error()
         if raw:
             ix.upload_raw(self.xb)
+        if self.deleted:
+            ix.set_deleted(np.array(self.deleted, np.int64), True)
         return ix
 
 

@@ -98,8 +98,7 @@ def test_filters_and_deletions_inside_the_scan():
     field = synth.filter_field(N)
     pass_flags = (field < 30).astype(np.uint8)
     dele = synth.deleted_docs(N, 0.01)
-    for doc in dele:
-        f.ref.delete(int(doc))
+    f.delete(dele)  # recorded on the shared fixture: every later mirror() replays the same deletions
     try:
         ix.set_deleted(dele, True)
         filt = [(0, N - 1, False, pass_flags)]
