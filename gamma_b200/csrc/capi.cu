@@ -82,6 +82,7 @@ struct gb200_index {
   bool trained = false;
 
   float *d_cent = nullptr, *d_cent_norm = nullptr, *d_pq = nullptr, *d_pq_t = nullptr;
+  float *d_cent_small = nullptr;  // centroid - tf32(centroid): second operand of the 3xTF32 tensor-core GEMM
 
   long long pool_cap = 0, pool_used = 0, pool_live_cap = 0;
   uint8_t *d_codes = nullptr;
@@ -105,7 +106,7 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs;
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
@@ -219,13 +220,13 @@ int gb200_destroy(gb200_index *ix) {
   if (!ix) return GB200_OK;
   cudaSetDevice(ix->p.device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  void *ptrs[] = {ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
+  void *ptrs[] = {ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
                   ix->d_off,  ix->d_len,       ix->d_raw, ix->d_deleted, ix->d_scanned};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 4; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
@@ -255,6 +256,9 @@ int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse, const float
       memcpy(&t[((size_t)c * M + m) * dsub], &pq[((size_t)m * 256 + c) * dsub], dsub * sizeof(float));
   CK(cudaMemcpyAsync(ix->d_pq_t, t.data(), pb, cudaMemcpyHostToDevice, ix->stream));
   CK(launch_row_norms(ix->d_cent, nlist, d, ix->d_cent_norm, ix->stream));
+  if (!ix->d_cent_small) CK(cudaMalloc(&ix->d_cent_small, cb));
+  CK(launch_tf32_residual(ix->d_cent, ix->d_cent_small, (size_t)nlist * d, ix->stream));
+  ix->launches++;
   ix->launches++;
   CK(cudaStreamSynchronize(ix->stream));
   ix->trained = true;
@@ -644,14 +648,28 @@ static int coarse_dev(gb200_index *ix, int n, const float *d_xq, int nprobe, int
   }
   CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
   CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
+  // distance producer: tcgen05 3xTF32 GEMM (default) or the CUDA-core fp32 kernel (GB200_COARSE=simt)
+  const char *cmode = getenv("GB200_COARSE");
+  const bool use_tc = !(cmode && !strcmp(cmode, "simt")) && (d % 4 == 0) && (nlist % 4 == 0);
+  if (use_tc) {
+    CKI(ix->ws_xs.ensure((size_t)n * d * sizeof(float)));
+    CK(launch_tf32_residual(d_xq, ix->ws_xs.as<float>(), (size_t)n * d, ix->stream));
+    ix->launches++;
+  }
   // bound the distance matrix scratch to ~1 GiB by chunking the queries
   long long rows = std::max<long long>(1, (1LL << 28) / nlist);
   if (rows > n) rows = n;
   CKI(ix->ws_dist.ensure((size_t)rows * nlist * sizeof(float)));
   for (long long r0 = 0; r0 < n; r0 += rows) {
     int m = (int)std::min<long long>(rows, n - r0);
-    CK(launch_coarse_dist(d_xq + (size_t)r0 * d, ix->ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
-                          ix->ws_dist.as<float>(), ix->stream));
+    if (use_tc) {
+      CK(launch_tc_gemm(d_xq + (size_t)r0 * d, ix->ws_xs.as<float>() + (size_t)r0 * d, ix->ws_xn.as<float>() + r0,
+                        ix->d_cent, ix->d_cent_small, ix->d_cent_norm, m, nlist, d, ix->ws_dist.as<float>(), nlist, 1,
+                        ix->stream));
+    } else {
+      CK(launch_coarse_dist(d_xq + (size_t)r0 * d, ix->ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
+                            ix->ws_dist.as<float>(), ix->stream));
+    }
     CK(launch_coarse_select(ix->ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
                             d_cdis + (size_t)r0 * nprobe, ix->stream));
     ix->launches += 2;
@@ -733,6 +751,13 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   CK(cudaMemsetAsync(ix->d_scanned, 0, sizeof(unsigned long long), ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
   P.lut_g = nullptr;
+  P.order = nullptr;
+  if (n <= 4096 && n > 148 && getenv("GB200_SCAN_ORDER")) {
+    CKI(ix->ws_order.ensure((size_t)n * sizeof(int)));
+    CK(launch_query_order(d_keys, ix->d_len, n, nprobe, ix->p.nlist, ix->ws_order.as<int>(), ix->stream));
+    ix->launches++;
+    P.order = ix->ws_order.as<int>();
+  }
   if (ix->mode == 1) {
     if (ix->p.d > 1024) {
       set_err("M=32 kernel: d=%d > 1024 not implemented", ix->p.d);

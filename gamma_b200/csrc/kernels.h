@@ -24,6 +24,7 @@ struct ScanParams {
   const float *coarse_dis;  // [n][nprobe]
   const float *centroids;   // [nlist][d]
   const float *pq_t;        // [256][M][dsub] code-major PQ codebook
+  const int *order;         // optional [n] query order (heaviest first) or nullptr
   const float *lut_g;       // M = 32 kernel: [n][256][64] per-query tables from launch_lut_build_m32
   const uint8_t *codes;     // posting pool (layout above)
   const int *ids;           // [pool] vid, -1 = padding / moved (kDelIdxMask)
@@ -42,6 +43,8 @@ struct ScanParams {
 size_t scan_smem_bytes(const ScanParams &P, int mode);
 int scan_buffer_cap(int R);
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);
+cudaError_t launch_query_order(const int *keys, const int *list_len, int n, int nprobe, int nlist, int *order,
+                               cudaStream_t st);
 cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
                                  cudaStream_t st);
 
@@ -70,6 +73,11 @@ cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaSt
 cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,
                                const float *cent_norm, int n, int nlist, int d, float *dist,
                                cudaStream_t st);
+// tensor-core distance producer (tc_gemm.cu): out[M][ldo] = L2^2 (l2=1) or inner product of a (M x K) vs b (N x K)
+cudaError_t launch_tf32_residual(const float *x, float *small, size_t n, cudaStream_t st);
+cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_norm, const float *b,
+                           const float *b_small, const float *b_norm, int M, int N, int K, float *out, int ldo, int l2,
+                           cudaStream_t st);
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys,
                                  float *coarse_dis, cudaStream_t st);
 

@@ -1,0 +1,300 @@
+// K1t / K4t — dense Q x Y^T contraction on the 5th-generation tensor cores (tcgen05 + TMEM + TMA),
+// the only GEMM-shaped work on the path: the coarse quantiser (n x nlist x d) and the flat scan
+// (n x N x d).  Replaces the sgemm inside faiss knn_L2sqr (faiss utils/distances.cpp:215-296) and the
+// per-vector fvec_L2sqr / fvec_inner_product loop of GammaFLATIndex::Search (gamma_index_flat.cc:183-232)
+// as the *distance producer*; selection and (for FLAT) the exact re-score stay in their own kernels.
+//
+// Precision: operands are fp32 in memory and the tensor core multiplies TF32 (it ignores the low 13
+// mantissa bits).  To keep fp32-level accuracy (the probe set must equal the CPU engine's) each
+// product is evaluated as  big*big + big*small + small*big  with small = x - tf32(x) precomputed
+// ("3xTF32"): three tcgen05.mma per k-step into the same TMEM accumulator, relative error ~2^-21.
+//
+// Structure (one 128 x 128 output tile per CTA, K pipelined in 32-float slabs, 3 stages):
+//   warp 0 lane 0 : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 operand tiles
+//   warp 1 lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::tf32, tcgen05.commit -> mbarriers
+//   warps 2..5    : epilogue      — tcgen05.ld (TMEM -> registers), |q|^2 + |y|^2 - 2 acc (clamped at 0)
+//                                   or acc (InnerProduct), 128-bit stores of the distance tile
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "kernels.h"
+
+namespace gb {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;  // tile; TC_BK floats = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;      // 16 KB per operand tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_big, A_small, B_big, B_small
+constexpr int TC_THREADS = 192;                       // 6 warps
+constexpr int TC_TMEM_COLS = 128;                     // fp32 accumulator: 128 lanes x 128 columns
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTCW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TCD_%=;\n\tbra TCW_%=;\n\tTCD_%=:\n\t}" ::"r"(tc_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          tc_smem_u32(dst)),
+      "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major operand tile, SWIZZLE_128B: rows at 128 B pitch, 8-row atoms 1024 B apart (SBO), LBO unused.
+// Bit layout: cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) LBO[16,30) SBO[32,46)
+// version[46,48)=1 layout_type[61,64)=2.
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32) a_format[7,10)=2 (TF32) b_format[10,13)=2, both K-major,
+// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4
+__device__ __forceinline__ uint32_t tc_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
+               : "memory");
+}
+
+struct TcGemmParams {
+  const float *a_norm;  // [M] or nullptr
+  const float *b_norm;  // [N] or nullptr
+  float *out;           // [M][ldo]
+  int M, N, K, ldo;
+  int l2;               // 1: out = an + bn - 2 acc clamped at 0 ; 0: out = acc
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __grid_constant__ CUtensorMap map_a_small,
+                      const __grid_constant__ CUtensorMap map_b_big, const __grid_constant__ CUtensorMap map_b_small,
+                      TcGemmParams P) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  // carve: stages (1024-aligned), then barriers + tmem pointer
+  unsigned char *tiles = tc_smem;
+  uint64_t *full = reinterpret_cast<uint64_t *>(tc_smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t *empty = full + TC_STAGES;
+  uint64_t *tmem_full = empty + TC_STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  const int num_kb = (P.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; s++) {
+      tc_mbar_init(&full[s], 1);
+      tc_mbar_init(&empty[s], 1);
+    }
+    tc_mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_ptr)),
+                 "n"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % TC_STAGES, it = kb / TC_STAGES;
+        if (it > 0) tc_mbar_wait(&empty[s], (it - 1) & 1);
+        unsigned char *st = tiles + s * TC_STAGE_BYTES;
+        tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+        tc_tma_load_2d(st + 0 * TC_TILE_BYTES, &map_a_big, kb * TC_BK, tile_m * TC_BM, &full[s]);
+        tc_tma_load_2d(st + 1 * TC_TILE_BYTES, &map_a_small, kb * TC_BK, tile_m * TC_BM, &full[s]);
+        tc_tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b_big, kb * TC_BK, tile_n * TC_BN, &full[s]);
+        tc_tma_load_2d(st + 3 * TC_TILE_BYTES, &map_b_small, kb * TC_BK, tile_n * TC_BN, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      const uint32_t idesc = tc_idesc();
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % TC_STAGES, it = kb / TC_STAGES;
+        tc_mbar_wait(&full[s], it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = tc_smem_u32(tiles + s * TC_STAGE_BYTES);
+        const uint64_t a_big = tc_make_desc(base), a_small = tc_make_desc(base + TC_TILE_BYTES);
+        const uint64_t b_big = tc_make_desc(base + 2 * TC_TILE_BYTES), b_small = tc_make_desc(base + 3 * TC_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+          const uint64_t adv = (uint64_t)(k * 2);
+          tc_mma(tmem_base, a_small + adv, b_big + adv, idesc, (kb | k) ? 1u : 0u);
+          tc_mma(tmem_base, a_big + adv, b_small + adv, idesc, 1u);
+          tc_mma(tmem_base, a_big + adv, b_big + adv, idesc, 1u);
+        }
+        tc_commit(&empty[s]);  // the slot is free once these MMAs have read it
+      }
+      tc_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lanes (warp % 4) * 32 .. + 31
+    tc_mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    const int row = tile_m * TC_BM + quarter * 32 + lane;
+    const float an = (P.l2 && P.a_norm && row < P.M) ? P.a_norm[row] : 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < P.M) {
+        float *dst = P.out + (size_t)row * P.ldo + (size_t)tile_n * TC_BN + c0;
+        const int col0 = tile_n * TC_BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            float acc = __uint_as_float(v[j + t]);
+            int col = col0 + j + t;
+            float r = acc;
+            if (P.l2) {
+              float bn = (P.b_norm && col < P.N) ? __ldg(P.b_norm + col) : 0.f;
+              r = an + bn - 2.f * acc;
+              r = r < 0.f ? 0.f : r;
+            }
+            o[t] = r;
+          }
+          if (col0 + j + 3 < P.N && ((P.ldo & 3) == 0)) {
+            *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+              if (col0 + j + t < P.N) dst[j + t] = o[t];
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// small = x - tf32_truncate(x)  (exact in fp32); the "big" operand is x itself: the tensor core drops the
+// low 13 mantissa bits on its own.
+__global__ void tf32_residual_kernel(const float *__restrict__ x, float *__restrict__ small, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = x[i];
+    float big = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    small[i] = v - big;
+  }
+}
+
+cudaError_t launch_tf32_residual(const float *x, float *small, size_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  tf32_residual_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, small, n);
+  return cudaGetLastError();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows][K] fp32, box = 32 floats x 128 rows, SWIZZLE_128B, out-of-bounds reads give zeros
+static bool make_map(CUtensorMap *m, const float *ptr, int rows, int K) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// out[M][ldo] (columns 0..N-1) = L2^2 or inner product of rows of a (M x K) against rows of b (N x K).
+// K % 4 == 0 and 16-byte aligned bases are required by the tensor maps.
+cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_norm, const float *b,
+                           const float *b_small, const float *b_norm, int M, int N, int K, float *out, int ldo, int l2,
+                           cudaStream_t st) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if ((K & 3) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)a_small & 15) || ((uintptr_t)b_small & 15))
+    return cudaErrorInvalidValue;
+  CUtensorMap ma, mas, mb, mbs;
+  if (!make_map(&ma, a, M, K) || !make_map(&mas, a_small, M, K) || !make_map(&mb, b, N, K) ||
+      !make_map(&mbs, b_small, N, K))
+    return cudaErrorNotSupported;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  TcGemmParams P;
+  P.a_norm = a_norm;
+  P.b_norm = b_norm;
+  P.out = out;
+  P.M = M;
+  P.N = N;
+  P.K = K;
+  P.ldo = ldo;
+  P.l2 = l2;
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+  tc_gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mas, mb, mbs, P);
+  return cudaGetLastError();
+}
+
+}  // namespace gb

@@ -77,7 +77,10 @@ int main(int argc, char **argv) {
   bitmap::BitmapManager *bm = new bitmap::BitmapManager();
   bm->Init(4 * N);
   RawVector *raw = RawVectorFactory::Create(meta, VectorStorageType::MemoryOnly, "/tmp/b200_plugin_parity/vectors", sp, bm);
-  if (!raw || raw->Init("gamma", false, false)) return 2;
+  if (!raw || raw->Init("gamma", false, false)) {
+    printf("{\"error\":\"raw vector init failed\"}\n");
+    return 2;
+  }
 
   const char *json = "{\"ncentroids\":256,\"nsubvector\":32,\"metric_type\":\"L2\",\"nprobe\":16}";
   RetrievalModel *cpu = reflector().GetNewModel("IVFPQ");
@@ -89,13 +92,26 @@ int main(int argc, char **argv) {
     return 3;
   }
   for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat}) m->vector_ = raw;
-  if (cpu->Init(json, N) || gpu->Init(json, N)) return 4;
-  if (cpu_flat->Init("{\"metric_type\":\"L2\"}", N) || gpu_flat->Init("{\"metric_type\":\"L2\"}", N)) return 4;
+  const int first = N - 5000;  // docs present when the index is trained (= indexing_size)
+  if (cpu->Init(json, first)) {
+    printf("{\"error\":\"cpu model Init failed\"}\n");
+    return 4;
+  }
+  if (gpu->Init(json, first)) {
+    printf("{\"error\":\"B200IVFPQ Init failed: %s\"}\n", gb200_last_error());
+    return 4;
+  }
+  if (cpu_flat->Init("{\"metric_type\":\"L2\"}", N) || gpu_flat->Init("{\"metric_type\":\"L2\"}", N)) {
+    printf("{\"error\":\"flat Init failed: %s\"}\n", gb200_last_error());
+    return 4;
+  }
 
   // the engine adds to the store first (AddToStore), trains once indexing_size docs exist, then feeds the index
-  const int first = N - 5000;
   for (int i = 0; i < first; i++) raw->Add(i, &xb[(size_t)i * d]);
-  if (cpu->Indexing()) return 5;
+  if (cpu->Indexing()) {
+    printf("{\"error\":\"cpu Indexing failed\"}\n");
+    return 5;
+  }
   {  // same trained state for both (what Dump/Load would give): copy quantizers into the plugin's embedded CPU model
     GammaIVFPQIndex *c = dynamic_cast<GammaIVFPQIndex *>(cpu), *g = dynamic_cast<GammaIVFPQIndex *>(gpu);
     faiss::IndexFlat *cf = dynamic_cast<faiss::IndexFlat *>(c->quantizer);
@@ -107,7 +123,10 @@ int main(int argc, char **argv) {
     g->use_precomputed_table = 0;
     g->precompute_table();
   }
-  if (gpu->Indexing()) return 5;
+  if (gpu->Indexing()) {
+    printf("{\"error\":\"B200IVFPQ Indexing failed: %s\"}\n", gb200_last_error());
+    return 5;
+  }
   auto feed = [&](int from, int to) {
     for (int s = from; s < to; s += 1000) {  // AddRTVecsToIndex chunks (vector_manager.cc:280-382)
       int n = std::min(1000, to - s);
@@ -117,7 +136,10 @@ int main(int argc, char **argv) {
       int off = 0;
       for (size_t j = 0; j < h.Size(); j++) {
         for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat})
-          if (!m->Add(lens[j], h.Get(j))) exit(6);
+          if (!m->Add(lens[j], h.Get(j))) {
+            printf("{\"error\":\"Add failed: %s\"}\n", gb200_last_error());
+            exit(6);
+          }
         off += lens[j];
       }
     }

@@ -18,7 +18,7 @@ def test_plugin_matches_reference_models_through_the_reflector():
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_WAIT_POLICY="PASSIVE")
     p = subprocess.run([BIN], capture_output=True, text=True, timeout=600, env=env)
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
-    assert lines, p.stdout + p.stderr
+    assert lines, (p.returncode, p.stdout, p.stderr)
     assert p.returncode == 0, lines
     assert lines[-1]["plugin_parity"] == "PASS", lines
     cases = {l["case"]: l for l in lines if "case" in l}
