@@ -4,6 +4,7 @@
 // every data-path step is a kernel launch; the host only moves bytes and keeps list extents.
 #include <cuda_runtime.h>
 #include <float.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -97,6 +98,9 @@ struct gb200_index {
 
   float *d_raw = nullptr;
   long long raw_cap = 0, raw_n = 0;
+  // lazily built companions of the raw store for the tensor-core flat path: x - tf32(x) and |x|^2
+  float *d_raw_small = nullptr, *d_raw_norm = nullptr;
+  long long aux_cap = 0, aux_n = 0;
 
   std::vector<uint32_t> h_deleted;
   uint32_t *d_deleted = nullptr;
@@ -106,7 +110,7 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate;
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
@@ -220,13 +224,13 @@ int gb200_destroy(gb200_index *ix) {
   if (!ix) return GB200_OK;
   cudaSetDevice(ix->p.device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  void *ptrs[] = {ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
+  void *ptrs[] = {ix->d_raw_small, ix->d_raw_norm, ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
                   ix->d_off,  ix->d_len,       ix->d_raw, ix->d_deleted, ix->d_scanned};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 4; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
@@ -496,6 +500,7 @@ int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float 
                      ix->stream));
   CK(cudaStreamSynchronize(ix->stream));
   if (need > ix->raw_n) ix->raw_n = need;
+  if (first_vid < ix->aux_n) ix->aux_n = first_vid;  // companions of the rewritten rows are stale
   ix->nodel_valid_dirty = true;
   return GB200_OK;
 }
@@ -946,6 +951,74 @@ int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, floa
 }
 
 // ---- flat ----------------------------------------------------------------------------------------
+// x - tf32(x) and |x|^2 of the raw rows [aux_n, raw_n), kept next to the raw store once a batched flat search needs them
+static int ensure_raw_aux(gb200_index *ix) {
+  const int d = ix->p.raw_d;
+  if (ix->aux_cap < ix->raw_cap) {
+    float *ns = nullptr, *nn = nullptr;
+    CK(cudaMalloc(&ns, (size_t)ix->raw_cap * d * sizeof(float)));
+    CK(cudaMalloc(&nn, (size_t)ix->raw_cap * sizeof(float)));
+    CK(cudaStreamSynchronize(ix->stream));
+    if (ix->d_raw_small) cudaFree(ix->d_raw_small);
+    if (ix->d_raw_norm) cudaFree(ix->d_raw_norm);
+    ix->d_raw_small = ns;
+    ix->d_raw_norm = nn;
+    ix->aux_cap = ix->raw_cap;
+    ix->aux_n = 0;
+  }
+  if (ix->aux_n < ix->raw_n) {
+    const long long r0 = ix->aux_n, m = ix->raw_n - r0;
+    CK(launch_tf32_residual(ix->d_raw + (size_t)r0 * d, ix->d_raw_small + (size_t)r0 * d, (size_t)m * d, ix->stream));
+    for (long long s0 = 0; s0 < m; s0 += (1 << 30) / 8) {  // row_norms takes int rows
+      int rows = (int)std::min<long long>((1 << 30) / 8, m - s0);
+      CK(launch_row_norms(ix->d_raw + (size_t)(r0 + s0) * d, rows, d, ix->d_raw_norm + r0 + s0, ix->stream));
+    }
+    ix->launches += 2;
+    ix->aux_n = ix->raw_n;
+  }
+  return GB200_OK;
+}
+
+// batched FLAT: tcgen05 3xTF32 GEMM per database chunk -> running candidate select -> exact re-score (flat_tc.cu)
+static int flat_tc_dev(gb200_index *ix, int n, const float *d_xq, int k, const gb200_search_params *sp,
+                       const uint32_t *d_valid, float *d_D, long long *d_I) {
+  const int d = ix->p.raw_d;
+  const bool ip = sp->metric == GB200_METRIC_INNER_PRODUCT;
+  CKI(ensure_raw_aux(ix));
+  CKI(ix->ws_xs.ensure((size_t)n * d * sizeof(float)));
+  CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
+  CK(launch_tf32_residual(d_xq, ix->ws_xs.as<float>(), (size_t)n * d, ix->stream));
+  CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
+  ix->launches += 2;
+  long long nc_max = ((1LL << 26) / n) & ~127LL;  // distance tile <= 256 MB
+  if (nc_max < 1024) nc_max = 1024;
+  if (nc_max > ix->raw_n) nc_max = (ix->raw_n + 127) & ~127LL;
+  CKI(ix->ws_dist.ensure((size_t)n * nc_max * sizeof(float)));
+  const int Kp = flat_tc_candidates(k);
+  CKI(ix->ws_fstate.ensure((size_t)n * Kp * sizeof(u64)));
+  // candidates are taken with a slightly widened window; the exact window is applied after the re-score
+  auto widen = [](float v, float sign) {
+    if (!(fabsf(v) < 1e30f)) return v;
+    return v + sign * (1e-3f * fabsf(v) + 1e-6f);
+  };
+  const float lo = widen(sp->min_score, -1.f), hi = widen(sp->max_score, 1.f);
+  int first = 1;
+  for (long long c0 = 0; c0 < ix->raw_n; c0 += nc_max) {
+    const int nc = (int)std::min<long long>(nc_max, ix->raw_n - c0);
+    CK(launch_tc_gemm(d_xq, ix->ws_xs.as<float>(), ix->ws_xn.as<float>(), ix->d_raw + (size_t)c0 * d,
+                      ix->d_raw_small + (size_t)c0 * d, ix->d_raw_norm + c0, n, nc, d, ix->ws_dist.as<float>(),
+                      (int)nc_max, ip ? 0 : 1, ix->stream));
+    CK(launch_flat_chunk_select(ix->ws_dist.as<float>(), (int)nc_max, nc, c0, d_valid, lo, hi, Kp, first,
+                                ix->ws_fstate.as<u64>(), n, ip ? 1 : 0, ix->stream));
+    ix->launches += 2;
+    first = 0;
+  }
+  CK(launch_flat_rescore(ix->ws_fstate.as<u64>(), Kp, d_xq, ix->d_raw, n, d, sp->min_score, sp->max_score, k, ip ? 1 : 0,
+                         d_D, d_I, ix->stream));
+  ix->launches += 1;
+  return GB200_OK;
+}
+
 static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, int k, const gb200_search_params *sp,
                      const gb200_range_filter *filters, int n_filters, bool use_installed_filter, float *D, int64_t *I,
                      bool out_on_dev) {
@@ -973,6 +1046,27 @@ static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, in
     CKI(ix->ws_out_i.ensure((size_t)n * k * sizeof(long long)));
     d_D = ix->ws_out_d.as<float>();
     d_I = ix->ws_out_i.as<long long>();
+  }
+  // batches go through the tensor cores (GB200_FLAT=exact forces the per-query exact scan)
+  const char *fmode = getenv("GB200_FLAT");
+  const bool force_exact = fmode && !strcmp(fmode, "exact");
+  const bool force_tc = fmode && !strcmp(fmode, "tc");
+  if (!force_exact && (n >= 16 || force_tc) && (d % 4 == 0) && k <= 1024) {
+    if (ix->profiling) {
+      CK(cudaEventRecord(ix->ev[0], ix->stream));
+      CK(cudaEventRecord(ix->ev[1], ix->stream));
+    }
+    CKI(flat_tc_dev(ix, n, d_xq, k, sp, d_valid, d_D, d_I));
+    if (ix->profiling) {
+      CK(cudaEventRecord(ix->ev[2], ix->stream));
+      CK(cudaEventRecord(ix->ev[3], ix->stream));
+    }
+    if (!out_on_dev) {
+      CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+      CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+      CKI(finish_profile(ix));
+    }
+    return GB200_OK;
   }
   FlatParams F;
   F.xq = d_xq;

@@ -124,8 +124,142 @@ __global__ void __launch_bounds__(CS_THREADS) coarse_select_kernel(const float *
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-per-row two-pass select for nprobe <= 128 (the common case): no sorting network, 4 barriers.
+//   pass 1: every thread takes the minimum key of its column stripe; threads are folded into
+//           G >= nprobe groups (G = 32/64/128), tau0 = the largest of the G group minima.  G distinct
+//           keys are <= tau0, so the nprobe-th smallest key of the row is <= tau0
+//           (keys = (ordered distance, column) are unique).
+//   pass 2: keys <= tau0 (about G ln G of them in expectation) are appended to a shared buffer.
+//   rank  : each survivor counts how many survivors are smaller; rank < nprobe writes output slot
+//           `rank` — ascending distance, ties by centroid id, for free.
+// If the survivors overflow the buffer (adversarial column order) tau is narrowed by bisection on
+// the key space, re-counting over the row (slow, rare, exact).
+// ---------------------------------------------------------------------------------------------
+constexpr int CW_THREADS = 256;
+constexpr int CW_CAP = 2048;  // survivors
+
+__device__ __forceinline__ u64 cw_key(float v, int col) {
+  return (v == v) ? (((u64)float_to_ordered(v) << 32) | (uint32_t)col) : GB_KEY_MAX;
+}
+
+__global__ void __launch_bounds__(CW_THREADS) coarse_select_row_kernel(const float *__restrict__ dist, int nlist, int nprobe,
+                                                                       int G, int *__restrict__ keys,
+                                                                       float *__restrict__ coarse_dis) {
+  __shared__ u64 cand[CW_CAP];
+  __shared__ u64 gmin[CW_THREADS];
+  __shared__ u64 s_tau;
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q = blockIdx.x;
+  const float *row = dist + (size_t)q * nlist;
+  const bool vec4 = (nlist & 3) == 0 && ((uintptr_t)row & 15) == 0;
+
+  // ---- pass 1: per-thread minimum
+  u64 best = GB_KEY_MAX;
+  if (vec4) {
+    for (int c = tid * 4; c < nlist; c += CW_THREADS * 4) {
+      float4 v = *reinterpret_cast<const float4 *>(row + c);
+      u64 k0 = cw_key(v.x, c), k1 = cw_key(v.y, c + 1), k2 = cw_key(v.z, c + 2), k3 = cw_key(v.w, c + 3);
+      k0 = k0 < k1 ? k0 : k1;
+      k2 = k2 < k3 ? k2 : k3;
+      k0 = k0 < k2 ? k0 : k2;
+      best = best < k0 ? best : k0;
+    }
+  } else {
+    for (int c = tid; c < nlist; c += CW_THREADS) {
+      u64 k = cw_key(row[c], c);
+      best = best < k ? best : k;
+    }
+  }
+  gmin[tid] = best;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (tid < 32) {  // group g = tid % G : fold the 256 thread minima into G group minima, tau0 = their maximum
+    u64 t = 0;
+    for (int g = tid; g < G; g += 32) {
+      u64 m = GB_KEY_MAX;
+      for (int j = g; j < CW_THREADS; j += G) m = gmin[j] < m ? gmin[j] : m;
+      t = m > t ? m : t;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      u64 x = __shfl_xor_sync(GB_FULL, t, o);
+      t = x > t ? x : t;
+    }
+    if (tid == 0) s_tau = t;
+  }
+  __syncthreads();
+  u64 tau = s_tau;
+  const bool all_valid_pass = tau == GB_KEY_MAX;  // some group saw no usable key: everything valid survives
+
+  // ---- pass 2 (+ bisection when the buffer overflows)
+  u64 lo_b = 0, hi_b = tau;  // count(key <= hi_b) >= nprobe, count(key < lo_b) < nprobe
+  int cnt = 0;
+  for (int attempt = 0;; attempt++) {
+    auto visit = [&](u64 key) {
+      bool pass = key <= tau && key != GB_KEY_MAX;
+      unsigned m = __ballot_sync(GB_FULL, pass);
+      if (m) {
+        int base = 0;
+        int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&s_cnt, __popc(m));
+        base = __shfl_sync(GB_FULL, base, leader);
+        int slot = base + __popc(m & ((1u << lane) - 1u));
+        if (pass && slot < CW_CAP) cand[slot] = key;
+      }
+    };
+    if (vec4) {
+      const int lim = ((nlist + CW_THREADS * 4 - 1) / (CW_THREADS * 4)) * (CW_THREADS * 4);
+      for (int c = tid * 4; c < lim; c += CW_THREADS * 4) {
+        const bool in = c < nlist;
+        float4 v = in ? *reinterpret_cast<const float4 *>(row + c) : make_float4(0, 0, 0, 0);
+        visit(in ? cw_key(v.x, c) : GB_KEY_MAX);
+        visit(in ? cw_key(v.y, c + 1) : GB_KEY_MAX);
+        visit(in ? cw_key(v.z, c + 2) : GB_KEY_MAX);
+        visit(in ? cw_key(v.w, c + 3) : GB_KEY_MAX);
+      }
+    } else {
+      const int lim = ((nlist + CW_THREADS - 1) / CW_THREADS) * CW_THREADS;
+      for (int c = tid; c < lim; c += CW_THREADS) visit(c < nlist ? cw_key(row[c], c) : GB_KEY_MAX);
+    }
+    __syncthreads();
+    cnt = s_cnt;
+    if (cnt <= CW_CAP && (cnt >= nprobe || (all_valid_pass && attempt == 0))) break;
+    if (attempt > 130) break;  // cannot happen (the interval halves every step); guards against a hang
+    if (cnt > CW_CAP)
+      hi_b = tau;      // still >= nprobe survivors at tau: a valid upper bound, try lower
+    else
+      lo_b = tau + 1;  // fewer than nprobe survivors: tau was lowered too far
+    tau = lo_b + (hi_b - lo_b) / 2;
+    __syncthreads();
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+  }
+  const int c = min(cnt, CW_CAP);
+  // ---- rank by counting; survivors are unique keys
+  for (int i = tid; i < c; i += CW_THREADS) {
+    const u64 k = cand[i];
+    int r = 0;
+    for (int j = 0; j < c; j++) r += cand[j] < k;
+    if (r < nprobe) {
+      keys[(size_t)q * nprobe + r] = (int)(uint32_t)k;
+      coarse_dis[(size_t)q * nprobe + r] = ordered_to_float((uint32_t)(k >> 32));
+    }
+  }
+  for (int r = c + tid; r < nprobe; r += CW_THREADS) {  // "not enough centroids": key -1
+    keys[(size_t)q * nprobe + r] = -1;
+    coarse_dis[(size_t)q * nprobe + r] = 3.402823466e38f;
+  }
+}
+
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys, float *coarse_dis,
                                  cudaStream_t st) {
+  if (nprobe <= 128 && !getenv("GB200_COARSE_SELECT_CTA")) {
+    const int G = nprobe <= 32 ? 32 : (nprobe <= 64 ? 64 : 128);
+    coarse_select_row_kernel<<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G, keys, coarse_dis);
+    return cudaGetLastError();
+  }
   int need = nprobe + CS_THREADS * CS_PER_ROUND;
   int cap = 1024;
   while (cap < need) cap <<= 1;

@@ -113,6 +113,15 @@ struct FlatParams {
 cudaError_t launch_flat_exact(const FlatParams &P, cudaStream_t st);
 int flat_exact_splits(long long N, int n);
 
+// K4t — batched flat through the tensor cores (flat_tc.cu)
+int flat_tc_candidates(int k);
+cudaError_t launch_flat_chunk_select(const float *dist, int ldo, int nc, long long chunk_base, const uint32_t *valid,
+                                     float lo, float hi, int Kp, int first, u64 *state, int n, int is_ip,
+                                     cudaStream_t st);
+cudaError_t launch_flat_rescore(const u64 *state, int Kp, const float *xq, const float *raw, int n, int d,
+                                float min_score, float max_score, int k, int is_ip, float *out_d, long long *out_i,
+                                cudaStream_t st);
+
 // test hook: BlockTopR selection on caller-provided keys (single CTA)
 cudaError_t launch_select_selftest(const u64 *keys, int n, int R, int cap, int batch, int threads, u64 *out, int *out_n,
                                    cudaStream_t st);

@@ -9,7 +9,8 @@
 // product is evaluated as  big*big + big*small + small*big  with small = x - tf32(x) precomputed
 // ("3xTF32"): three tcgen05.mma per k-step into the same TMEM accumulator, relative error ~2^-21.
 //
-// Structure (one 128 x 128 output tile per CTA, K pipelined in 32-float slabs, 3 stages):
+// Structure (persistent CTA per SM over 128 x 128 output tiles, K pipelined in 32-float slabs, 3 smem stages,
+// 2 TMEM accumulator stages so the epilogue of one tile overlaps the mainloop of the next):
 //   warp 0 lane 0 : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 operand tiles
 //   warp 1 lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::tf32, tcgen05.commit -> mbarriers
 //   warps 2..5    : epilogue      — tcgen05.ld (TMEM -> registers), |q|^2 + |y|^2 - 2 acc (clamped at 0)
@@ -88,20 +89,28 @@ struct TcGemmParams {
   int l2;               // 1: out = an + bn - 2 acc clamped at 0 ; 0: out = acc
 };
 
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+// Persistent: one CTA per SM walks the output tiles; the TMEM accumulator is double-buffered
+// (2 x 128 columns) so the epilogue of tile i overlaps the TMA/MMA of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __grid_constant__ CUtensorMap map_a_small,
                       const __grid_constant__ CUtensorMap map_b_big, const __grid_constant__ CUtensorMap map_b_small,
                       TcGemmParams P) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
-  // carve: stages (1024-aligned), then barriers + tmem pointer
   unsigned char *tiles = tc_smem;
   uint64_t *full = reinterpret_cast<uint64_t *>(tc_smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t *empty = full + TC_STAGES;
-  uint64_t *tmem_full = empty + TC_STAGES;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  uint64_t *tmem_full = empty + TC_STAGES;   // [2]
+  uint64_t *tmem_empty = tmem_full + 2;      // [2]
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *tr_all = reinterpret_cast<float *>(tmem_ptr + 4);  // 4 epilogue warps x 32 x 33 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  const int tiles_m = (P.M + TC_BM - 1) / TC_BM, tiles_n = (P.N + TC_BN - 1) / TC_BN;
+  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (P.K + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane == 0) {
@@ -109,12 +118,15 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
       tc_mbar_init(&full[s], 1);
       tc_mbar_init(&empty[s], 1);
     }
-    tc_mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; s++) {
+      tc_mbar_init(&tmem_full[s], 1);
+      tc_mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_ptr)),
-                 "n"(TC_TMEM_COLS)
+                 "n"(2 * TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -125,92 +137,109 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % TC_STAGES, it = kb / TC_STAGES;
-        if (it > 0) tc_mbar_wait(&empty[s], (it - 1) & 1);
-        unsigned char *st = tiles + s * TC_STAGE_BYTES;
-        tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-        tc_tma_load_2d(st + 0 * TC_TILE_BYTES, &map_a_big, kb * TC_BK, tile_m * TC_BM, &full[s]);
-        tc_tma_load_2d(st + 1 * TC_TILE_BYTES, &map_a_small, kb * TC_BK, tile_m * TC_BM, &full[s]);
-        tc_tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b_big, kb * TC_BK, tile_n * TC_BN, &full[s]);
-        tc_tma_load_2d(st + 3 * TC_TILE_BYTES, &map_b_small, kb * TC_BK, tile_n * TC_BN, &full[s]);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tile_m = t % tiles_m, tile_n = t / tiles_m;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % TC_STAGES, use = it / TC_STAGES;
+          if (use > 0) tc_mbar_wait(&empty[s], (use - 1) & 1);
+          unsigned char *st = tiles + s * TC_STAGE_BYTES;
+          tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+          tc_tma_load_2d(st + 0 * TC_TILE_BYTES, &map_a_big, kb * TC_BK, tile_m * TC_BM, &full[s]);
+          tc_tma_load_2d(st + 1 * TC_TILE_BYTES, &map_a_small, kb * TC_BK, tile_m * TC_BM, &full[s]);
+          tc_tma_load_2d(st + 2 * TC_TILE_BYTES, &map_b_big, kb * TC_BK, tile_n * TC_BN, &full[s]);
+          tc_tma_load_2d(st + 3 * TC_TILE_BYTES, &map_b_small, kb * TC_BK, tile_n * TC_BN, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer
       const uint32_t idesc = tc_idesc();
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % TC_STAGES, it = kb / TC_STAGES;
-        tc_mbar_wait(&full[s], it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = tc_smem_u32(tiles + s * TC_STAGE_BYTES);
-        const uint64_t a_big = tc_make_desc(base), a_small = tc_make_desc(base + TC_TILE_BYTES);
-        const uint64_t b_big = tc_make_desc(base + 2 * TC_TILE_BYTES), b_small = tc_make_desc(base + 3 * TC_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
-          const uint64_t adv = (uint64_t)(k * 2);
-          tc_mma(tmem_base, a_small + adv, b_big + adv, idesc, (kb | k) ? 1u : 0u);
-          tc_mma(tmem_base, a_big + adv, b_small + adv, idesc, 1u);
-          tc_mma(tmem_base, a_big + adv, b_big + adv, idesc, 1u);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
+        const int as = i & 1, ause = i >> 1;
+        if (ause > 0) {  // the epilogue must have drained this accumulator
+          tc_mbar_wait(&tmem_empty[as], (ause - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        tc_commit(&empty[s]);  // the slot is free once these MMAs have read it
+        const uint32_t tmem_c = tmem_base + (uint32_t)(as * TC_TMEM_COLS);
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % TC_STAGES, use = it / TC_STAGES;
+          tc_mbar_wait(&full[s], use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = tc_smem_u32(tiles + s * TC_STAGE_BYTES);
+          const uint64_t a_big = tc_make_desc(base), a_small = tc_make_desc(base + TC_TILE_BYTES);
+          const uint64_t b_big = tc_make_desc(base + 2 * TC_TILE_BYTES), b_small = tc_make_desc(base + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+            const uint64_t adv = (uint64_t)(k * 2);
+            tc_mma(tmem_c, a_small + adv, b_big + adv, idesc, (kb | k) ? 1u : 0u);
+            tc_mma(tmem_c, a_big + adv, b_small + adv, idesc, 1u);
+            tc_mma(tmem_c, a_big + adv, b_big + adv, idesc, 1u);
+          }
+          tc_commit(&empty[s]);  // the slot is free once these MMAs have read it
+        }
+        tc_commit(&tmem_full[as]);  // accumulator complete
       }
-      tc_commit(tmem_full);    // accumulator complete
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lanes (warp % 4) * 32 .. + 31
-    tc_mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
-    const int row = tile_m * TC_BM + quarter * 32 + lane;
-    const float an = (P.l2 && P.a_norm && row < P.M) ? P.a_norm[row] : 0.f;
+    int i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
+      const int tile_m = t % tiles_m, tile_n = t / tiles_m;
+      const int as = i & 1, ause = i >> 1;
+      tc_mbar_wait(&tmem_full[as], ause & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row0 = tile_m * TC_BM + quarter * 32;          // this warp's 32 rows; lane l holds row row0 + l
+      const float an_mine = (P.l2 && P.a_norm && row0 + lane < P.M) ? P.a_norm[row0 + lane] : 0.f;
+      float *tr = tr_all + (warp - 2) * (32 * 33);              // per-warp 32 x 32 transpose tile (+1 pad)
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < P.M) {
-        float *dst = P.out + (size_t)row * P.ldo + (size_t)tile_n * TC_BN + c0;
-        const int col0 = tile_n * TC_BN + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            float acc = __uint_as_float(v[j + t]);
-            int col = col0 + j + t;
-            float r = acc;
-            if (P.l2) {
-              float bn = (P.b_norm && col < P.N) ? __ldg(P.b_norm + col) : 0.f;
-              r = an + bn - 2.f * acc;
-              r = r < 0.f ? 0.f : r;
-            }
-            o[t] = r;
-          }
-          if (col0 + j + 3 < P.N && ((P.ldo & 3) == 0)) {
-            *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 4; t++)
-              if (col0 + j + t < P.N) dst[j + t] = o[t];
-          }
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_TMEM_COLS + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= TC_BN) {  // all of this warp's accumulator rows are in registers: hand the buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
         }
+        // transpose through shared memory so that a warp stores 32 consecutive columns of ONE row (128 B)
+        // per instruction instead of 16 B of 32 different rows; conflict-free both ways thanks to the pad
+#pragma unroll
+        for (int j = 0; j < 32; j++) tr[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = tile_n * TC_BN + c0 + lane;
+        const float bn = (P.l2 && P.b_norm && col < P.N) ? __ldg(P.b_norm + col) : 0.f;
+        float *dst = P.out + (size_t)row0 * P.ldo + col;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr++) {
+          const float acc = tr[rr * 33 + lane];
+          const float an = __shfl_sync(0xffffffffu, an_mine, rr);
+          float r = acc;
+          if (P.l2) {
+            r = an + bn - 2.f * acc;
+            r = r < 0.f ? 0.f : r;
+          }
+          if (row0 + rr < P.M && col < P.N) dst[(size_t)rr * P.ldo] = r;
+        }
+        __syncwarp();
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_TMEM_COLS)
+                 : "memory");
   }
 }
 
@@ -276,7 +305,8 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
   if (!make_map(&ma, a, M, K) || !make_map(&mas, a_small, M, K) || !make_map(&mb, b, N, K) ||
       !make_map(&mbs, b_small, N, K))
     return cudaErrorNotSupported;
-  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * sizeof(uint64_t) + 16 +
+                      4 * 32 * 33 * sizeof(float) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -292,7 +322,13 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
   P.K = K;
   P.ldo = ldo;
   P.l2 = l2;
-  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+  const int num_tiles = ((N + TC_BN - 1) / TC_BN) * ((M + TC_BM - 1) / TC_BM);
+  int sms = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = num_tiles < sms ? num_tiles : sms;  // persistent: one CTA per SM
   tc_gemm_tf32x3_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mas, mb, mbs, P);
   return cudaGetLastError();
 }

@@ -74,3 +74,19 @@ def test_flat_empty_store_and_k_gt_n():
     rc, D, I = ix.Search(xq, 5, metric="L2")
     assert rc == 0
     assert np.array_equal(I[0], [0, 1, 2, -1, -1]) and np.all(D[0, :3] == 1.0)
+
+
+@pytest.mark.parametrize("metric,d,N,nq", [("InnerProduct", 64, 150000, 64), ("L2", 96, 70000, 40)])
+def test_flat_batch_tensor_core_path_is_exact(metric, d, N, nq, monkeypatch):
+    """Batches (n >= 16) take the tcgen05 GEMM -> candidate select -> exact re-score route; the result
+    must still be bit-identical to the CPU engine (ids and distances), including across database chunks."""
+    xb, xq, r, ix = build(N, d, metric, nq, normalize=(metric != "L2"))
+    pj = json.dumps({"metric_type": metric, "parallel_on_queries": 0})
+    D_ref, I_ref = r.search(xq, 10, pj)
+    rc, D, I = ix.Search(xq, 10, metric=metric)
+    assert rc == 0
+    assert np.array_equal(I_ref, I) and np.array_equal(D_ref, D)
+    # the per-query exact scan (GB200_FLAT=exact) gives the same answer
+    monkeypatch.setenv("GB200_FLAT", "exact")
+    rc, D2, I2 = ix.Search(xq, 10, metric=metric)
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)

@@ -222,3 +222,15 @@ def test_large_recall_num_uses_the_wide_select(fx, metric):
     rc, D, I = ix.Search(f.xq, R, nprobe=nprobe, recall_num=R, metric=metric, has_rank=False, keys=k_ref, coarse_dis=cd_ref)
     assert rc == 0
     assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("nprobe", [1, 31, 32, 33, 64, 100, 128])
+def test_coarse_select_nprobe_sweep(nprobe):
+    """warp-per-row select (nprobe <= 128): all KPL variants, ascending order, ties by centroid id."""
+    f = fx_l2_m32()
+    ix = f.mirror(raw=False)
+    cd_ref, k_ref = f.ref.coarse(f.xq, nprobe)
+    cd, k = ix.coarse(f.xq, nprobe)
+    r = compare_topk(cd_ref, k_ref, cd, k, rtol=1e-4, atol=1e-4)
+    assert r["n_id_mismatch_unexplained"] == 0 and r["max_rel_err"] <= 1e-4, r
+    assert np.all(np.diff(cd, axis=1) >= 0)
