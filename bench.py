@@ -109,12 +109,28 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _cache_path(tag):
+    """dev only: GB200_BENCH_CACHE=<dir> keeps the seeded synthetic set and the trained/encoded index between
+    bench.py invocations on the same box (setup is outside every timed region; the data are identical)."""
+    c = os.environ.get("GB200_BENCH_CACHE")
+    if not c:
+        return None
+    os.makedirs(c, exist_ok=True)
+    return os.path.join(c, tag)
+
+
 def build_dataset(w, scale):
     from gamma_b200 import synth
     N = max(int(w["N"] * scale), 50 * 256)
     nlist = w["nlist"] if scale == 1.0 else max(64, int(w["nlist"] * scale))
     t = time.time()
-    xb = synth.base_vectors(N, w["d"])
+    cache = _cache_path("data_%d_%d" % (N, w["d"]))
+    if cache and os.path.exists(cache + ".xb.npy"):
+        xb = np.load(cache + ".xb.npy")
+    else:
+        xb = synth.base_vectors(N, w["d"])
+        if cache and int(os.environ.get("RANK", "0")) == 0:
+            np.save(cache + ".xb.npy", xb)
     xq_all = synth.query_vectors(w["batch"] * 8, w["d"])
     log("synthetic data N=%d d=%d in %.1fs" % (N, w["d"], time.time() - t))
     return N, nlist, xb, xq_all
@@ -128,7 +144,14 @@ def build_index_state(w, N, nlist, xb, device, dist_ctx):
     M, d = w["M"], w["d"]
     if rank == 0:
         t = time.time()
-        coarse, pq, list_no, codes = builder.build_ivfpq(xb, nlist, M, device=device)
+        cache = _cache_path("index_%d_%d_%d_%d.npz" % (N, d, nlist, M))
+        if cache and os.path.exists(cache):
+            z = np.load(cache)
+            coarse, pq, list_no, codes = z["coarse"], z["pq"], z["list_no"], z["codes"]
+        else:
+            coarse, pq, list_no, codes = builder.build_ivfpq(xb, nlist, M, device=device)
+            if cache:
+                np.savez(cache, coarse=coarse, pq=pq, list_no=list_no, codes=codes)
         log("trained + encoded in %.1fs" % (time.time() - t))
     if world > 1:
         import torch.distributed as dist
