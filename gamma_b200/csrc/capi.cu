@@ -78,6 +78,7 @@ struct gb200_index {
   int kind = 0;  // 0 = IVFPQ, 1 = FLAT
   gb200_ivfpq_params p{};
   int dsub = 0, chunk = 0, layout = 0, mode = 0;
+  int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the v2 scan's LDS immediates assume 1024)
   cudaStream_t stream = nullptr;
   std::mutex mu;
   bool trained = false;
@@ -110,7 +111,7 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe;
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
@@ -151,6 +152,7 @@ static int common_create(gb200_index *ix) {
             prop.minor);
     return GB200_EUNSUPPORTED;
   }
+  ix->smem_reserved = (int)prop.reservedSharedMemPerBlock;
   CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ix->ev[i]));
   CK(cudaMalloc(&ix->d_scanned, sizeof(unsigned long long)));
@@ -230,7 +232,7 @@ int gb200_destroy(gb200_index *ix) {
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 4; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
@@ -699,8 +701,25 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     set_err("has_rank search but no raw vectors uploaded");
     return GB200_EINVAL;
   }
-  // splits: enough CTAs for ~2 waves of 148 SMs x 3 resident CTAs, merge buffer <= 8192 keys
+  // M = 32 kernel version and shape (tuning knobs are environment variables; defaults are the measured best)
+  int variant = 2, m32_threads = 256, pf_blocks = 4;
+  if (const char *e = getenv("GB200_SCAN_VARIANT")) variant = atoi(e);
+  if (const char *e = getenv("GB200_SCAN_THREADS")) m32_threads = atoi(e);
+  if (const char *e = getenv("GB200_SCAN_PF")) pf_blocks = atoi(e);
+  if (ix->mode != 1 || scan_buffer_cap(R) > 1024 || ix->smem_reserved != 1024) variant = 1;
+  // splits: each query is scanned by S CTAs (probes dealt round-robin).  v1: ~2 waves of 148 x 3 resident CTAs.
+  // v2: the S in 1..8 that best fills whole waves of resident CTAs, charging ~4 % of a CTA per extra split
+  // for the table load / final select, merge buffer <= 8192 keys
   int S = (148 * 3 * 2 + n - 1) / n;
+  if (variant == 2) {
+    const double slots = 148.0 * (m32_threads == 384 ? 2 : 3);
+    double best = -1.0;
+    for (int s = 1; s <= 8 && s <= nprobe; s++) {
+      const double waves = (double)n * s / slots;
+      const double eff = waves / std::ceil(waves) - 0.04 * (s - 1);
+      if (eff > best) best = eff, S = s;
+    }
+  }
   if (const char *es = getenv("GB200_SCAN_SPLITS")) S = atoi(es);  // tuning knob
   S = std::max(1, std::min(S, nprobe));
   while (S > 1 && (long long)S * R > 8192) S--;
@@ -746,8 +765,12 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     P.force_sym = (fs && fs[0] == '1') ? 1 : 0;
     const char *nt = getenv("GB200_SCAN_NO_TMA");
     P.no_tma = (nt && nt[0] == '1') ? 1 : 0;
-    const char *th = getenv("GB200_SCAN_THREADS");
-    P.m32_threads = th ? atoi(th) : 256;
+    P.m32_threads = m32_threads;
+    P.variant = variant;
+    P.pf_blocks = pf_blocks;
+    P.loop = 3;
+    if (const char *e = getenv("GB200_SCAN_LOOP")) P.loop = atoi(e);
+    P.probe_g = nullptr;
   }
   if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d): not implemented", scan_smem_bytes(P, ix->mode), M, R);
@@ -772,6 +795,12 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
     ix->launches++;
     P.lut_g = ix->ws_lut.as<float>();
+    if (variant == 2) {
+      CKI(ix->ws_probe.ensure((size_t)n * S * scan_probe_bytes_host(P.max_np_s)));
+      P.probe_g = ix->ws_probe.as<unsigned char>();
+      CK(launch_probe_setup(P, ix->stream));
+      ix->launches++;
+    }
   }
   CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));

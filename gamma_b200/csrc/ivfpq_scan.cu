@@ -88,6 +88,13 @@ struct ScanSmem {
   unsigned long long *mbar;
 };
 
+// bytes of the [ProbeInfo x max_np_s][blk_prefix x (max_np_s + 1)] region, padded to 16 so that one bulk copy
+// can fill it (the v2 kernel receives it precomputed from probe_setup_kernel)
+__host__ __device__ inline size_t scan_probe_bytes(int max_np_s) {
+  size_t b = (size_t)max_np_s * sizeof(ProbeInfo) + (size_t)(max_np_s + 1) * sizeof(int);
+  return (b + 15) & ~(size_t)15;
+}
+
 __device__ __forceinline__ ScanSmem carve(unsigned char *smem, const ScanParams &P, int mode) {
   ScanSmem S;
   S.lut = reinterpret_cast<float *>(smem);
@@ -98,23 +105,22 @@ __device__ __forceinline__ ScanSmem carve(unsigned char *smem, const ScanParams 
   o += (size_t)((P.d + 3) & ~3) * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   S.pinfo = reinterpret_cast<ProbeInfo *>(smem + o);
-  o += (size_t)P.max_np_s * sizeof(ProbeInfo);
-  S.blk_prefix = reinterpret_cast<int *>(smem + o);
-  o += (size_t)(P.max_np_s + 1) * sizeof(int);
-  o = (o + 7) & ~(size_t)7;
+  S.blk_prefix = reinterpret_cast<int *>(smem + o + (size_t)P.max_np_s * sizeof(ProbeInfo));
+  o += scan_probe_bytes(P.max_np_s);
   S.misc = reinterpret_cast<int *>(smem + o);  // [0..1] tau (u64), [2] cnt, [4..67] warp_part, [68..70] round flags
   o += (4 + 64 + 4) * sizeof(int);
   S.mbar = reinterpret_cast<unsigned long long *>(smem + o);
   return S;
 }
 
+size_t scan_probe_bytes_host(int max_np_s) { return scan_probe_bytes(max_np_s); }
+
 size_t scan_smem_bytes(const ScanParams &P, int mode) {
   size_t o = scan_lut_bytes(P.M, mode);
   o += (size_t)P.cap * sizeof(u64);
   o += (size_t)((P.d + 3) & ~3) * sizeof(float);
-  o = ((o + 15) & ~(size_t)15) + (size_t)P.max_np_s * sizeof(ProbeInfo);
-  o += (size_t)(P.max_np_s + 1) * sizeof(int);
-  o = ((o + 7) & ~(size_t)7) + (4 + 64 + 4) * sizeof(int);
+  o = ((o + 15) & ~(size_t)15) + scan_probe_bytes(P.max_np_s);
+  o += (4 + 64 + 4) * sizeof(int);
   o += 2 * sizeof(unsigned long long);
   return o;
 }
@@ -531,6 +537,509 @@ __global__ void __launch_bounds__(M32_THREADS, PER == 4 ? 3 : 1) ivfpq_scan_m32_
   if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
 }
 
+// =============================================================================================
+// M = 32 kernel, v2.  Same data structures and selection as above; what changed and why (profiles/r01a):
+//  * v1 issued 212 instructions per 32-posting block for 96 useful ones (PRMT + LDS + FADD per lookup): the
+//    prefetched block was copied register-to-register every iteration.  Here the 32 table addresses are formed
+//    first, which kills the code registers, and the NEXT block is loaded straight into those registers —
+//    no copies, still one block in flight per warp during the 32 lookups;
+//  * no periodic CTA barrier: warps meet only when the candidate buffer needs a prune (all of them see
+//    cnt > soft_limit within one block) and at the end — v1 spent 20 % of its issue stalls at barriers;
+//  * the probe table of the (query, split) — list extents, dis0, block prefix — is precomputed by
+//    probe_setup_kernel and arrives with the lookup table through the same mbarrier (one more bulk copy)
+//    instead of three dependent global round trips per CTA;
+//  * the posting stream is pulled towards L2 `pf` blocks ahead with prefetch.global.L2 (one
+//    instruction per block, one 128 B line per lane), so the register prefetch only has to cover L2 latency.
+// =============================================================================================
+__device__ __forceinline__ void l2_prefetch_line(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ uint32_t prmt_v(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_volatile_v4(const void *p) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(smem_u32(p)));
+  return r;
+}
+template <int S0>
+__device__ __forceinline__ float lds_raw(uint32_t off) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(GB_SMEM_RESERVED + 4 * S0));
+  return v;
+}
+
+template <bool IP, bool HAS_VALID, int WARPS, int PER>
+__device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
+                                                 const int total_blocks, const int np_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane4 = lane * 4;
+  const int per_warp = (total_blocks + WARPS - 1) / WARPS;
+  const int w0 = min(total_blocks, warp * per_warp);
+  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
+  const int soft_limit = P.cap - WARPS * 32;
+  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
+  const int pf = P.pf_blocks;
+
+  int pj = 0;
+  if (left > 0)
+    while (S.blk_prefix[pj + 1] <= w0) pj++;
+  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
+  uint32_t seq0 = 0;
+  float dis0 = 0.f;
+  const uint8_t *cptr = nullptr;
+  const int *iptr = nullptr;
+  const float *nptr = nullptr;
+  // L2 prefetch streams, one 128 B line per lane and block: lanes 0..7 the 1 KB of codes, lane 8 the ids,
+  // lane 9 the t(p) words (L2 metric only)
+  const char *pfp = nullptr;
+  const uint32_t pf_stride = lane < 8 ? 1024u : 128u;
+  const bool pf_lane = pf > 0 && lane < (IP ? 9 : 10);
+  auto stream_base = [&](const ProbeInfo &pi, int b_start) -> const char * {
+    const long long first = pi.off + (long long)b_start * 32;
+    return lane < 8 ? reinterpret_cast<const char *>(P.codes + (size_t)first * 32) + lane * 128
+                    : lane == 8 ? reinterpret_cast<const char *>(P.ids + first)
+                                : reinterpret_cast<const char *>(P.norms + first);
+  };
+  auto open_list = [&](int j, int b_start) {
+    const ProbeInfo pi = S.pinfo[j];
+    bl = ((pi.len + 31) >> 5) - b_start;
+    dis0 = pi.dis0;
+    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
+    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
+    const long long first = pi.off + (long long)b_start * 32;
+    cptr = P.codes + (size_t)first * 32 + lane * 16;
+    iptr = P.ids + first + lane;
+    nptr = P.norms + first + lane;
+    if (pf_lane) {
+      pfp = stream_base(pi, b_start) + (size_t)pf * pf_stride;  // steady state: block (current + pf)
+      // head of the NEXT list this warp will walk (its first blocks have no steady-state prefetch)
+      if (left > bl && j + 1 < np_s) {
+        const ProbeInfo pn = S.pinfo[j + 1];
+        const int nb = min(min((pn.len + 31) >> 5, pf), left - bl);
+        const char *h = stream_base(pn, 0);
+#pragma unroll 1
+  #pragma unroll 1
+      for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
+      }
+    }
+  };
+  if (left > 0) {
+    if (pf_lane) {  // head of this warp's first list
+      const ProbeInfo pi = S.pinfo[pj];
+      const int b0 = w0 - S.blk_prefix[pj];
+      const int nb = min(min(((pi.len + 31) >> 5) - b0, pf), left);
+      const char *h = stream_base(pi, b0);
+#pragma unroll 1
+      for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
+    }
+    open_list(pj, w0 - S.blk_prefix[pj]);
+  }
+
+  // the block in flight (per lane): 32 pre-rotated code bytes, vid, t(p), list dis0, scan-order word
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+  int id_n = -1;
+  float nrm_n = 0.f, base_n = 0.f;
+  uint32_t seq_n = 0xffffffffu;
+  auto issue_loads = [&]() {
+    if (left > 0) {  // warp-uniform
+      while (bl == 0) open_list(++pj, 0);
+      const uint4 v0 = ldg_nc_v4(cptr);
+      const uint4 v1 = ldg_nc_v4(cptr + 512);
+      c0 = v0.x, c1 = v0.y, c2 = v0.z, c3 = v0.w, c4 = v1.x, c5 = v1.y, c6 = v1.z, c7 = v1.w;
+      seq_n = seq0;
+      base_n = dis0;
+      id_n = -1;
+      nrm_n = 0.f;
+      if (len > 0) {
+        id_n = ldg_nc_s32(iptr);
+        if (!IP) nrm_n = ldg_nc_f32(nptr);
+      }
+      if (pf_lane) {
+        if (bl > pf) l2_prefetch_line(pfp);
+        pfp += pf_stride;
+      }
+      cptr += 1024;
+      iptr += 32;
+      nptr += 32;
+      seq0 += 32;
+      len -= 32;
+      bl--;
+      left--;
+    } else {
+      seq_n = 0xffffffffu;
+    }
+  };
+
+  u64 skey = 0;
+  bool spend = false;
+  auto try_append = [&](bool pass, u64 key) -> bool {
+    const unsigned m = __ballot_sync(GB_FULL, pass);
+    if (m == 0) return false;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
+    base = __shfl_sync(GB_FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    bool pending = pass;
+    if (pass && slot < topr.cap) {
+      topr.buf[slot] = key;
+      pending = false;
+    }
+    spend = pending;
+    skey = key;
+    return __any_sync(GB_FULL, pending);
+  };
+
+  bool stalled = false;
+  issue_loads();
+  int round = 0;
+  for (;;) {
+    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
+    bool over = false;
+    while (!stalled && !over && seq_n != 0xffffffffu) {  // warp-uniform
+      // ---- A: the 32 table addresses (code << 8 | lane * 4); the code registers die here
+      uint32_t a[32];
+#define GB_ADDR4(W, I)                     \
+  a[I + 0] = prmt_v(W, lane4, 0x5504);     \
+  a[I + 1] = prmt_v(W, lane4, 0x5514);     \
+  a[I + 2] = prmt_v(W, lane4, 0x5524);     \
+  a[I + 3] = prmt_v(W, lane4, 0x5534);
+      GB_ADDR4(c0, 0) GB_ADDR4(c1, 4) GB_ADDR4(c2, 8) GB_ADDR4(c3, 12)
+      GB_ADDR4(c4, 16) GB_ADDR4(c5, 20) GB_ADDR4(c6, 24) GB_ADDR4(c7, 28)
+#undef GB_ADDR4
+      const int id = id_n;
+      const uint32_t seq = seq_n;
+      const float nb = base_n + nrm_n;
+      uint32_t vw = 0xffffffffu;
+      if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
+      // ---- B: next block straight into the registers just freed
+      issue_loads();
+      // ---- C: 32 conflict-free lookups, four accumulation chains
+      float s0, s1, s2, s3;
+      s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
+#define GB_LOOK4(I)                  \
+  s0 += lds_raw<I + 0>(a[I + 0]);    \
+  s1 += lds_raw<I + 1>(a[I + 1]);    \
+  s2 += lds_raw<I + 2>(a[I + 2]);    \
+  s3 += lds_raw<I + 3>(a[I + 3]);
+      GB_LOOK4(4) GB_LOOK4(8) GB_LOOK4(12) GB_LOOK4(16) GB_LOOK4(20) GB_LOOK4(24) GB_LOOK4(28)
+#undef GB_LOOK4
+      // ---- D: filter, key, admission
+      // {tau, cnt} in one 16-byte read: every warp notices within one block that a prune is wanted, whether
+      // or not it has anything to append itself
+      const uint4 tc = lds_volatile_v4(S.misc);
+      const float dis = nb + ((s0 + s1) + (s2 + s3));
+      bool ok = id >= 0;
+      if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
+      const uint32_t k32 = dist_to_key32<IP>(dis);
+      const bool pass = ok && (dis == dis) && k32 <= tc.y;  // cheap pre-test on the distance word
+      over = (int)tc.z > soft_limit;
+      if (__any_sync(GB_FULL, pass)) {
+        const u64 key = ((u64)k32 << 32) | seq;
+        stalled = try_append(pass && key < (((u64)tc.y << 32) | tc.x), key);
+      }
+    }
+    const bool more = stalled || seq_n != 0xffffffffu;
+    over = over || stalled;
+    const int slot = round % 3;
+    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
+    __syncthreads();
+    const int v = flags[slot];
+    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
+    round++;
+    if (v & 1) {
+      long long tp0 = clock64();
+      topr.prune_collective<PER>();
+      if (P.timing && threadIdx.x == 0) {
+        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
+        atomicAdd(P.timing + 5, 1ull);
+      }
+    }
+    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
+    if (!(v & 2)) break;
+  }
+}
+
+// v3 loop: TWO blocks in flight per warp.  Measured on v2 (profiles/r01b): with one 1.25 KB block in flight per
+// warp and 24 warps per SM the scan is latency bound (30 KB in flight per SM ~ 3 TB/s at ~1.5 us loaded latency),
+// not issue bound.  Here each warp keeps two register sets X / Y that are consumed alternately; a set is
+// refilled (next-but-one block) as soon as its code registers are dead.  To pay for the second set the 32
+// table addresses are formed 16 at a time and the three per-lane stream pointers became two 32-bit indices
+// (address = base + index * size is one IMAD.WIDE).
+struct Blk {
+  uint32_t c0, c1, c2, c3, c4, c5, c6, c7;  // 32 pre-rotated code bytes of this lane's posting
+  int id;                                    // vid, < 0 = padding / dead / beyond the list end
+  float nrm, base;                           // t(p), dis0 of the list
+  uint32_t seq;                              // (probe rank << 21) | position ; 0xffffffff = no block
+};
+
+template <bool IP, bool HAS_VALID, int WARPS, int PER>
+__device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
+                                                 const int total_blocks, const int np_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane4 = lane * 4;
+  const int per_warp = (total_blocks + WARPS - 1) / WARPS;
+  const int w0 = min(total_blocks, warp * per_warp);
+  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
+  const int soft_limit = P.cap - WARPS * 32;
+  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
+
+  int pj = 0;
+  if (left > 0)
+    while (S.blk_prefix[pj + 1] <= w0) pj++;
+  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
+  uint32_t seq0 = 0;
+  float dis0 = 0.f;
+  uint32_t qi = 0, ri = 0;  // this lane's 16-byte code slot / posting index in the pools
+  auto open_list = [&](int j, int b_start) {
+    const ProbeInfo pi = S.pinfo[j];
+    bl = ((pi.len + 31) >> 5) - b_start;
+    dis0 = pi.dis0;
+    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
+    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
+    const uint32_t first = (uint32_t)pi.off + (uint32_t)b_start * 32u;  // pool < 2^31 postings (host checks)
+    qi = first * 2u + lane;  // block of 32 postings = 64 slots of 16 B: chunk j of posting `lane` at slot j*32 + lane
+    ri = first + lane;
+  };
+  if (left > 0) open_list(pj, w0 - S.blk_prefix[pj]);
+
+  auto issue_loads = [&](Blk &b) {
+    if (left > 0) {  // warp-uniform
+      while (bl == 0) open_list(++pj, 0);
+      const uint8_t *cp = P.codes + (size_t)qi * 16;
+      const uint4 v0 = ldg_nc_v4(cp);
+      const uint4 v1 = ldg_nc_v4(cp + 512);
+      b.c0 = v0.x, b.c1 = v0.y, b.c2 = v0.z, b.c3 = v0.w, b.c4 = v1.x, b.c5 = v1.y, b.c6 = v1.z, b.c7 = v1.w;
+      b.seq = seq0;
+      b.base = dis0;
+      b.id = -1;
+      b.nrm = 0.f;
+      if (len > 0) {
+        b.id = ldg_nc_s32(P.ids + ri);
+        if (!IP) b.nrm = ldg_nc_f32(P.norms + ri);
+      }
+      qi += 64;
+      ri += 32;
+      seq0 += 32;
+      len -= 32;
+      bl--;
+      left--;
+    } else {
+      b.seq = 0xffffffffu;
+    }
+  };
+
+  u64 skey = 0;
+  bool spend = false;
+  auto try_append = [&](bool pass, u64 key) -> bool {
+    const unsigned m = __ballot_sync(GB_FULL, pass);
+    if (m == 0) return false;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
+    base = __shfl_sync(GB_FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    bool pending = pass;
+    if (pass && slot < topr.cap) {
+      topr.buf[slot] = key;
+      pending = false;
+    }
+    spend = pending;
+    skey = key;
+    return __any_sync(GB_FULL, pending);
+  };
+
+  bool stalled = false, over = false;
+  // look up block b, refill its registers with the next-but-one block, append what passes
+  auto consume = [&](Blk &b) {
+    uint32_t a[16];
+    float s0, s1, s2, s3;
+#define GB_ADDR4(W, I)                   \
+  a[I + 0] = prmt_v(W, lane4, 0x5504);   \
+  a[I + 1] = prmt_v(W, lane4, 0x5514);   \
+  a[I + 2] = prmt_v(W, lane4, 0x5524);   \
+  a[I + 3] = prmt_v(W, lane4, 0x5534);
+#define GB_LOOK4(I, O)               \
+  s0 += lds_raw<O + 0>(a[I + 0]);    \
+  s1 += lds_raw<O + 1>(a[I + 1]);    \
+  s2 += lds_raw<O + 2>(a[I + 2]);    \
+  s3 += lds_raw<O + 3>(a[I + 3]);
+    GB_ADDR4(b.c0, 0) GB_ADDR4(b.c1, 4) GB_ADDR4(b.c2, 8) GB_ADDR4(b.c3, 12)
+    s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
+    GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
+    GB_ADDR4(b.c4, 0) GB_ADDR4(b.c5, 4) GB_ADDR4(b.c6, 8) GB_ADDR4(b.c7, 12)
+    const int id = b.id;
+    const uint32_t seq = b.seq;
+    const float nb = b.base + b.nrm;
+    uint32_t vw = 0xffffffffu;
+    if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
+    issue_loads(b);  // the code registers are dead: refill them
+    GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
+#undef GB_ADDR4
+#undef GB_LOOK4
+    const uint4 tc = lds_volatile_v4(S.misc);  // {tau, cnt}
+    const float dis = nb + ((s0 + s1) + (s2 + s3));
+    bool ok = id >= 0;
+    if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
+    const uint32_t k32 = dist_to_key32<IP>(dis);
+    const bool pass = ok && (dis == dis) && k32 <= tc.y;  // cheap pre-test on the distance word
+    over = (int)tc.z > soft_limit;
+    if (__any_sync(GB_FULL, pass)) {
+      const u64 key = ((u64)k32 << 32) | seq;
+      stalled = try_append(pass && key < (((u64)tc.y << 32) | tc.x), key);
+    }
+  };
+
+  Blk X, Y;
+  X.c0 = X.c1 = X.c2 = X.c3 = X.c4 = X.c5 = X.c6 = X.c7 = 0, X.id = -1, X.nrm = X.base = 0.f;
+  Y = X;
+  issue_loads(X);
+  issue_loads(Y);
+  int round = 0, phase = 0;
+  for (;;) {
+    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
+    over = false;
+    for (;;) {  // warp-uniform control flow; blocks are consumed X, Y, X, Y, ... in stream order
+      if (phase == 0) {
+        if (stalled || over || X.seq == 0xffffffffu) break;
+        consume(X);
+        phase = 1;
+      }
+      if (stalled || over || Y.seq == 0xffffffffu) break;
+      consume(Y);
+      phase = 0;
+    }
+    const bool more = stalled || (phase == 0 ? X.seq : Y.seq) != 0xffffffffu;
+    over = over || stalled;
+    const int slot = round % 3;
+    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
+    __syncthreads();
+    const int v = flags[slot];
+    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
+    round++;
+    if (v & 1) {
+      long long tp0 = clock64();
+      topr.prune_collective<PER>();
+      if (P.timing && threadIdx.x == 0) {
+        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
+        atomicAdd(P.timing + 5, 1ull);
+      }
+    }
+    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
+    if (!(v & 2)) break;
+  }
+}
+
+template <bool IP, int THREADS, int MINB, int PER>
+__global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanParams P) {
+  constexpr int WARPS = THREADS / 32;
+  long long t_last = clock64();
+  const int q = P.order ? P.order[blockIdx.y] : blockIdx.y;
+  const int split = blockIdx.x, tid = threadIdx.x;
+  ScanSmem S = carve(gb_scan_smem, P, 1);
+  BlockTopR topr = make_topr(S, P);
+  if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
+  const int np_s = (P.nprobe - split + P.S - 1) / P.S;
+  if (tid == 0) {
+    *topr.cnt = 0;
+    *topr.tau = GB_KEY_MAX;
+    S.misc[68] = S.misc[69] = S.misc[70] = 0;
+    mbar_init(&S.mbar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the query's table [256][64] (lut_build_m32_kernel, L2 resident) and this (query, split)'s probe table
+    // (probe_setup_kernel) land in shared memory through one mbarrier
+    const uint32_t pbytes = (uint32_t)scan_probe_bytes(P.max_np_s);
+    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
+    mbar_expect_tx(&S.mbar[0], 65536u + pbytes);
+    tma_bulk_g2s(S.pinfo, P.probe_g + ((size_t)q * P.S + split) * pbytes, pbytes, &S.mbar[0]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
+  }
+  __syncthreads();  // mbarrier initialised before anyone polls it
+  mbar_wait(&S.mbar[0], 0);
+  GB_TICK(0);  // wait for the tables
+  const int total_blocks = S.blk_prefix[np_s];
+  if (P.loop == 2) {
+    if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
+    else scan_loop_m32_v2<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  } else {
+    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
+    else scan_loop_m32_v3<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  }
+  GB_TICK(2);  // scan loop incl. in-loop prunes
+  write_survivors<PER>(topr, P, q, split);
+  GB_TICK(3);  // final prune + write
+  if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
+}
+
+// K2b — probe tables for the v2 kernel: one warp per (query, split) writes, in the kernel's shared-memory
+// layout, [ProbeInfo x max_np_s][exclusive prefix of 32-posting block counts x (max_np_s + 1)]:
+// scan_one_list's list lookup (gamma_index_ivfpq.cc:597-640) and dis0 of precompute_list_tables
+// (gamma_index_ivfpq.h:216-230, 236-299) hoisted out of the scan.
+__global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (item >= P.n * P.S) return;
+  const int q = item / P.S, split = item - q * P.S;
+  const int np_s = (P.nprobe - split + P.S - 1) / P.S;
+  const size_t pbytes = scan_probe_bytes(P.max_np_s);
+  unsigned char *dst = P.probe_g + (size_t)item * pbytes;
+  ProbeInfo *pinfo = reinterpret_cast<ProbeInfo *>(dst);
+  int *prefix = reinterpret_cast<int *>(dst + (size_t)P.max_np_s * sizeof(ProbeInfo));
+  const float *xq = P.xq + (size_t)q * P.d;
+  int carry = 0;
+  unsigned my_postings = 0;
+  for (int j0 = 0; j0 < np_s; j0 += 32) {
+    const int j = j0 + lane;
+    ProbeInfo pi;
+    pi.off = 0, pi.len = 0, pi.rank = 0, pi.dis0 = 0.f;
+    if (j < np_s) {
+      const int p = split + j * P.S;
+      const int key = P.keys[(size_t)q * P.nprobe + p];
+      pi.rank = p;
+      if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
+        pi.off = P.list_off[key];
+        pi.len = P.list_len[key];
+        if (P.is_ip) {  // dis0 = <q, centroid>
+          const float *cen = P.centroids + (size_t)key * P.d;
+          float s = 0.f;
+          for (int i = 0; i < P.d; i++) s = fmaf(__ldg(xq + i), __ldg(cen + i), s);
+          pi.dis0 = s;
+        } else {
+          pi.dis0 = P.coarse_dis[(size_t)q * P.nprobe + p];
+        }
+      }
+      pinfo[j] = pi;
+    }
+    const int nb = (pi.len + 31) >> 5;
+    int incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(GB_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (j < np_s) prefix[j] = carry + incl - nb;
+    carry += __shfl_sync(GB_FULL, incl, 31);
+    my_postings += (unsigned)pi.len;
+  }
+  my_postings = __reduce_add_sync(GB_FULL, my_postings);
+  if (lane == 0) {
+    prefix[np_s] = carry;
+    if (P.scanned) atomicAdd(P.scanned, (unsigned long long)my_postings);
+  }
+}
+
+cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st) {
+  const int items = P.n * P.S;
+  probe_setup_kernel<<<(items + 7) / 8, 256, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
 // K2a — per-query lookup tables for the M = 32 kernel: lut_g[q][c][m] = lut_g[q][c][32 + m] =
 // scale * <q_m, cb[m][c]>  (scale = -2 for L2, +1 for InnerProduct): QueryTables::init_query /
 // ProductQuantizer::compute_inner_prod_table (gamma_index_ivfpq.h:148-168, faiss ProductQuantizer.cpp:504-530).
@@ -633,9 +1142,23 @@ static cudaError_t launch_m32(const ScanParams &P, cudaStream_t st) {
                  : launch_kernel(ivfpq_scan_m32_kernel<false, T, PER>, P, 1, T, &conf[1], st);
 }
 
+template <int T, int MINB>
+static cudaError_t launch_m32_v2(const ScanParams &P, cudaStream_t st) {
+  static size_t conf[2] = {0, 0};
+  return P.is_ip ? launch_kernel(ivfpq_scan_m32_v2_kernel<true, T, MINB, 4>, P, 1, T, &conf[0], st)
+                 : launch_kernel(ivfpq_scan_m32_v2_kernel<false, T, MINB, 4>, P, 1, T, &conf[1], st);
+}
+
+// v2 needs: cap <= 1024 (4 keys per thread in the select), the probe tables, and dynamic shared memory at
+// shared-window offset GB_SMEM_RESERVED (checked by the host with cudaDevAttrReservedSharedMemoryPerBlock)
+bool scan_m32_v2_usable(const ScanParams &P) { return P.cap <= 1024 && P.probe_g != nullptr; }
+int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads == 384 ? 2 : 3; }
+
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
   if (mode == 1) {
+    if (P.variant == 2 && scan_m32_v2_usable(P))
+      return P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
     if (P.cap > 4 * 256) return launch_m32<256, 16>(P, st);  // large recall_num: 16 keys per thread in the select
     switch (P.m32_threads) {
       case 384: return launch_m32<384, 4>(P, st);

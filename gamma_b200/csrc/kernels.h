@@ -39,7 +39,15 @@ struct ScanParams {
   int m32_threads;          // tuning: CTA size of the M = 32 kernel (256 / 320 / 384)
   int no_tma;               // tuning: build the table with plain LDG instead of TMA-staged chunks
   int force_sym;            // debug: take the symbol-addressed LDS path even when the raw one is valid
+  int variant;              // M = 32: 2 = v2 kernel (precomputed probe tables, in-place prefetch), 1 = v1
+  int pf_blocks;            // v2 loop: L2 prefetch distance in 32-posting blocks (0 = off)
+  int loop;                 // v2 kernel: 3 = two blocks in flight per warp (default), 2 = one block + L2 prefetch
+  unsigned char *probe_g;   // v2: [n][S][scan_probe_bytes(max_np_s)] from launch_probe_setup
 };
+size_t scan_probe_bytes_host(int max_np_s);
+cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st);
+bool scan_m32_v2_usable(const ScanParams &P);
+int scan_m32_v2_ctas_per_sm(const ScanParams &P);
 size_t scan_smem_bytes(const ScanParams &P, int mode);
 int scan_buffer_cap(int R);
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);
