@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgamma_b200.so")
+LIB_PATH = os.environ.get("GB200_LIB") or os.path.join(_HERE, "lib", "libgamma_b200.so")  # GB200_LIB: dev A/B builds
 
 METRIC_IP, METRIC_L2 = 0, 1
 FLT_MAX = float(np.finfo(np.float32).max)

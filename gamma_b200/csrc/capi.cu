@@ -80,6 +80,9 @@ struct gb200_index {
   int dsub = 0, chunk = 0, layout = 0, mode = 0;
   int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the v2 scan's LDS immediates assume 1024)
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: per-query lookup tables are built while the coarse quantiser runs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
   std::mutex mu;
   bool trained = false;
 
@@ -111,7 +114,7 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe, ws_items, ws_nsplit;
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
@@ -154,6 +157,9 @@ static int common_create(gb200_index *ix) {
   }
   ix->smem_reserved = (int)prop.reservedSharedMemPerBlock;
   CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ix->ev[i]));
   CK(cudaMalloc(&ix->d_scanned, sizeof(unsigned long long)));
   CK(cudaMemset(ix->d_scanned, 0, sizeof(unsigned long long)));
@@ -232,10 +238,13 @@ int gb200_destroy(gb200_index *ix) {
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe, &ix->ws_items, &ix->ws_nsplit};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 4; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  if (ix->stream2) cudaStreamDestroy(ix->stream2);
+  if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+  if (ix->ev_join) cudaEventDestroy(ix->ev_join);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
   return GB200_OK;
@@ -706,19 +715,45 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   if (const char *e = getenv("GB200_SCAN_VARIANT")) variant = atoi(e);
   if (const char *e = getenv("GB200_SCAN_THREADS")) m32_threads = atoi(e);
   if (const char *e = getenv("GB200_SCAN_PF")) pf_blocks = atoi(e);
-  if (ix->mode != 1 || scan_buffer_cap(R) > 1024 || ix->smem_reserved != 1024) variant = 1;
+  if (m32_threads != 256 && m32_threads != 384 && m32_threads != 512) m32_threads = 256;
+  // candidate buffer: the v2 kernel with 512 threads keeps 2048 keys (its 16 warps admit up to 512 per round)
+  int cap = scan_buffer_cap(R);
+  if (variant == 2 && m32_threads == 512 && cap < 2048) cap = 2048;
+  if (ix->mode != 1 || cap > 4 * m32_threads || cap > 2048 || ix->smem_reserved != 1024) {
+    variant = 1;
+    cap = scan_buffer_cap(R);
+  }
   // splits: each query is scanned by S CTAs (probes dealt round-robin).  v1: ~2 waves of 148 x 3 resident CTAs.
   // v2: the S in 1..8 that best fills whole waves of resident CTAs, charging ~4 % of a CTA per extra split
   // for the table load / final select, merge buffer <= 8192 keys
   int S = (148 * 3 * 2 + n - 1) / n;
   if (variant == 2) {
-    const double slots = 148.0 * (m32_threads == 384 ? 2 : 3);
+    const double slots = 148.0 * (m32_threads >= 384 ? 2 : 3);
     double best = -1.0;
     for (int s = 1; s <= 8 && s <= nprobe; s++) {
       const double waves = (double)n * s / slots;
       const double eff = waves / std::ceil(waves) - 0.04 * (s - 1);
       if (eff > best) best = eff, S = s;
     }
+  }
+  // v2 work plan: heaviest queries first, one CTA each; only the queries of the last partial wave of resident CTAs
+  // are split (s_tail ways) so the launch ends on short items.  Batches smaller than one wave are split uniformly.
+  bool plan = variant == 2 && n <= 4096 && !getenv("GB200_SCAN_SPLITS") && !getenv("GB200_SCAN_NOPLAN");
+  int n_full = 0, s_tail = 1, n_items = 0;
+  if (plan) {
+    const int slots = 148 * (m32_threads >= 384 ? 2 : 3);
+    if (n >= slots) {
+      n_full = (n / slots) * slots;
+      const int n_tail = n - n_full;
+      s_tail = n_tail ? std::max(1, std::min(std::min(8, nprobe), slots / n_tail)) : 1;
+    } else {
+      s_tail = S;
+    }
+    if (const char *e = getenv("GB200_SCAN_TAIL")) s_tail = atoi(e);
+    s_tail = std::max(1, std::min(s_tail, nprobe));
+    while (s_tail > 1 && (long long)s_tail * R > 8192) s_tail--;
+    n_items = n_full + (n - n_full) * s_tail;
+    S = (n_full == n) ? 1 : s_tail;  // candidate rows per query
   }
   if (const char *es = getenv("GB200_SCAN_SPLITS")) S = atoi(es);  // tuning knob
   S = std::max(1, std::min(S, nprobe));
@@ -756,9 +791,13 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   P.nprobe = nprobe;
   P.S = S;
   P.R = R;
-  P.cap = scan_buffer_cap(R);
+  P.cap = cap;
   P.chunk = ix->chunk;
-  P.max_np_s = (nprobe + S - 1) / S;
+  P.max_np_s = (plan && n_full > 0) ? nprobe : (nprobe + S - 1) / S;
+  P.items = nullptr;
+  P.n_items = 0;
+  P.n_full = 0;
+  P.s_tail = 1;
   P.is_ip = ip ? 1 : 0;
   {
     const char *fs = getenv("GB200_SCAN_FORCE_SYM");
@@ -768,8 +807,6 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     P.m32_threads = m32_threads;
     P.variant = variant;
     P.pf_blocks = pf_blocks;
-    P.loop = 3;
-    if (const char *e = getenv("GB200_SCAN_LOOP")) P.loop = atoi(e);
     P.probe_g = nullptr;
   }
   if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {
@@ -791,12 +828,31 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
       set_err("M=32 kernel: d=%d > 1024 not implemented", ix->p.d);
       return GB200_EUNSUPPORTED;
     }
-    CKI(ix->ws_lut.ensure((size_t)n * 65536));
-    CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
-    ix->launches++;
+    if (ix->lut_built_n == n && ix->lut_built_ip == (ip ? 1 : 0)) {
+      CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));  // built on the side stream during the coarse stage
+    } else {
+      CKI(ix->ws_lut.ensure((size_t)n * 65536));
+      CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
+      ix->launches++;
+    }
+    ix->lut_built_n = 0;
     P.lut_g = ix->ws_lut.as<float>();
     if (variant == 2) {
-      CKI(ix->ws_probe.ensure((size_t)n * S * scan_probe_bytes_host(P.max_np_s)));
+      if (plan) {
+        P.n_items = n_items;
+        P.n_full = n_full;
+        P.s_tail = s_tail;
+      }
+      if (plan && getenv("GB200_SCAN_SORTED")) {  // optional: heaviest queries first (costs a single-CTA sort)
+        CKI(ix->ws_items.ensure((size_t)n_items * sizeof(int4)));
+        CKI(ix->ws_nsplit.ensure((size_t)n * sizeof(int)));
+        CK(launch_plan_items(d_keys, ix->d_len, n, nprobe, ix->p.nlist, n_full, s_tail, ix->ws_items.as<int4>(),
+                             ix->ws_nsplit.as<int>(), ix->stream));
+        ix->launches++;
+        P.items = ix->ws_items.as<int4>();
+        P.n_items = n_items;
+      }
+      CKI(ix->ws_probe.ensure((size_t)(plan ? n_items : n * S) * scan_probe_bytes_host(P.max_np_s)));
       P.probe_g = ix->ws_probe.as<unsigned char>();
       CK(launch_probe_setup(P, ix->stream));
       ix->launches++;
@@ -825,6 +881,8 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   Q.is_ip = ip ? 1 : 0;
   Q.min_score = sp->min_score;
   Q.max_score = sp->max_score;
+  Q.nsplit = P.items ? ix->ws_nsplit.as<int>() : nullptr;
+  Q.n_full = (P.n_items > 0 && !P.items) ? P.n_full : 0;
   CK(launch_rerank(Q, ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[3], ix->stream));
   ix->launches += 2;
@@ -892,6 +950,19 @@ static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on
   CKI(ix->ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
   CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
+  ix->lut_built_n = 0;
+  if (ix->mode == 1 && d <= 1024 && !keys_h && !getenv("GB200_LUT_INLINE")) {
+    // K2a depends on the queries only: fork it onto the side stream so it overlaps the coarse quantiser
+    const int ipm = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
+    CKI(ix->ws_lut.ensure((size_t)n * 65536));
+    CK(cudaEventRecord(ix->ev_fork, ix->stream));
+    CK(cudaStreamWaitEvent(ix->stream2, ix->ev_fork, 0));
+    CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
+    CK(cudaEventRecord(ix->ev_join, ix->stream2));
+    ix->launches++;
+    ix->lut_built_n = n;
+    ix->lut_built_ip = ipm;
+  }
   if (keys_h) {
     std::vector<int> k32((size_t)n * nprobe);
     for (size_t i = 0; i < k32.size(); i++) k32[i] = (keys_h[i] < 0 || keys_h[i] >= ix->p.nlist) ? -1 : (int)keys_h[i];

@@ -702,16 +702,25 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
     if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
     bool over = false;
     while (!stalled && !over && seq_n != 0xffffffffu) {  // warp-uniform
-      // ---- A: the 32 table addresses (code << 8 | lane * 4); the code registers die here
-      uint32_t a[32];
+      // ---- A/C: table addresses (code << 8 | lane * 4) 16 at a time (keeps the kernel at 64 registers so that
+      // 32 warps fit on an SM), 32 conflict-free lookups on four accumulation chains.  The second half's
+      // addresses kill the code registers, which are then refilled with the NEXT block (B).
+      uint32_t a[16];
+      float s0, s1, s2, s3;
 #define GB_ADDR4(W, I)                     \
   a[I + 0] = prmt_v(W, lane4, 0x5504);     \
   a[I + 1] = prmt_v(W, lane4, 0x5514);     \
   a[I + 2] = prmt_v(W, lane4, 0x5524);     \
   a[I + 3] = prmt_v(W, lane4, 0x5534);
+#define GB_LOOK4(I, O)               \
+  s0 += lds_raw<O + 0>(a[I + 0]);    \
+  s1 += lds_raw<O + 1>(a[I + 1]);    \
+  s2 += lds_raw<O + 2>(a[I + 2]);    \
+  s3 += lds_raw<O + 3>(a[I + 3]);
       GB_ADDR4(c0, 0) GB_ADDR4(c1, 4) GB_ADDR4(c2, 8) GB_ADDR4(c3, 12)
-      GB_ADDR4(c4, 16) GB_ADDR4(c5, 20) GB_ADDR4(c6, 24) GB_ADDR4(c7, 28)
-#undef GB_ADDR4
+      s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
+      GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
+      GB_ADDR4(c4, 0) GB_ADDR4(c5, 4) GB_ADDR4(c6, 8) GB_ADDR4(c7, 12)
       const int id = id_n;
       const uint32_t seq = seq_n;
       const float nb = base_n + nrm_n;
@@ -719,202 +728,39 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
       if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
       // ---- B: next block straight into the registers just freed
       issue_loads();
-      // ---- C: 32 conflict-free lookups, four accumulation chains
-      float s0, s1, s2, s3;
-      s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
-#define GB_LOOK4(I)                  \
-  s0 += lds_raw<I + 0>(a[I + 0]);    \
-  s1 += lds_raw<I + 1>(a[I + 1]);    \
-  s2 += lds_raw<I + 2>(a[I + 2]);    \
-  s3 += lds_raw<I + 3>(a[I + 3]);
-      GB_LOOK4(4) GB_LOOK4(8) GB_LOOK4(12) GB_LOOK4(16) GB_LOOK4(20) GB_LOOK4(24) GB_LOOK4(28)
+      GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
+#undef GB_ADDR4
 #undef GB_LOOK4
       // ---- D: filter, key, admission
+#ifndef GB_OVER_MODE
+#define GB_OVER_MODE 2
+#endif
+#if GB_OVER_MODE == 1
       // {tau, cnt} in one 16-byte read: every warp notices within one block that a prune is wanted, whether
       // or not it has anything to append itself
       const uint4 tc = lds_volatile_v4(S.misc);
+      const uint32_t tau_hi = tc.y;
+      over = (int)tc.z > soft_limit;  // view from before this block's own append: enough to notice a wanted prune
+#elif GB_OVER_MODE == 2
+      const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
+      over = *((volatile int *)topr.cnt) > soft_limit;
+#else
+      const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
+#endif
       const float dis = nb + ((s0 + s1) + (s2 + s3));
       bool ok = id >= 0;
       if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
       const uint32_t k32 = dist_to_key32<IP>(dis);
-      const bool pass = ok && (dis == dis) && k32 <= tc.y;  // cheap pre-test on the distance word
-      over = (int)tc.z > soft_limit;
+      const bool pass = ok && (dis == dis) && k32 <= tau_hi;  // cheap pre-test on the distance word
       if (__any_sync(GB_FULL, pass)) {
         const u64 key = ((u64)k32 << 32) | seq;
-        stalled = try_append(pass && key < (((u64)tc.y << 32) | tc.x), key);
+        stalled = try_append(pass && key < topr.threshold(), key);
+        // appenders re-read the counter after their own atomicAdd: a warp starts a block only while
+        // cnt <= cap - 32 * WARPS, so the buffer cannot overflow between sync points
+        over = over || *((volatile int *)topr.cnt) > soft_limit;
       }
     }
     const bool more = stalled || seq_n != 0xffffffffu;
-    over = over || stalled;
-    const int slot = round % 3;
-    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
-    __syncthreads();
-    const int v = flags[slot];
-    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
-    round++;
-    if (v & 1) {
-      long long tp0 = clock64();
-      topr.prune_collective<PER>();
-      if (P.timing && threadIdx.x == 0) {
-        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
-        atomicAdd(P.timing + 5, 1ull);
-      }
-    }
-    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
-    if (!(v & 2)) break;
-  }
-}
-
-// v3 loop: TWO blocks in flight per warp.  Measured on v2 (profiles/r01b): with one 1.25 KB block in flight per
-// warp and 24 warps per SM the scan is latency bound (30 KB in flight per SM ~ 3 TB/s at ~1.5 us loaded latency),
-// not issue bound.  Here each warp keeps two register sets X / Y that are consumed alternately; a set is
-// refilled (next-but-one block) as soon as its code registers are dead.  To pay for the second set the 32
-// table addresses are formed 16 at a time and the three per-lane stream pointers became two 32-bit indices
-// (address = base + index * size is one IMAD.WIDE).
-struct Blk {
-  uint32_t c0, c1, c2, c3, c4, c5, c6, c7;  // 32 pre-rotated code bytes of this lane's posting
-  int id;                                    // vid, < 0 = padding / dead / beyond the list end
-  float nrm, base;                           // t(p), dis0 of the list
-  uint32_t seq;                              // (probe rank << 21) | position ; 0xffffffff = no block
-};
-
-template <bool IP, bool HAS_VALID, int WARPS, int PER>
-__device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
-                                                 const int total_blocks, const int np_s) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lane4 = lane * 4;
-  const int per_warp = (total_blocks + WARPS - 1) / WARPS;
-  const int w0 = min(total_blocks, warp * per_warp);
-  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
-  const int soft_limit = P.cap - WARPS * 32;
-  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
-
-  int pj = 0;
-  if (left > 0)
-    while (S.blk_prefix[pj + 1] <= w0) pj++;
-  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
-  uint32_t seq0 = 0;
-  float dis0 = 0.f;
-  uint32_t qi = 0, ri = 0;  // this lane's 16-byte code slot / posting index in the pools
-  auto open_list = [&](int j, int b_start) {
-    const ProbeInfo pi = S.pinfo[j];
-    bl = ((pi.len + 31) >> 5) - b_start;
-    dis0 = pi.dis0;
-    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
-    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
-    const uint32_t first = (uint32_t)pi.off + (uint32_t)b_start * 32u;  // pool < 2^31 postings (host checks)
-    qi = first * 2u + lane;  // block of 32 postings = 64 slots of 16 B: chunk j of posting `lane` at slot j*32 + lane
-    ri = first + lane;
-  };
-  if (left > 0) open_list(pj, w0 - S.blk_prefix[pj]);
-
-  auto issue_loads = [&](Blk &b) {
-    if (left > 0) {  // warp-uniform
-      while (bl == 0) open_list(++pj, 0);
-      const uint8_t *cp = P.codes + (size_t)qi * 16;
-      const uint4 v0 = ldg_nc_v4(cp);
-      const uint4 v1 = ldg_nc_v4(cp + 512);
-      b.c0 = v0.x, b.c1 = v0.y, b.c2 = v0.z, b.c3 = v0.w, b.c4 = v1.x, b.c5 = v1.y, b.c6 = v1.z, b.c7 = v1.w;
-      b.seq = seq0;
-      b.base = dis0;
-      b.id = -1;
-      b.nrm = 0.f;
-      if (len > 0) {
-        b.id = ldg_nc_s32(P.ids + ri);
-        if (!IP) b.nrm = ldg_nc_f32(P.norms + ri);
-      }
-      qi += 64;
-      ri += 32;
-      seq0 += 32;
-      len -= 32;
-      bl--;
-      left--;
-    } else {
-      b.seq = 0xffffffffu;
-    }
-  };
-
-  u64 skey = 0;
-  bool spend = false;
-  auto try_append = [&](bool pass, u64 key) -> bool {
-    const unsigned m = __ballot_sync(GB_FULL, pass);
-    if (m == 0) return false;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
-    base = __shfl_sync(GB_FULL, base, leader);
-    const int slot = base + __popc(m & ((1u << lane) - 1u));
-    bool pending = pass;
-    if (pass && slot < topr.cap) {
-      topr.buf[slot] = key;
-      pending = false;
-    }
-    spend = pending;
-    skey = key;
-    return __any_sync(GB_FULL, pending);
-  };
-
-  bool stalled = false, over = false;
-  // look up block b, refill its registers with the next-but-one block, append what passes
-  auto consume = [&](Blk &b) {
-    uint32_t a[16];
-    float s0, s1, s2, s3;
-#define GB_ADDR4(W, I)                   \
-  a[I + 0] = prmt_v(W, lane4, 0x5504);   \
-  a[I + 1] = prmt_v(W, lane4, 0x5514);   \
-  a[I + 2] = prmt_v(W, lane4, 0x5524);   \
-  a[I + 3] = prmt_v(W, lane4, 0x5534);
-#define GB_LOOK4(I, O)               \
-  s0 += lds_raw<O + 0>(a[I + 0]);    \
-  s1 += lds_raw<O + 1>(a[I + 1]);    \
-  s2 += lds_raw<O + 2>(a[I + 2]);    \
-  s3 += lds_raw<O + 3>(a[I + 3]);
-    GB_ADDR4(b.c0, 0) GB_ADDR4(b.c1, 4) GB_ADDR4(b.c2, 8) GB_ADDR4(b.c3, 12)
-    s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
-    GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
-    GB_ADDR4(b.c4, 0) GB_ADDR4(b.c5, 4) GB_ADDR4(b.c6, 8) GB_ADDR4(b.c7, 12)
-    const int id = b.id;
-    const uint32_t seq = b.seq;
-    const float nb = b.base + b.nrm;
-    uint32_t vw = 0xffffffffu;
-    if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
-    issue_loads(b);  // the code registers are dead: refill them
-    GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
-#undef GB_ADDR4
-#undef GB_LOOK4
-    const uint4 tc = lds_volatile_v4(S.misc);  // {tau, cnt}
-    const float dis = nb + ((s0 + s1) + (s2 + s3));
-    bool ok = id >= 0;
-    if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
-    const uint32_t k32 = dist_to_key32<IP>(dis);
-    const bool pass = ok && (dis == dis) && k32 <= tc.y;  // cheap pre-test on the distance word
-    over = (int)tc.z > soft_limit;
-    if (__any_sync(GB_FULL, pass)) {
-      const u64 key = ((u64)k32 << 32) | seq;
-      stalled = try_append(pass && key < (((u64)tc.y << 32) | tc.x), key);
-    }
-  };
-
-  Blk X, Y;
-  X.c0 = X.c1 = X.c2 = X.c3 = X.c4 = X.c5 = X.c6 = X.c7 = 0, X.id = -1, X.nrm = X.base = 0.f;
-  Y = X;
-  issue_loads(X);
-  issue_loads(Y);
-  int round = 0, phase = 0;
-  for (;;) {
-    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
-    over = false;
-    for (;;) {  // warp-uniform control flow; blocks are consumed X, Y, X, Y, ... in stream order
-      if (phase == 0) {
-        if (stalled || over || X.seq == 0xffffffffu) break;
-        consume(X);
-        phase = 1;
-      }
-      if (stalled || over || Y.seq == 0xffffffffu) break;
-      consume(Y);
-      phase = 0;
-    }
-    const bool more = stalled || (phase == 0 ? X.seq : Y.seq) != 0xffffffffu;
     over = over || stalled;
     const int slot = round % 3;
     if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
@@ -939,12 +785,32 @@ template <bool IP, int THREADS, int MINB, int PER>
 __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanParams P) {
   constexpr int WARPS = THREADS / 32;
   long long t_last = clock64();
-  const int q = P.order ? P.order[blockIdx.y] : blockIdx.y;
-  const int split = blockIdx.x, tid = threadIdx.x;
+  // work item = (query, split, number of splits of that query): either the plan of plan_items_kernel (heaviest
+  // queries first and unsplit, the queries of the last partial wave split so that it fills the machine) or the
+  // plain (split, query) grid
+  int q, split, nsp;
+  size_t item;
+  if (P.n_items > 0) {
+    item = blockIdx.x;
+    if (P.items) {
+      const int4 it = P.items[blockIdx.x];
+      q = it.x, split = it.y, nsp = it.z;
+    } else if ((int)blockIdx.x < P.n_full) {
+      q = blockIdx.x, split = 0, nsp = 1;
+    } else {
+      const int t = blockIdx.x - P.n_full;
+      q = P.n_full + t / P.s_tail, split = t % P.s_tail, nsp = P.s_tail;
+    }
+  } else {
+    q = P.order ? P.order[blockIdx.y] : blockIdx.y;
+    split = blockIdx.x, nsp = P.S;
+    item = (size_t)q * P.S + split;
+  }
+  const int tid = threadIdx.x;
   ScanSmem S = carve(gb_scan_smem, P, 1);
   BlockTopR topr = make_topr(S, P);
   if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
-  const int np_s = (P.nprobe - split + P.S - 1) / P.S;
+  const int np_s = (P.nprobe - split + nsp - 1) / nsp;
   if (tid == 0) {
     *topr.cnt = 0;
     *topr.tau = GB_KEY_MAX;
@@ -956,7 +822,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanPa
     const uint32_t pbytes = (uint32_t)scan_probe_bytes(P.max_np_s);
     const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
     mbar_expect_tx(&S.mbar[0], 65536u + pbytes);
-    tma_bulk_g2s(S.pinfo, P.probe_g + ((size_t)q * P.S + split) * pbytes, pbytes, &S.mbar[0]);
+    tma_bulk_g2s(S.pinfo, P.probe_g + item * pbytes, pbytes, &S.mbar[0]);
 #pragma unroll
     for (int i = 0; i < 4; i++)
       tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
@@ -965,15 +831,12 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanPa
   mbar_wait(&S.mbar[0], 0);
   GB_TICK(0);  // wait for the tables
   const int total_blocks = S.blk_prefix[np_s];
-  if (P.loop == 2) {
-    if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
-    else scan_loop_m32_v2<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
-  } else {
-    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
-    else scan_loop_m32_v3<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
-  }
+  if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  else scan_loop_m32_v2<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
   GB_TICK(2);  // scan loop incl. in-loop prunes
   write_survivors<PER>(topr, P, q, split);
+  if (split == 0)  // an unsplit (or less split) query leaves the other slots of its [S][R] candidate row empty
+    for (int i = nsp * P.R + tid; i < P.S * P.R; i += THREADS) P.cand[(size_t)q * P.S * P.R + i] = GB_KEY_MAX;
   GB_TICK(3);  // final prune + write
   if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
 }
@@ -984,9 +847,22 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanPa
 // (gamma_index_ivfpq.h:216-230, 236-299) hoisted out of the scan.
 __global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (item >= P.n * P.S) return;
-  const int q = item / P.S, split = item - q * P.S;
-  const int np_s = (P.nprobe - split + P.S - 1) / P.S;
+  if (item >= (P.n_items > 0 ? P.n_items : P.n * P.S)) return;
+  int q, split, nsp;
+  if (P.items) {
+    const int4 it = P.items[item];
+    q = it.x, split = it.y, nsp = it.z;
+  } else if (P.n_items > 0) {
+    if (item < P.n_full) {
+      q = item, split = 0, nsp = 1;
+    } else {
+      const int t = item - P.n_full;
+      q = P.n_full + t / P.s_tail, split = t % P.s_tail, nsp = P.s_tail;
+    }
+  } else {
+    q = item / P.S, split = item - q * P.S, nsp = P.S;
+  }
+  const int np_s = (P.nprobe - split + nsp - 1) / nsp;
   const size_t pbytes = scan_probe_bytes(P.max_np_s);
   unsigned char *dst = P.probe_g + (size_t)item * pbytes;
   ProbeInfo *pinfo = reinterpret_cast<ProbeInfo *>(dst);
@@ -999,7 +875,7 @@ __global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
     ProbeInfo pi;
     pi.off = 0, pi.len = 0, pi.rank = 0, pi.dis0 = 0.f;
     if (j < np_s) {
-      const int p = split + j * P.S;
+      const int p = split + j * nsp;
       const int key = P.keys[(size_t)q * P.nprobe + p];
       pi.rank = p;
       if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
@@ -1035,7 +911,7 @@ __global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
 }
 
 cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st) {
-  const int items = P.n * P.S;
+  const int items = P.n_items > 0 ? P.n_items : P.n * P.S;
   probe_setup_kernel<<<(items + 7) / 8, 256, 0, st>>>(P);
   return cudaGetLastError();
 }
@@ -1105,6 +981,51 @@ __global__ void __launch_bounds__(1024) query_order_kernel(const int *__restrict
   for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (int)(unsigned)k[i];
 }
 
+// K2c — work plan of one batch (single CTA, n <= 4096): queries sorted by the number of postings they will scan,
+// heaviest first (longest-processing-time order); the first n_full of them become one work item each, the
+// remaining n - n_full (the last, partial wave of resident CTAs) are cut into s_tail items each so that the
+// tail of the launch is made of short items that fill the machine.  nsplit[q] tells the re-rank how many
+// candidate rows the query has.
+__global__ void __launch_bounds__(1024) plan_items_kernel(const int *__restrict__ keys, const int *__restrict__ list_len,
+                                                          int n, int nprobe, int nlist, int p2, int n_full, int s_tail,
+                                                          int4 *__restrict__ items, int *__restrict__ nsplit) {
+  extern __shared__ __align__(16) unsigned char osm[];
+  u64 *k = reinterpret_cast<u64 *>(osm);
+  for (int q = threadIdx.x; q < p2; q += blockDim.x) {
+    u64 key = GB_KEY_MAX;
+    if (q < n) {
+      unsigned w = 0;
+      for (int p = 0; p < nprobe; p++) {
+        int key_l = keys[(size_t)q * nprobe + p];
+        if (key_l >= 0 && key_l < nlist) w += (unsigned)list_len[key_l];
+      }
+      key = ((u64)(~w) << 32) | (unsigned)q;
+    }
+    k[q] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort(k, p2);
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int q = (int)(unsigned)k[r];
+    if (r < n_full) {
+      items[r] = make_int4(q, 0, 1, 0);
+      nsplit[q] = 1;
+    } else {
+      for (int s = 0; s < s_tail; s++) items[n_full + (r - n_full) * s_tail + s] = make_int4(q, s, s_tail, 0);
+      nsplit[q] = s_tail;
+    }
+  }
+}
+
+cudaError_t launch_plan_items(const int *keys, const int *list_len, int n, int nprobe, int nlist, int n_full, int s_tail,
+                              int4 *items, int *nsplit, cudaStream_t st) {
+  int p2 = next_pow2(n);
+  if (p2 > 4096) return cudaErrorInvalidValue;
+  plan_items_kernel<<<1, 1024, (size_t)p2 * sizeof(u64), st>>>(keys, list_len, n, nprobe, nlist, p2, n_full, s_tail, items,
+                                                               nsplit);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_query_order(const int *keys, const int *list_len, int n, int nprobe, int nlist, int *order,
                                cudaStream_t st) {
   int p2 = next_pow2(n);
@@ -1131,6 +1052,7 @@ static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int th
     *configured = smem;
   }
   dim3 grid(P.S, P.n);
+  if (P.n_items > 0) grid = dim3(P.n_items, 1);
   kernel<<<grid, threads, smem, st>>>(P);
   return cudaGetLastError();
 }
@@ -1151,14 +1073,15 @@ static cudaError_t launch_m32_v2(const ScanParams &P, cudaStream_t st) {
 
 // v2 needs: cap <= 1024 (4 keys per thread in the select), the probe tables, and dynamic shared memory at
 // shared-window offset GB_SMEM_RESERVED (checked by the host with cudaDevAttrReservedSharedMemoryPerBlock)
-bool scan_m32_v2_usable(const ScanParams &P) { return P.cap <= 1024 && P.probe_g != nullptr; }
-int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads == 384 ? 2 : 3; }
+bool scan_m32_v2_usable(const ScanParams &P) { return P.cap <= 4 * P.m32_threads && P.probe_g != nullptr; }
+int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads >= 384 ? 2 : 3; }
 
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
   if (mode == 1) {
     if (P.variant == 2 && scan_m32_v2_usable(P))
-      return P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
+      return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)
+             : P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
     if (P.cap > 4 * 256) return launch_m32<256, 16>(P, st);  // large recall_num: 16 keys per thread in the select
     switch (P.m32_threads) {
       case 384: return launch_m32<384, 4>(P, st);

@@ -41,9 +41,13 @@ struct ScanParams {
   int force_sym;            // debug: take the symbol-addressed LDS path even when the raw one is valid
   int variant;              // M = 32: 2 = v2 kernel (precomputed probe tables, in-place prefetch), 1 = v1
   int pf_blocks;            // v2 loop: L2 prefetch distance in 32-posting blocks (0 = off)
-  int loop;                 // v2 kernel: 3 = two blocks in flight per warp (default), 2 = one block + L2 prefetch
-  unsigned char *probe_g;   // v2: [n][S][scan_probe_bytes(max_np_s)] from launch_probe_setup
+  unsigned char *probe_g;   // v2: [items][scan_probe_bytes(max_np_s)] from launch_probe_setup
+  const int4 *items;        // v2: work plan (query, split, splits of that query, 0) from launch_plan_items, or nullptr
+  int n_items;              //     > 0: grid = n_items work items; S is then the row count of cand per query.  With items ==
+  int n_full, s_tail;       //     nullptr the plan is positional: query q < n_full is one item, the others s_tail items each
 };
+cudaError_t launch_plan_items(const int *keys, const int *list_len, int n, int nprobe, int nlist, int n_full, int s_tail,
+                              int4 *items, int *nsplit, cudaStream_t st);
 size_t scan_probe_bytes_host(int max_np_s);
 cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st);
 bool scan_m32_v2_usable(const ScanParams &P);
@@ -102,6 +106,8 @@ struct RerankParams {
   long long *out_ids;       // [n][k]
   int n, S, R, k, nprobe, raw_d, xq_stride, has_rank, is_ip;
   float min_score, max_score;
+  const int *nsplit;        // optional [n]: candidate rows the query really has (<= S); nullptr = S ...
+  int n_full;               // ... or, when > 0 (positional plan), 1 row for q < n_full and S rows otherwise
 };
 cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st);
 
