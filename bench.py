@@ -380,7 +380,7 @@ def main():
         evs[i][1].record(stream)
         ix.sync()  # host sync so the per-stage event times of this step can be read
         st = ix.last_stage_ms()
-        scan_ms.append(st["scan"])
+        scan_ms.append(ix.last_scan_kernel_ms())
         for k_ in stage_acc:
             stage_acc[k_] += st[k_] / args.steps
         scanned = ix.last_scanned_postings()
@@ -472,7 +472,8 @@ def main():
     scan_avg_ms = float(np.mean(scan_ms))
     achieved = alg_bytes / (scan_avg_ms / 1e3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel="ivfpq_scan_kernel", algorithmic_bytes_per_launch=alg_bytes,
+                    kernel=("ivfpq_scan_m32_v2_kernel" if w["M"] == 32 else "ivfpq_scan_generic_kernel") + " (CUDA events around that one launch on the search stream)",
+                    algorithmic_bytes_per_launch=alg_bytes,
                     scanned_postings_per_launch=scanned, kernel_ms=scan_avg_ms, peak_source=peak_src,
                     stage_ms=stage_acc)
     tr = os.path.join(ROOT, "profiles", "scan_traffic.json")

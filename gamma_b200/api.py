@@ -44,7 +44,7 @@ EXPORTS = [
     "gb200_ivfpq_get_list", "gb200_upload_raw", "gb200_raw_count", "gb200_set_deleted",
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
-    "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_sync",
+    "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
     "gb200_debug_select",
 ]
 
@@ -91,6 +91,8 @@ def lib():
         L.gb200_launch_count.argtypes = [C.c_void_p]
         L.gb200_last_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
+        L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
         L.gb200_debug_select.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p]
@@ -197,6 +199,9 @@ class _Base:
         out = (C.c_float * 4)()
         lib().gb200_last_stage_ms(self.h, out)
         return dict(coarse=out[0], scan=out[1], rerank=out[2], total=out[3])
+
+    def last_scan_kernel_ms(self):
+        return float(lib().gb200_last_scan_kernel_ms(self.h))
 
     @staticmethod
     def _sp(metric, nprobe, recall_num, has_rank, min_score, max_score):

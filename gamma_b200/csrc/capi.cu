@@ -119,8 +119,9 @@ struct gb200_index {
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
   bool profiling = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4, 5 bracket the scan kernel alone
   float stage_ms[4] = {0, 0, 0, 0};
+  float scan_kernel_ms = 0;
 
   long long doc_bits() const { return std::max(max_vid + 1, raw_n); }
 };
@@ -160,7 +161,7 @@ static int common_create(gb200_index *ix) {
   CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
-  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ix->ev[i]));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ix->ev[i]));
   CK(cudaMalloc(&ix->d_scanned, sizeof(unsigned long long)));
   CK(cudaMemset(ix->d_scanned, 0, sizeof(unsigned long long)));
   return GB200_OK;
@@ -240,7 +241,7 @@ int gb200_destroy(gb200_index *ix) {
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
                     &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe, &ix->ws_items, &ix->ws_nsplit};
   for (DevBuf *b : bufs) b->release();
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 6; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
   if (ix->stream2) cudaStreamDestroy(ix->stream2);
   if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
@@ -858,7 +859,9 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
       ix->launches++;
     }
   }
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[4], ix->stream));
   CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
+  if (ix->profiling) CK(cudaEventRecord(ix->ev[5], ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));
   RerankParams Q;
   Q.cand = P.cand;
@@ -909,6 +912,7 @@ static int finish_profile(gb200_index *ix) {
     cudaEventElapsedTime(&ix->stage_ms[1], ix->ev[1], ix->ev[2]);
     cudaEventElapsedTime(&ix->stage_ms[2], ix->ev[2], ix->ev[3]);
     cudaEventElapsedTime(&ix->stage_ms[3], ix->ev[0], ix->ev[3]);
+    cudaEventElapsedTime(&ix->scan_kernel_ms, ix->ev[4], ix->ev[5]);
   }
   return GB200_OK;
 }
@@ -1279,6 +1283,8 @@ int gb200_last_stage_ms(gb200_index *ix, float *out4) {
   for (int i = 0; i < 4; i++) out4[i] = ix->stage_ms[i];
   return GB200_OK;
 }
+float gb200_last_scan_kernel_ms(gb200_index *ix) { return ix ? ix->scan_kernel_ms : 0.f; }
+
 int gb200_sync(gb200_index *ix) {
   if (!ix) return GB200_EINVAL;
   std::lock_guard<std::mutex> g(ix->mu);

@@ -253,10 +253,119 @@ __global__ void __launch_bounds__(CW_THREADS) coarse_select_row_kernel(const flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant of the row select for nlist <= 256 * 4 * V (16384 at V = 16): the row is read from
+// HBM/L2 exactly once (V independent 16-byte loads per thread) and both passes run on registers.  Pass 1 is a
+// plain float minimum (NaN -> +inf), tau0 = the largest of the G group minima as a VALUE (every column with a
+// value <= tau0 survives, which is a superset of the key-based bound), pass 2 appends the ~G ln G survivors with
+// one shared atomic each (rare), ranking as above.  The bisection fallback (survivors overflow the buffer,
+// e.g. thousands of equal distances) runs on the 64-bit keys so that it terminates on ties.
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(CW_THREADS, 2) coarse_select_reg_kernel(const float *__restrict__ dist, int nlist,
+                                                                       int nprobe, int G, int *__restrict__ keys,
+                                                                       float *__restrict__ coarse_dis) {
+  __shared__ u64 cand[CW_CAP];
+  __shared__ float gminf[CW_THREADS];
+  __shared__ float s_tauf;
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x;
+  const float *row = dist + (size_t)q * nlist;
+  const float INF = __int_as_float(0x7f800000);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; i++) {
+    const int c = (i * CW_THREADS + tid) * 4;
+    v[i] = c < nlist ? __ldg(reinterpret_cast<const float4 *>(row + c)) : make_float4(INF, INF, INF, INF);
+  }
+  float m = INF;
+#pragma unroll
+  for (int i = 0; i < V; i++) {
+    v[i].x = v[i].x == v[i].x ? v[i].x : INF;  // NaN never selected (cw_key gives it the neutral key)
+    v[i].y = v[i].y == v[i].y ? v[i].y : INF;
+    v[i].z = v[i].z == v[i].z ? v[i].z : INF;
+    v[i].w = v[i].w == v[i].w ? v[i].w : INF;
+    m = fminf(m, fminf(fminf(v[i].x, v[i].y), fminf(v[i].z, v[i].w)));
+  }
+  gminf[tid] = m;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (tid < 32) {  // fold the 256 thread minima into G group minima, tau0 = their maximum
+    float t = -INF;
+    for (int g = tid; g < G; g += 32) {
+      float gm = INF;
+      for (int j = g; j < CW_THREADS; j += G) gm = fminf(gm, gminf[j]);
+      t = fmaxf(t, gm);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t = fmaxf(t, __shfl_xor_sync(GB_FULL, t, o));
+    if (tid == 0) s_tauf = t;
+  }
+  __syncthreads();
+  const float tauf = s_tauf;  // +inf: some group has no usable value, every finite column survives
+  auto visit = [&](float x, int c) {
+    if (x <= tauf && x < INF) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      if (slot < CW_CAP) cand[slot] = ((u64)float_to_ordered(x) << 32) | (uint32_t)c;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < V; i++) {
+    const int c = (i * CW_THREADS + tid) * 4;
+    visit(v[i].x, c), visit(v[i].y, c + 1), visit(v[i].z, c + 2), visit(v[i].w, c + 3);
+  }
+  __syncthreads();
+  int cnt = s_cnt;
+  if (cnt > CW_CAP) {  // slow path: bisection on the key space
+    u64 lo_b = 0, hi_b = ((u64)float_to_ordered(tauf) << 32) | 0xffffffffu, tau = hi_b;
+    for (int attempt = 0; attempt < 130; attempt++) {
+      tau = lo_b + (hi_b - lo_b) / 2;
+      __syncthreads();
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int c = tid; c < nlist; c += CW_THREADS) {  // rare path: re-read the row (L2) instead of unrolling over registers
+        const u64 key = cw_key(row[c], c);
+        if (key != GB_KEY_MAX && key <= tau) {
+          const int slot = atomicAdd(&s_cnt, 1);
+          if (slot < CW_CAP) cand[slot] = key;
+        }
+      }
+      __syncthreads();
+      cnt = s_cnt;
+      if (cnt <= CW_CAP && cnt >= nprobe) break;
+      if (cnt > CW_CAP) hi_b = tau;
+      else lo_b = tau + 1;
+    }
+  }
+  const int c = min(cnt, CW_CAP);
+  for (int i = tid; i < c; i += CW_THREADS) {  // rank by counting; survivors are unique keys
+    const u64 k = cand[i];
+    int r = 0;
+    for (int j = 0; j < c; j++) r += cand[j] < k;
+    if (r < nprobe) {
+      keys[(size_t)q * nprobe + r] = (int)(uint32_t)k;
+      coarse_dis[(size_t)q * nprobe + r] = ordered_to_float((uint32_t)(k >> 32));
+    }
+  }
+  for (int r = c + tid; r < nprobe; r += CW_THREADS) {  // "not enough centroids": key -1
+    keys[(size_t)q * nprobe + r] = -1;
+    coarse_dis[(size_t)q * nprobe + r] = 3.402823466e38f;
+  }
+}
+
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys, float *coarse_dis,
                                  cudaStream_t st) {
   if (nprobe <= 128 && !getenv("GB200_COARSE_SELECT_CTA")) {
     const int G = nprobe <= 32 ? 32 : (nprobe <= 64 ? 64 : 128);
+    const bool aligned = (nlist & 3) == 0 && ((uintptr_t)dist & 15) == 0;
+    if (aligned && nlist <= CW_THREADS * 4 * 16 && nlist >= nprobe && !getenv("GB200_COARSE_SELECT_ROW")) {
+      if (nlist <= CW_THREADS * 4 * 4)
+        coarse_select_reg_kernel<4><<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G, keys, coarse_dis);
+      else
+        coarse_select_reg_kernel<16><<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G, keys, coarse_dis);
+      return cudaGetLastError();
+    }
     coarse_select_row_kernel<<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G, keys, coarse_dis);
     return cudaGetLastError();
   }

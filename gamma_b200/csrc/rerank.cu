@@ -90,6 +90,16 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
     vids[i] = vid;
   }
   __syncthreads();
+  if (P.has_rank) {  // pull the candidates' raw rows towards L2 now; the distance loop below then runs on L2 latency
+    const int lines = (P.raw_d * 4 + 127) >> 7;
+    const int nr = min(P.R, p2_r);
+    for (int i = tid; i < nr * lines; i += RR_THREADS) {
+      const int c = i / lines, l = i - c * lines;
+      const int vid = vids[c];
+      if (vid >= 0 && (long long)vid < P.nraw)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.raw + (size_t)vid * P.raw_d + l * 32));
+    }
+  }
 
   float *od = P.out_dist + (size_t)q * P.k;
   long long *oi = P.out_ids + (size_t)q * P.k;

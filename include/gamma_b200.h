@@ -166,6 +166,9 @@ int64_t gb200_launch_count(gb200_index *ix);
  * out[0]=coarse, out[1]=scan, out[2]=merge/rerank, out[3]=total.                        */
 int gb200_last_stage_ms(gb200_index *ix, float *out4);
 int gb200_set_profiling(gb200_index *ix, int enable);
+/* device time (ms) of the ADC scan kernel alone in the last IVFPQ search (CUDA events around that one launch on the
+ * search stream; profiling must be enabled) — the duration bench.py divides the algorithmic bytes by.            */
+float gb200_last_scan_kernel_ms(gb200_index *ix);
 /* wait for the index's stream (after *_dev calls) and refresh the counters above.          */
 int gb200_sync(gb200_index *ix);
 
