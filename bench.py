@@ -323,22 +323,23 @@ def main():
 
     dev = torch.device(device)
     xq_d = torch.from_numpy(xq).to(dev)
-    D_d = torch.empty(n, K_TOP, dtype=torch.float32, device=dev)
-    I_d = torch.empty(n, K_TOP, dtype=torch.int64, device=dev)
+    # distances and ids of one rank live in ONE buffer ([n*k] f32 followed by [n*k] i64) so that the multi-GPU
+    # exchange is a single all-gather (two small collectives cost ~35 us of launch latency each)
+    from gamma_b200 import dist as gdist
+    out_d, D_d, I_d = gdist.packed_topk_buffer(n, K_TOP, dev)
+    out_bytes = out_d.numel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
     if world > 1:
         import torch.distributed as dist
-        D_all = torch.empty(world * n, K_TOP, dtype=torch.float32, device=dev)
-        I_all = torch.empty(world * n, K_TOP, dtype=torch.int64, device=dev)
+        out_all = torch.empty(world * out_bytes, dtype=torch.uint8, device=dev)  # rank r's block at r * out_bytes
 
     def step_dev():
         rc_ = ix.search_dev(xq_d.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
                             nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
         assert rc_ == 0, api.lib().gb200_last_error()
         if world > 1:
-            dist.all_gather_into_tensor(D_all, D_d)
-            dist.all_gather_into_tensor(I_all, I_d)
+            dist.all_gather_into_tensor(out_all, out_d)
 
     # correctness side: recall@10 vs exact ground truth (and the raw result for the CPU cross-check)
     step_dev()
@@ -390,7 +391,7 @@ def main():
     clocks = sampler.stop()
     launches = ix.launch_count() - launches0
     if world > 1:
-        launches += 2 * args.steps  # the two NCCL all-gathers per step
+        launches += args.steps  # the NCCL all-gather per step
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:

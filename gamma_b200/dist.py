@@ -20,22 +20,44 @@ def shard_queries(xq, rank=None, world=None):
     return xq[lo:hi], lo, hi
 
 
-def allgather_topk(D_local, I_local, n_total=None):
-    """every rank gets the full [n_total, k] result in query order.  Equal shards use
-    all_gather_into_tensor (one NCCL collective per tensor); ragged shards pad to the largest."""
+def packed_topk_buffer(n_local, k, device):
+    """one buffer for a rank's result: [n_local*k] f32 distances followed by [n_local*k] i64 ids.  Searching
+    straight into its two views (bench.py does) makes the exchange a single collective with no packing copy."""
+    buf = torch.empty(n_local * k * 12, dtype=torch.uint8, device=device)
+    D = buf[: n_local * k * 4].view(torch.float32).view(n_local, k)
+    I = buf[n_local * k * 4:].view(torch.int64).view(n_local, k)
+    return buf, D, I
+
+
+def unpack_topk(buf_all, world, n_local, k):
+    per = n_local * k * 12
+    blocks = buf_all.view(world, per)
+    D = blocks[:, : n_local * k * 4].contiguous().view(torch.float32).view(world * n_local, k)
+    I = blocks[:, n_local * k * 4:].contiguous().view(torch.int64).view(world * n_local, k)
+    return D, I
+
+
+def allgather_topk(D_local, I_local, equal_shards=None):
+    """every rank gets the full [n_total, k] result in query order.  Equal shards: distances and ids travel in
+    ONE all_gather_into_tensor of a packed byte buffer; ragged shards pad to the largest.  equal_shards=True
+    skips the size exchange (the caller knows, e.g. a fixed batch per rank)."""
     world = dist.get_world_size()
     k = D_local.shape[1]
-    n_local = torch.tensor([D_local.shape[0]], device=D_local.device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local)
-    sizes = [int(s.item()) for s in sizes]
+    if equal_shards is None:
+        n_local = torch.tensor([D_local.shape[0]], device=D_local.device, dtype=torch.int64)
+        sizes = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(sizes, n_local)
+        sizes = [int(s.item()) for s in sizes]
+    else:
+        sizes = [D_local.shape[0]] * world
     mx = max(sizes)
     if all(s == mx for s in sizes):
-        D_all = torch.empty(world * mx, k, dtype=D_local.dtype, device=D_local.device)
-        I_all = torch.empty(world * mx, k, dtype=I_local.dtype, device=I_local.device)
-        dist.all_gather_into_tensor(D_all, D_local.contiguous())
-        dist.all_gather_into_tensor(I_all, I_local.contiguous())
-        return D_all, I_all
+        buf, D, I = packed_topk_buffer(mx, k, D_local.device)
+        D.copy_(D_local)
+        I.copy_(I_local)
+        buf_all = torch.empty(world * buf.numel(), dtype=torch.uint8, device=D_local.device)
+        dist.all_gather_into_tensor(buf_all, buf)
+        return unpack_topk(buf_all, world, mx, k)
     Dp = torch.zeros(mx, k, dtype=D_local.dtype, device=D_local.device)
     Ip = torch.full((mx, k), -1, dtype=I_local.dtype, device=I_local.device)
     Dp[:D_local.shape[0]] = D_local

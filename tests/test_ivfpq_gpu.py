@@ -90,6 +90,37 @@ def test_full_search_with_rerank(fx, metric):
     assert same.mean() > 0.995
 
 
+def test_large_batch_work_plan_parity(monkeypatch):
+    """More queries than resident CTA slots (148 SMs x 3): the scan runs its positional work plan — full waves of
+    unsplit queries, the queries of the last partial wave split over several CTAs and merged by the re-rank —
+    and must still reproduce the CPU engine; the plain (uniform-split) grid and the v1 kernel must agree with it."""
+    from gamma_b200 import synth
+    f = fx_l2_m32()
+    ix = f.mirror()
+    nprobe, R, k = 16, 100, 10
+    xq = synth.mixture(1100, f.d, synth.SEED_QUERY + 5, n_clusters=128)
+    D_ref, I_ref = f.ref.search(xq, k, rj(nprobe, R, "L2"), has_rank=True)
+    rc, D, I = ix.Search(xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=True)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+    same = I_ref == I
+    assert np.array_equal(D_ref[same], D[same]) and same.mean() > 0.995
+    # split (tail) queries and unsplit ones alike
+    assert (I_ref[900:] == I[900:]).mean() > 0.995
+    for env in ({"GB200_SCAN_NOPLAN": "1"}, {"GB200_SCAN_VARIANT": "1"}, {"GB200_SCAN_THREADS": "512"}):
+        for kk, vv in env.items():
+            monkeypatch.setenv(kk, vv)
+        rc, D2, I2 = ix.Search(xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=True)
+        for kk in env:
+            monkeypatch.delenv(kk)
+        assert rc == 0 and np.array_equal(I2, I) and np.array_equal(D2, D), env
+    # has_rank = False: the ADC distances themselves, merged across the split CTAs
+    D_ref, I_ref = f.ref.search(xq, k, rj(nprobe, R, "L2"), has_rank=False)
+    rc, D, I = ix.Search(xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=False)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5, max_bad_frac=0.002)
+
+
 def test_filters_and_deletions_inside_the_scan():
     from gamma_b200 import synth
     f = fx_l2_m32()
