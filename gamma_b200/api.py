@@ -41,7 +41,7 @@ _lib = None
 EXPORTS = [
     "gb200_last_error", "gb200_device_count", "gb200_ivfpq_create", "gb200_flat_create", "gb200_destroy",
     "gb200_ivfpq_set_quantizers", "gb200_ivfpq_append", "gb200_ivfpq_update", "gb200_ivfpq_list_sizes",
-    "gb200_ivfpq_get_list", "gb200_upload_raw", "gb200_raw_count", "gb200_set_deleted",
+    "gb200_ivfpq_get_list", "gb200_upload_raw", "gb200_upload_raw_dev", "gb200_raw_count", "gb200_set_deleted",
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
@@ -66,6 +66,7 @@ def lib():
         L.gb200_ivfpq_list_sizes.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_get_list.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.gb200_upload_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.gb200_upload_raw_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.gb200_raw_count.restype = C.c_int64
         L.gb200_raw_count.argtypes = [C.c_void_p]
         L.gb200_set_deleted.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
@@ -169,6 +170,11 @@ class _Base:
         if first_vid is None:
             first_vid = lib().gb200_raw_count(self.h)
         _check(lib().gb200_upload_raw(self.h, int(first_vid), x.shape[0], x.ctypes.data), "upload_raw")
+
+    def upload_raw_dev(self, ptr, n, first_vid=None):
+        if first_vid is None:
+            first_vid = lib().gb200_raw_count(self.h)
+        _check(lib().gb200_upload_raw_dev(self.h, int(first_vid), int(n), C.c_void_p(ptr)), "upload_raw_dev")
 
     def set_deleted(self, docids, deleted=True):
         ids = np.ascontiguousarray(docids, dtype=np.int64).reshape(-1)

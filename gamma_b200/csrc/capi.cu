@@ -489,7 +489,7 @@ int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t
 }
 
 // ---- raw vectors -----------------------------------------------------------------------
-int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x) {
+static int upload_raw_impl(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, cudaMemcpyKind kind) {
   if (!ix || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
   if (n == 0) return GB200_OK;
   std::lock_guard<std::mutex> g(ix->mu);
@@ -508,13 +508,19 @@ int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float 
     ix->d_raw = nr;
     ix->raw_cap = ncap;
   }
-  CK(cudaMemcpyAsync(ix->d_raw + (size_t)first_vid * rd, x, (size_t)n * rd * sizeof(float), cudaMemcpyHostToDevice,
-                     ix->stream));
+  CK(cudaMemcpyAsync(ix->d_raw + (size_t)first_vid * rd, x, (size_t)n * rd * sizeof(float), kind, ix->stream));
   CK(cudaStreamSynchronize(ix->stream));
   if (need > ix->raw_n) ix->raw_n = need;
   if (first_vid < ix->aux_n) ix->aux_n = first_vid;  // companions of the rewritten rows are stale
   ix->nodel_valid_dirty = true;
   return GB200_OK;
+}
+
+int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x) {
+  return upload_raw_impl(ix, first_vid, n, x, cudaMemcpyHostToDevice);
+}
+int gb200_upload_raw_dev(gb200_index *ix, int64_t first_vid, int64_t n, const float *x_dev) {
+  return upload_raw_impl(ix, first_vid, n, x_dev, cudaMemcpyDeviceToDevice);
 }
 
 int64_t gb200_raw_count(gb200_index *ix) { return ix ? ix->raw_n : 0; }
@@ -1096,6 +1102,7 @@ static int flat_tc_dev(gb200_index *ix, int n, const float *d_xq, int k, const g
   ix->launches += 2;
   long long nc_max = ((1LL << 26) / n) & ~127LL;  // distance tile <= 256 MB
   if (nc_max < 1024) nc_max = 1024;
+  if (const char *e = getenv("GB200_FLAT_CHUNK_ROWS")) nc_max = std::max(1024LL, (long long)atoll(e) & ~127LL);  // tests: force many chunks
   if (nc_max > ix->raw_n) nc_max = (ix->raw_n + 127) & ~127LL;
   CKI(ix->ws_dist.ensure((size_t)n * nc_max * sizeof(float)));
   const int Kp = flat_tc_candidates(k);

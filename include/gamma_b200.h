@@ -113,6 +113,8 @@ int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t
  * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are
  * implicit = first_vid .. first_vid+n-1; re-upload of an existing range = UpdateToStore. */
 int gb200_upload_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x);
+/* same, rows already in device memory (a loader that decodes on the GPU, bench tooling)  */
+int gb200_upload_raw_dev(gb200_index *ix, int64_t first_vid, int64_t n, const float *x_dev);
 int64_t gb200_raw_count(gb200_index *ix);
 
 /* ---- deleted-docs bitmap: bitmap::BitmapManager::Set/Unset (util/bitmap_manager.cc),

@@ -86,6 +86,20 @@ def test_flat_batch_tensor_core_path_is_exact(metric, d, N, nq, monkeypatch):
     rc, D, I = ix.Search(xq, 10, metric=metric)
     assert rc == 0
     assert np.array_equal(I_ref, I) and np.array_equal(D_ref, D)
+    # many database chunks: the running candidate state is carried (and its threshold applied) across chunk selects;
+    # a filter + a score window ride along; the older select kernel must agree
+    flags = (np.arange(N) % 3 != 0).astype(np.uint8)
+    filt = [(0, N - 1, False, flags)]
+    D_reff, I_reff = r.search(xq, 10, pj, filters=filt)
+    for env in ({"GB200_FLAT_CHUNK_ROWS": "4096"}, {"GB200_FLAT_CHUNK_ROWS": "8192", "GB200_FLAT_SELECT_V1": "1"}):
+        for kk, vv in env.items():
+            monkeypatch.setenv(kk, vv)
+        rc, D3, I3 = ix.Search(xq, 10, metric=metric)
+        assert rc == 0 and np.array_equal(I_ref, I3) and np.array_equal(D_ref, D3), env
+        rc, D4, I4 = ix.Search(xq, 10, metric=metric, filters=filt)
+        assert rc == 0 and np.array_equal(I_reff, I4) and np.array_equal(D_reff, D4), env
+        for kk in env:
+            monkeypatch.delenv(kk)
     # the per-query exact scan (GB200_FLAT=exact) gives the same answer
     monkeypatch.setenv("GB200_FLAT", "exact")
     rc, D2, I2 = ix.Search(xq, 10, metric=metric)
