@@ -13,7 +13,7 @@
 // 2 TMEM accumulator stages so the epilogue of one tile overlaps the mainloop of the next):
 //   warp 0 lane 0 : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 operand tiles
 //   warp 1 lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::tf32, tcgen05.commit -> mbarriers
-//   warps 2..5    : epilogue      — tcgen05.ld (TMEM -> registers), |q|^2 + |y|^2 - 2 acc (clamped at 0)
+//   warps 2..9    : epilogue      — tcgen05.ld (TMEM -> registers), |q|^2 + |y|^2 - 2 acc (clamped at 0)
 //                                   or acc (InnerProduct), 128-bit stores of the distance tile
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -28,7 +28,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;  // tile; TC_BK floats = one
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;      // 16 KB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_big, A_small, B_big, B_small
-constexpr int TC_THREADS = 192;                       // 6 warps
+constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, 64 columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;    // TMA warp + MMA warp + epilogue warps
 constexpr int TC_TMEM_COLS = 128;                     // fp32 accumulator: 128 lanes x 128 columns
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +107,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
   uint64_t *tmem_full = empty + TC_STAGES;   // [2]
   uint64_t *tmem_empty = tmem_full + 2;      // [2]
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-  float *tr_all = reinterpret_cast<float *>(tmem_ptr + 4);  // 4 epilogue warps x 32 x 33 floats
+  float *tr_all = reinterpret_cast<float *>(tmem_ptr + 4);  // TC_EPI_WARPS x 32 x 33 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (P.M + TC_BM - 1) / TC_BM, tiles_n = (P.N + TC_BN - 1) / TC_BN;
@@ -120,7 +121,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
     }
     for (int s = 0; s < 2; s++) {
       tc_mbar_init(&tmem_full[s], 1);
-      tc_mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      tc_mbar_init(&tmem_empty[s], TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,8 +184,11 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lanes (warp % 4) * 32 .. + 31
+    // ===== epilogue warps 2..9: TMEM lanes (warp % 4) * 32 .. + 31 (the hardware ties a warp to that lane quarter);
+    // two warps share a quarter and take 64 of the tile's 128 columns each — with K = 128 (coarse quantiser) the
+    // tile's 48 MMAs take ~3.2k cycles and four epilogue warps (one per scheduler) could not drain 64 KB in that time
     const int quarter = warp & 3;
+    const int col_half = (warp - 2) >> 2;  // 0: columns 0..63, 1: columns 64..127
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
       const int tile_m = t % tiles_m, tile_n = t / tiles_m;
@@ -195,7 +199,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
       const float an_mine = (P.l2 && P.a_norm && row0 + lane < P.M) ? P.a_norm[row0 + lane] : 0.f;
       float *tr = tr_all + (warp - 2) * (32 * 33);              // per-warp 32 x 32 transpose tile (+1 pad)
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      for (int c0 = col_half * (TC_BN / 2); c0 < (col_half + 1) * (TC_BN / 2); c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_TMEM_COLS + c0);
         asm volatile(
@@ -208,7 +212,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= TC_BN) {  // all of this warp's accumulator rows are in registers: hand the buffer back
+        if (c0 + 32 >= (col_half + 1) * (TC_BN / 2)) {  // this warp's share of the accumulator is in registers: hand it back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
         }
@@ -306,7 +310,7 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
       !make_map(&mbs, b_small, N, K))
     return cudaErrorNotSupported;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * sizeof(uint64_t) + 16 +
-                      4 * 32 * 33 * sizeof(float) + 1024;
+                      TC_EPI_WARPS * 32 * 33 * sizeof(float) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
