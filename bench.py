@@ -52,33 +52,99 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs (B200_PROFILING.md).  NVML from a thread every
+    few milliseconds (the timed region of this bench is ~10 ms, far below nvidia-smi's loop period); the nvidia-smi
+    recipe line is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    MASKS = dict(sw_power_cap=0x4, hw_slowdown=0x8, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40)
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.gpu = gpu_index
+        self.uuid = uuid
         self.lines = []
+        self.samples = []  # (sm_mhz, reasons bitmask)
         self.proc = None
+        self.h = None
+        self.max_mhz = None
+        self.stop_flag = False
+        self.th = None
+        self.how = None
+
+    def _nvml_start(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                u = str(self.uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+            except Exception:
+                h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                except Exception:
+                    pass
+                time.sleep(0.003)
+
+        loop_once = (float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h)))  # fails here, not in the thread
+        del loop_once
+        self.th = threading.Thread(target=loop, daemon=True)
+        self.th.start()
+        self.how = "nvml"
 
     def start(self):
+        try:
+            self._nvml_start()
+            return
+        except Exception:
+            self.th = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """number of samples so far (the caller brackets the timed region with two marks)"""
+        return len(self.samples) if self.th else len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, m0=None, m1=None):
+        if self.th:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[1]
+            reasons = sorted(k for k, v in self.MASKS.items() if bits & v)
+            out = dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_mhz, reasons=reasons,
+                       samples=len(sm), how="nvml thread, 3 ms period, over pre-load + timed region + post-load")
+            if m0 is not None and m1 is not None:
+                tr = sm[m0:m1]
+                out["samples_in_timed_region"] = len(tr)
+                if tr:
+                    out["sm_mhz_timed_region"] = float(np.median(tr))
+            return out
         if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampling unavailable"], samples=0)
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -95,7 +161,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), how="nvidia-smi -lms 100 over pre-load + timed region + post-load")
 
 
 def measured_peaks():
@@ -367,10 +433,25 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches0 = ix.launch_count()
-    sampler = ClockSampler(local)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)
     sampler.start()
+
+    def load_for(iters):  # the same step, untimed, a FIXED count on every rank (the step holds a collective when N > 1):
+        for i_ in range(iters):  # the clock samples then see the load the timed region runs under
+            flush.fill_(i_ & 0xff)
+            step_dev()
+        torch.cuda.synchronize()
+
+    load_for(400)
+    if world > 1:
+        dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ix.launch_count()
+    mark0 = sampler.mark()
     scan_ms, stage_acc = [], dict(coarse=0.0, scan=0.0, rerank=0.0, total=0.0)
     scanned = 0
     torch.cuda.synchronize()
@@ -386,10 +467,12 @@ def main():
             stage_acc[k_] += st[k_] / args.steps
         scanned = ix.last_scanned_postings()
     torch.cuda.synchronize()
+    mark1 = sampler.mark()
+    launches = ix.launch_count() - launches0
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
-    launches = ix.launch_count() - launches0
+    load_for(400)
+    clocks = sampler.stop(mark0, mark1)
     if world > 1:
         launches += args.steps  # the NCCL all-gather per step
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
