@@ -191,6 +191,13 @@ int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
   bool generic = force && force[0] == '1';
   ix->layout = (M == 32 && !generic) ? LAYOUT_M32_ROT : LAYOUT_PLAIN;
   ix->mode = ix->layout == LAYOUT_M32_ROT ? 1 : 0;
+  // opt-in (not yet validated on hardware): conflict-free M = 64 scan, fixed at creation because it decides the
+  // posting layout.  Default for M = 64 stays the generic kernel.
+  if (const char *m64 = getenv("GB200_SCAN_M64"))
+    if (M == 64 && m64[0] == '1' && !generic && p->d <= 1024) {
+      ix->layout = LAYOUT_M64_ROT;
+      ix->mode = 2;
+    }
   int rc = common_create(ix);
   if (rc != GB200_OK) {
     delete ix;
@@ -726,7 +733,16 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   // candidate buffer: the v2 kernel with 512 threads keeps 2048 keys (its 16 warps admit up to 512 per round)
   int cap = scan_buffer_cap(R);
   if (variant == 2 && m32_threads == 512 && cap < 2048) cap = 2048;
-  if (ix->mode != 1 || cap > 4 * m32_threads || cap > 2048 || ix->smem_reserved != 1024) {
+  if (ix->mode == 2) {  // M = 64 kernel: 384 threads, 2 CTAs per SM, same work plan as v2
+    if (ix->smem_reserved != 1024) {
+      set_err("M=64 scan needs 1 KB of driver-reserved shared memory per block (found %d)", ix->smem_reserved);
+      return GB200_EUNSUPPORTED;
+    }
+    variant = 2;
+    m32_threads = 384;
+    cap = scan_buffer_cap(R);
+    if (cap < R + 384) cap *= 2;  // room for one block of every warp above the survivors
+  } else if (ix->mode != 1 || cap > 4 * m32_threads || cap > 2048 || ix->smem_reserved != 1024) {
     variant = 1;
     cap = scan_buffer_cap(R);
   }
@@ -830,16 +846,20 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     ix->launches++;
     P.order = ix->ws_order.as<int>();
   }
-  if (ix->mode == 1) {
+  if (ix->mode == 1 || ix->mode == 2) {
     if (ix->p.d > 1024) {
-      set_err("M=32 kernel: d=%d > 1024 not implemented", ix->p.d);
+      set_err("M=32/64 kernel: d=%d > 1024 not implemented", ix->p.d);
       return GB200_EUNSUPPORTED;
     }
+    const size_t lut_bytes = ix->mode == 2 ? 98304 : 65536;
     if (ix->lut_built_n == n && ix->lut_built_ip == (ip ? 1 : 0)) {
       CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));  // built on the side stream during the coarse stage
     } else {
-      CKI(ix->ws_lut.ensure((size_t)n * 65536));
-      CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
+      CKI(ix->ws_lut.ensure((size_t)n * lut_bytes));
+      if (ix->mode == 2)
+        CK(launch_lut_build_m64(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
+      else
+        CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
       ix->launches++;
     }
     ix->lut_built_n = 0;
@@ -850,7 +870,7 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
         P.n_full = n_full;
         P.s_tail = s_tail;
       }
-      if (plan && getenv("GB200_SCAN_SORTED")) {  // optional: heaviest queries first (costs a single-CTA sort)
+      if (plan && ix->mode == 1 && getenv("GB200_SCAN_SORTED")) {  // optional: heaviest queries first (costs a single-CTA sort)
         CKI(ix->ws_items.ensure((size_t)n_items * sizeof(int4)));
         CKI(ix->ws_nsplit.ensure((size_t)n * sizeof(int)));
         CK(launch_plan_items(d_keys, ix->d_len, n, nprobe, ix->p.nlist, n_full, s_tail, ix->ws_items.as<int4>(),
@@ -961,13 +981,16 @@ static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on
   CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
   ix->lut_built_n = 0;
-  if (ix->mode == 1 && d <= 1024 && !keys_h && !getenv("GB200_LUT_INLINE")) {
+  if ((ix->mode == 1 || ix->mode == 2) && d <= 1024 && !keys_h && !getenv("GB200_LUT_INLINE")) {
     // K2a depends on the queries only: fork it onto the side stream so it overlaps the coarse quantiser
     const int ipm = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
-    CKI(ix->ws_lut.ensure((size_t)n * 65536));
+    CKI(ix->ws_lut.ensure((size_t)n * (ix->mode == 2 ? 98304 : 65536)));
     CK(cudaEventRecord(ix->ev_fork, ix->stream));
     CK(cudaStreamWaitEvent(ix->stream2, ix->ev_fork, 0));
-    CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
+    if (ix->mode == 2)
+      CK(launch_lut_build_m64(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
+    else
+      CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
     CK(cudaEventRecord(ix->ev_join, ix->stream2));
     ix->launches++;
     ix->lut_built_n = n;

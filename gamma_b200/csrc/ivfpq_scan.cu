@@ -50,7 +50,7 @@ struct ProbeInfo {
 // shared-memory carve-up (host mirrors this in scan_smem_bytes)
 //  [lut][buf u64 cap][qs d floats][probe infos][blk prefix][misc]
 __host__ __device__ inline size_t scan_lut_bytes(int M, int mode) {
-  return mode == 1 ? (size_t)256 * 64 * 4 : (size_t)M * 257 * 4;
+  return mode == 1 ? (size_t)256 * 64 * 4 : mode == 2 ? (size_t)256 * 96 * 4 : (size_t)M * 257 * 4;
 }
 
 template <bool IP>
@@ -1076,8 +1076,305 @@ static cudaError_t launch_m32_v2(const ScanParams &P, cudaStream_t st) {
 bool scan_m32_v2_usable(const ScanParams &P) { return P.cap <= 4 * P.m32_threads && P.probe_g != nullptr; }
 int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads >= 384 ? 2 : 3; }
 
+// =============================================================================================
+// M = 64 kernel (opt-in: GB200_SCAN_M64=1 at index creation; BASELINE config C3 = PQ64x8).
+// Same structure as the M = 32 v2 kernel.  Differences:
+//  * table [256 codes][96 words] = 96 KB: words 64..95 duplicate 0..31, lane l reads word (l + s) of row `code` at step
+//    s = 0..63 — bank (l + s) mod 32, conflict free; the mirror pre-rotates the 64 code bytes of posting i by i
+//    (LAYOUT_M64_ROT) so that step s uses stored byte s;
+//  * the row pitch (384 B) is not a power of two, so the address is PRMT (byte extract) + IMAD (byte * 384 + lane * 4)
+//    + LDS + FADD = 4 instructions per lookup; IMAD runs on the FMA pipe next to PRMT on the ALU pipe;
+//  * a block of 32 postings is 2 KB of codes (4 chunks of 16 B per posting): 16 code registers, refilled in two
+//    halves as soon as the addresses of that half have been formed;
+//  * 384 threads, 2 CTAs per SM (2 x 108 KB of shared memory), candidate buffer of 1024 keys.
+// NOT yet validated on hardware (written after the round's GPU budget was spent): tests/test_ivfpq_gpu.py holds the
+// parity test, skipped unless GB200_TEST_M64=1.
+// =============================================================================================
+template <bool IP, bool HAS_VALID, int WARPS, int PER>
+__device__ __forceinline__ void scan_loop_m64(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
+                                              const int total_blocks, const int np_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane4 = lane * 4;
+  const int per_warp = (total_blocks + WARPS - 1) / WARPS;
+  const int w0 = min(total_blocks, warp * per_warp);
+  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
+  const int soft_limit = P.cap - WARPS * 32;
+  volatile int *flags = S.misc + 68;
+  const int pf = P.pf_blocks;
+
+  int pj = 0;
+  if (left > 0)
+    while (S.blk_prefix[pj + 1] <= w0) pj++;
+  int bl = 0, len = 0;
+  uint32_t seq0 = 0;
+  float dis0 = 0.f;
+  const uint8_t *cptr = nullptr, *hptr = nullptr;  // this lane's 16 B of chunk 0 of the next block / chunk 2 of the block being loaded
+  const int *iptr = nullptr;
+  const float *nptr = nullptr;
+  // L2 prefetch streams, one 128 B line per lane and block: lanes 0..15 the 2 KB of codes, lane 16 ids, lane 17 t(p)
+  const char *pfp = nullptr;
+  const uint32_t pf_stride = lane < 16 ? 2048u : 128u;
+  const bool pf_lane = pf > 0 && lane < (IP ? 17 : 18);
+  auto stream_base = [&](const ProbeInfo &pi, int b_start) -> const char * {
+    const long long first = pi.off + (long long)b_start * 32;
+    return lane < 16 ? reinterpret_cast<const char *>(P.codes + (size_t)first * 64) + lane * 128
+                     : lane == 16 ? reinterpret_cast<const char *>(P.ids + first)
+                                  : reinterpret_cast<const char *>(P.norms + first);
+  };
+  auto open_list = [&](int j, int b_start) {
+    const ProbeInfo pi = S.pinfo[j];
+    bl = ((pi.len + 31) >> 5) - b_start;
+    dis0 = pi.dis0;
+    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
+    len = pi.len - (b_start * 32 + lane);
+    const long long first = pi.off + (long long)b_start * 32;
+    cptr = P.codes + (size_t)first * 64 + lane * 16;
+    iptr = P.ids + first + lane;
+    nptr = P.norms + first + lane;
+    if (pf_lane) {
+      pfp = stream_base(pi, b_start) + (size_t)pf * pf_stride;
+      if (left > bl && j + 1 < np_s) {  // head of the next list this warp will walk
+        const ProbeInfo pn = S.pinfo[j + 1];
+        const int nb = min(min((pn.len + 31) >> 5, pf), left - bl);
+        const char *h = stream_base(pn, 0);
+#pragma unroll 1
+        for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
+      }
+    }
+  };
+  if (left > 0) {
+    if (pf_lane) {
+      const ProbeInfo pi = S.pinfo[pj];
+      const int b0 = w0 - S.blk_prefix[pj];
+      const int nb = min(min(((pi.len + 31) >> 5) - b0, pf), left);
+      const char *h = stream_base(pi, b0);
+#pragma unroll 1
+      for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
+    }
+    open_list(pj, w0 - S.blk_prefix[pj]);
+  }
+
+  // the block in flight: 64 pre-rotated code bytes (chunks 0,1 in c0..c7, chunks 2,3 in c8..c15), vid, t(p), dis0, seq
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+  uint32_t c8 = 0, c9 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0, c14 = 0, c15 = 0;
+  int id_n = -1;
+  float nrm_n = 0.f, base_n = 0.f;
+  uint32_t seq_n = 0xffffffffu;
+  bool hi_pending = false;  // issue_lo loaded a block whose chunks 2,3 are still to be requested
+  auto issue_lo = [&]() {
+    hi_pending = false;
+    if (left > 0) {  // warp-uniform
+      while (bl == 0) open_list(++pj, 0);
+      const uint4 v0 = ldg_nc_v4(cptr);
+      const uint4 v1 = ldg_nc_v4(cptr + 512);
+      c0 = v0.x, c1 = v0.y, c2 = v0.z, c3 = v0.w, c4 = v1.x, c5 = v1.y, c6 = v1.z, c7 = v1.w;
+      hptr = cptr + 1024;
+      hi_pending = true;
+      seq_n = seq0;
+      base_n = dis0;
+      id_n = -1;
+      nrm_n = 0.f;
+      if (len > 0) {
+        id_n = ldg_nc_s32(iptr);
+        if (!IP) nrm_n = ldg_nc_f32(nptr);
+      }
+      if (pf_lane) {
+        if (bl > pf) l2_prefetch_line(pfp);
+        pfp += pf_stride;
+      }
+      cptr += 2048;
+      iptr += 32;
+      nptr += 32;
+      seq0 += 32;
+      len -= 32;
+      bl--;
+      left--;
+    } else {
+      seq_n = 0xffffffffu;
+    }
+  };
+  auto issue_hi = [&]() {
+    if (hi_pending) {  // warp-uniform
+      const uint4 v2 = ldg_nc_v4(hptr);
+      const uint4 v3 = ldg_nc_v4(hptr + 512);
+      c8 = v2.x, c9 = v2.y, c10 = v2.z, c11 = v2.w, c12 = v3.x, c13 = v3.y, c14 = v3.z, c15 = v3.w;
+    }
+  };
+
+  u64 skey = 0;
+  bool spend = false;
+  auto try_append = [&](bool pass, u64 key) -> bool {
+    const unsigned m = __ballot_sync(GB_FULL, pass);
+    if (m == 0) return false;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
+    base = __shfl_sync(GB_FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    bool pending = pass;
+    if (pass && slot < topr.cap) {
+      topr.buf[slot] = key;
+      pending = false;
+    }
+    spend = pending;
+    skey = key;
+    return __any_sync(GB_FULL, pending);
+  };
+
+  bool stalled = false;
+  issue_lo();
+  issue_hi();
+  int round = 0;
+  for (;;) {
+    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
+    bool over = false;
+    while (!stalled && !over && seq_n != 0xffffffffu) {  // warp-uniform
+      uint32_t a[16];
+      float s0, s1, s2, s3;
+      // address of table word (lane + step) of row `code`: code * 384 + lane * 4 (+ 0x400 + 4 * step in the LDS immediate)
+#define GB64_ADDR4(W, I)                                   \
+  a[I + 0] = prmt_v(W, 0u, 0x4440) * 384u + lane4;         \
+  a[I + 1] = prmt_v(W, 0u, 0x4441) * 384u + lane4;         \
+  a[I + 2] = prmt_v(W, 0u, 0x4442) * 384u + lane4;         \
+  a[I + 3] = prmt_v(W, 0u, 0x4443) * 384u + lane4;
+#define GB64_LOOK4(I, O)             \
+  s0 += lds_raw<O + 0>(a[I + 0]);    \
+  s1 += lds_raw<O + 1>(a[I + 1]);    \
+  s2 += lds_raw<O + 2>(a[I + 2]);    \
+  s3 += lds_raw<O + 3>(a[I + 3]);
+      // quarter 0: steps 0..15 from chunk 0
+      GB64_ADDR4(c0, 0) GB64_ADDR4(c1, 4) GB64_ADDR4(c2, 8) GB64_ADDR4(c3, 12)
+      s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
+      GB64_LOOK4(4, 4) GB64_LOOK4(8, 8) GB64_LOOK4(12, 12)
+      // quarter 1: steps 16..31 from chunk 1; c0..c7 are dead afterwards -> first half of the next block
+      GB64_ADDR4(c4, 0) GB64_ADDR4(c5, 4) GB64_ADDR4(c6, 8) GB64_ADDR4(c7, 12)
+      const int id = id_n;
+      const uint32_t seq = seq_n;
+      const float nb = base_n + nrm_n;
+      uint32_t vw = 0xffffffffu;
+      if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;
+      issue_lo();
+      GB64_LOOK4(0, 16) GB64_LOOK4(4, 20) GB64_LOOK4(8, 24) GB64_LOOK4(12, 28)
+      // quarter 2: steps 32..47 from chunk 2
+      GB64_ADDR4(c8, 0) GB64_ADDR4(c9, 4) GB64_ADDR4(c10, 8) GB64_ADDR4(c11, 12)
+      GB64_LOOK4(0, 32) GB64_LOOK4(4, 36) GB64_LOOK4(8, 40) GB64_LOOK4(12, 44)
+      // quarter 3: steps 48..63 from chunk 3; c8..c15 are dead afterwards -> second half of the next block
+      GB64_ADDR4(c12, 0) GB64_ADDR4(c13, 4) GB64_ADDR4(c14, 8) GB64_ADDR4(c15, 12)
+      issue_hi();
+      GB64_LOOK4(0, 48) GB64_LOOK4(4, 52) GB64_LOOK4(8, 56) GB64_LOOK4(12, 60)
+#undef GB64_ADDR4
+#undef GB64_LOOK4
+      const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
+      over = *((volatile int *)topr.cnt) > soft_limit;
+      const float dis = nb + ((s0 + s1) + (s2 + s3));
+      bool ok = id >= 0;
+      if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
+      const uint32_t k32 = dist_to_key32<IP>(dis);
+      const bool pass = ok && (dis == dis) && k32 <= tau_hi;
+      if (__any_sync(GB_FULL, pass)) {
+        const u64 key = ((u64)k32 << 32) | seq;
+        stalled = try_append(pass && key < topr.threshold(), key);
+        over = over || *((volatile int *)topr.cnt) > soft_limit;
+      }
+    }
+    const bool more = stalled || seq_n != 0xffffffffu;
+    over = over || stalled;
+    const int slot = round % 3;
+    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
+    __syncthreads();
+    const int v = flags[slot];
+    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;
+    round++;
+    if (v & 1) topr.prune_collective<PER>();
+    if (!(v & 2)) break;
+  }
+}
+
+template <bool IP, int THREADS, int MINB, int PER>
+__global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m64_kernel(ScanParams P) {
+  constexpr int WARPS = THREADS / 32;
+  int q, split, nsp;
+  size_t item;
+  if (P.n_items > 0) {
+    item = blockIdx.x;
+    if ((int)blockIdx.x < P.n_full) {
+      q = blockIdx.x, split = 0, nsp = 1;
+    } else {
+      const int t = blockIdx.x - P.n_full;
+      q = P.n_full + t / P.s_tail, split = t % P.s_tail, nsp = P.s_tail;
+    }
+  } else {
+    q = blockIdx.y;
+    split = blockIdx.x, nsp = P.S;
+    item = (size_t)q * P.S + split;
+  }
+  const int tid = threadIdx.x;
+  ScanSmem S = carve(gb_scan_smem, P, 2);
+  BlockTopR topr = make_topr(S, P);
+  if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();
+  const int np_s = (P.nprobe - split + nsp - 1) / nsp;
+  if (tid == 0) {
+    *topr.cnt = 0;
+    *topr.tau = GB_KEY_MAX;
+    S.misc[68] = S.misc[69] = S.misc[70] = 0;
+    mbar_init(&S.mbar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t pbytes = (uint32_t)scan_probe_bytes(P.max_np_s);
+    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 98304;
+    mbar_expect_tx(&S.mbar[0], 98304u + pbytes);
+    tma_bulk_g2s(S.pinfo, P.probe_g + item * pbytes, pbytes, &S.mbar[0]);
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
+  }
+  __syncthreads();
+  mbar_wait(&S.mbar[0], 0);
+  const int total_blocks = S.blk_prefix[np_s];
+  if (P.valid) scan_loop_m64<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  else scan_loop_m64<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  write_survivors<PER>(topr, P, q, split);
+  if (split == 0)
+    for (int i = nsp * P.R + tid; i < P.S * P.R; i += THREADS) P.cand[(size_t)q * P.S * P.R + i] = GB_KEY_MAX;
+}
+
+// per-query tables for the M = 64 kernel: lut_g[q][c][w] = scale * <q_m, cb[m][c]>, m = w mod 64, w < 96
+__global__ void __launch_bounds__(256) lut_build_m64_kernel(const float *__restrict__ xq, const float *__restrict__ pq_t,
+                                                            float *__restrict__ lut_g, int d, int dsub, float scale) {
+  __shared__ float qs[1024];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < d; i += 256) qs[i] = xq[(size_t)q * d + i];
+  __syncthreads();
+  float *out = lut_g + (size_t)q * (256 * 96);
+  for (int e = tid; e < 256 * 64; e += 256) {  // e = c * 64 + m: pq_t is code-major [256][M][dsub]
+    const int c = e >> 6, m = e & 63;
+    const float *cb = pq_t + (size_t)e * dsub;
+    const float *qm = qs + m * dsub;
+    float ip = 0.f;
+    for (int j = 0; j < dsub; j++) ip = fmaf(qm[j], __ldg(cb + j), ip);
+    const float v = scale * ip;
+    out[c * 96 + m] = v;
+    if (m < 32) out[c * 96 + 64 + m] = v;
+  }
+}
+
+cudaError_t launch_lut_build_m64(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
+                                 cudaStream_t st) {
+  if (d > 1024) return cudaErrorInvalidValue;
+  lut_build_m64_kernel<<<n, 256, 0, st>>>(xq, pq_t, lut_g, d, dsub, is_ip ? 1.f : -2.f);
+  return cudaGetLastError();
+}
+
+template <int PER>
+static cudaError_t launch_m64(const ScanParams &P, cudaStream_t st) {
+  static size_t conf[2] = {0, 0};
+  constexpr int MINB = PER == 4 ? 2 : 1;  // the 16-keys-per-thread select needs the registers
+  return P.is_ip ? launch_kernel(ivfpq_scan_m64_kernel<true, 384, MINB, PER>, P, 2, 384, &conf[0], st)
+                 : launch_kernel(ivfpq_scan_m64_kernel<false, 384, MINB, PER>, P, 2, 384, &conf[1], st);
+}
+
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
+  if (mode == 2) return P.cap <= 4 * 384 ? launch_m64<4>(P, st) : launch_m64<16>(P, st);
   if (mode == 1) {
     if (P.variant == 2 && scan_m32_v2_usable(P))
       return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)

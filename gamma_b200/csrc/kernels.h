@@ -16,7 +16,8 @@ typedef unsigned long long u64;
 //   0: chunk-major, chunk = largest of {16,8,4} dividing M: byte b of posting i at
 //      ((b/chunk)*32 + i)*chunk + b%chunk
 //   1: M == 32, chunk 16, bytes pre-rotated per lane: stored byte s of posting i = code[(i + s) % 32]
-enum { LAYOUT_PLAIN = 0, LAYOUT_M32_ROT = 1 };
+//   2: M == 64, chunk 16, bytes pre-rotated per lane: stored byte s of posting i = code[(i + s) % 64]  (opt-in)
+enum { LAYOUT_PLAIN = 0, LAYOUT_M32_ROT = 1, LAYOUT_M64_ROT = 2 };
 
 struct ScanParams {
   const float *xq;          // [n][d]
@@ -59,6 +60,8 @@ cudaError_t launch_query_order(const int *keys, const int *list_len, int n, int 
                                cudaStream_t st);
 cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
                                  cudaStream_t st);
+cudaError_t launch_lut_build_m64(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
+                                 cudaStream_t st);  // [n][256][96]
 
 // K0 — device-side append into the posting mirror (+ t(p) for L2)
 struct AppendParams {

@@ -33,7 +33,7 @@ __global__ void append_kernel(AppendParams P) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       int s = w + j;
-      int src = (P.layout == LAYOUT_M32_ROT) ? ((i + s) & 31) : s;
+      int src = (P.layout == LAYOUT_PLAIN) ? s : ((i + s) % M);  // rotated layouts: M = 32 or 64
       word |= (uint32_t)code[src] << (8 * j);
     }
     *reinterpret_cast<uint32_t *>(P.codes + code_byte_addr(blk_base, i, w, P.chunk)) = word;
@@ -87,7 +87,7 @@ __global__ void gather_list_kernel(const uint8_t *codes, const int *ids, long lo
   long long blk_base = (off + (pos & ~31)) * (long long)M;
   for (int s = 0; s < M; s++) {
     uint8_t v = codes[code_byte_addr(blk_base, i, s, chunk)];
-    int dst = (layout == LAYOUT_M32_ROT) ? ((i + s) & 31) : s;
+    int dst = (layout == LAYOUT_PLAIN) ? s : ((i + s) % M);
     out_codes[(size_t)pos * M + dst] = v;
   }
   out_ids[pos] = ids[off + pos];

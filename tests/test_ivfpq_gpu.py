@@ -6,6 +6,7 @@ floating-point near-tie; ADC distances within 1e-4 relative; re-ranked (exact) d
 bit-identical because exact_distance reproduces faiss' AVX summation order.
 """
 import json
+import os
 
 import numpy as np
 import pytest
@@ -265,3 +266,39 @@ def test_coarse_select_nprobe_sweep(nprobe):
     r = compare_topk(cd_ref, k_ref, cd, k, rtol=1e-4, atol=1e-4)
     assert r["n_id_mismatch_unexplained"] == 0 and r["max_rel_err"] <= 1e-4, r
     assert np.all(np.diff(cd, axis=1) >= 0)
+
+
+@pytest.mark.skipif(os.environ.get("GB200_TEST_M64") != "1",
+                    reason="opt-in conflict-free M=64 scan kernel (GB200_SCAN_M64=1): written after the round's GPU budget was "
+                           "spent, to be validated on hardware with GB200_TEST_M64=1 before it becomes the default")
+@pytest.mark.parametrize("metric", ["L2", "InnerProduct"])
+def test_m64_conflict_free_kernel_parity(metric, monkeypatch):
+    from gamma_b200 import synth
+    monkeypatch.setenv("GB200_SCAN_M64", "1")  # read at index creation: decides the posting layout
+    f = get_ref_fixture("m64_" + metric, N=40000, d=128, nlist=128, M=64, metric=metric, nq=96, n_clusters=128)
+    ix = f.mirror()
+    for l in [0, 1, f.nlist // 2, f.nlist - 1]:  # the rotated layout reads back as the reference's AoS lists
+        ids, codes = ix.get_list(l)
+        rids, rcodes = f.lists[l]
+        assert np.array_equal(ids, rids) and np.array_equal(codes, rcodes)
+    nprobe, R = 12, 50
+    cd_ref, k_ref = f.ref.coarse(f.xq, nprobe)
+    D_ref, I_ref = f.ref.search(f.xq, R, rj(nprobe, R, metric), has_rank=False, keys=k_ref, coarse_dis=cd_ref)
+    rc, D, I = ix.Search(f.xq, R, nprobe=nprobe, recall_num=R, metric=metric, has_rank=False, keys=k_ref, coarse_dis=cd_ref)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
+    # full search with re-rank, a batch larger than the resident CTA slots (work plan with a split tail), a filter
+    normalize = metric != "L2"
+    xq = synth.mixture(700, f.d, synth.SEED_QUERY + 9, n_clusters=128, normalize=normalize)
+    flags = (synth.filter_field(f.N) < 50).astype(np.uint8)
+    for filt in ([], [(0, f.N - 1, False, flags)]):
+        D_ref, I_ref = f.ref.search(xq, 10, rj(16, 100, metric), has_rank=True, filters=filt)
+        rc, D, I = ix.Search(xq, 10, nprobe=16, recall_num=100, metric=metric, has_rank=True, filters=filt)
+        assert rc == 0
+        assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+        assert (I_ref == I).mean() > 0.995
+    # large recall_num: the 16-keys-per-thread select variant
+    D_ref, I_ref = f.ref.search(f.xq, 10, rj(16, 700, metric), has_rank=True)
+    rc, D, I = ix.Search(f.xq, 10, nprobe=16, recall_num=700, metric=metric, has_rank=True)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
