@@ -708,6 +708,36 @@ static int coarse_dev(gb200_index *ix, int n, const float *d_xq, int nprobe, int
   return GB200_OK;
 }
 
+// Positional work plan of one scan launch (DESIGN.md §4 "Work plan"): queries [0, n_full) are one work item each,
+// queries [n_full, n) are s_tail items each, rows = candidate rows per query in the [n][rows][R] buffer.
+// n >= slots: whole waves of resident CTAs stay unsplit, the last partial wave is split slots / n_tail ways;
+// n < slots: every query is split s_uniform ways (the caller's whole-wave heuristic).  Pure arithmetic (CPU-testable
+// through gb200_debug_plan).
+static void plan_work(int n, int slots, int nprobe, int R, int s_uniform, int tail_override, int *n_full, int *s_tail,
+                      int *n_items, int *rows) {
+  int nf = 0, st = 1;
+  if (n >= slots) {
+    nf = (n / slots) * slots;
+    const int n_tail = n - nf;
+    st = n_tail ? std::max(1, std::min(std::min(8, nprobe), slots / n_tail)) : 1;
+  } else {
+    st = s_uniform;
+  }
+  if (tail_override > 0) st = tail_override;
+  st = std::max(1, std::min(st, nprobe));
+  while (st > 1 && (long long)st * R > 8192) st--;
+  *n_full = nf;
+  *s_tail = st;
+  *n_items = nf + (n - nf) * st;
+  *rows = (nf == n) ? 1 : st;
+}
+
+int gb200_debug_plan(int n, int slots, int nprobe, int recall_num, int s_uniform, int *out4) {
+  if (n <= 0 || slots <= 0 || nprobe <= 0 || recall_num <= 0 || s_uniform <= 0 || !out4) return GB200_EINVAL;
+  plan_work(n, slots, nprobe, recall_num, s_uniform, 0, &out4[0], &out4[1], &out4[2], &out4[3]);
+  return GB200_OK;
+}
+
 // scan + rerank with probes already on the device
 static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, const gb200_search_params *sp, int nprobe,
                            const int *d_keys, const float *d_cdis, const uint32_t *d_valid, float *d_out_d,
@@ -765,18 +795,11 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   int n_full = 0, s_tail = 1, n_items = 0;
   if (plan) {
     const int slots = 148 * (m32_threads >= 384 ? 2 : 3);
-    if (n >= slots) {
-      n_full = (n / slots) * slots;
-      const int n_tail = n - n_full;
-      s_tail = n_tail ? std::max(1, std::min(std::min(8, nprobe), slots / n_tail)) : 1;
-    } else {
-      s_tail = S;
-    }
-    if (const char *e = getenv("GB200_SCAN_TAIL")) s_tail = atoi(e);
-    s_tail = std::max(1, std::min(s_tail, nprobe));
-    while (s_tail > 1 && (long long)s_tail * R > 8192) s_tail--;
-    n_items = n_full + (n - n_full) * s_tail;
-    S = (n_full == n) ? 1 : s_tail;  // candidate rows per query
+    int tail_override = 0;
+    if (const char *e = getenv("GB200_SCAN_TAIL")) tail_override = atoi(e);
+    int rows = 1;
+    plan_work(n, slots, nprobe, R, S, tail_override, &n_full, &s_tail, &n_items, &rows);
+    S = rows;  // candidate rows per query
   }
   if (const char *es = getenv("GB200_SCAN_SPLITS")) S = atoi(es);  // tuning knob
   S = std::max(1, std::min(S, nprobe));

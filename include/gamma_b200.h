@@ -181,6 +181,11 @@ int gb200_sync(gb200_index *ix);
 int gb200_debug_select(int device, const uint64_t *keys, int n, int R, int cap, int batch, int threads,
                        uint64_t *out, int *out_n);
 
+/* test hook (pure host arithmetic, no device needed): the positional work plan of one IVFPQ scan launch for a batch of
+ * n queries on `slots` resident CTAs — out4 = {n_full, s_tail, n_items, rows}: queries [0, n_full) are one work item
+ * each, the rest s_tail items each; rows = candidate rows per query handed to the re-rank.            */
+int gb200_debug_plan(int n, int slots, int nprobe, int recall_num, int s_uniform, int *out4);
+
 #ifdef __cplusplus
 }
 #endif
