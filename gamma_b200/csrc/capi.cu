@@ -853,6 +853,8 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     P.m32_threads = m32_threads;
     P.variant = variant;
     P.pf_blocks = pf_blocks;
+    P.steal = 0;
+    if (const char *e = getenv("GB200_SCAN_STEAL")) P.steal = e[0] == '1' ? 1 : 0;
     P.probe_g = nullptr;
   }
   if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {

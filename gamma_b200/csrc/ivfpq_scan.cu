@@ -573,7 +573,15 @@ __device__ __forceinline__ float lds_raw(uint32_t off) {
   return v;
 }
 
-template <bool IP, bool HAS_VALID, int WARPS, int PER>
+// STEAL (opt-in, GB200_SCAN_STEAL=1, not yet validated on hardware): intra-CTA work stealing.  Every warp still owns a
+// contiguous share of the CTA's blocks and walks it front to back, but claims it STEAL_CH blocks at a time from a
+// shared (front, back) word; a warp whose share is empty takes chunks from the BACK of the share with the most
+// blocks left (one 64-bit CAS, re-opening the list there).  profiles/r01c: 17 % of all warp time is spent at the
+// CTA's final barrier waiting for the slowest warp of the static split; taking fixed chunks from a single shared
+// counter was measured and lost more to re-opening lists than it gained — here only the thieves re-open.
+constexpr int STEAL_CH = 4;
+
+template <bool IP, bool HAS_VALID, int WARPS, int PER, bool STEAL = false>
 __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
                                                  const int total_blocks, const int np_s) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -581,6 +589,16 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
   const int per_warp = (total_blocks + WARPS - 1) / WARPS;
   const int w0 = min(total_blocks, warp * per_warp);
   int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
+  // STEAL: shares live in shared memory as (front | back << 32), block indices in the CTA's block sequence
+  u64 *rng = reinterpret_cast<u64 *>(S.misc + 4);  // [WARPS <= 16], the unused warp_part scratch
+  int ahead = 0;                                    // STEAL: blocks of my own share not yet claimed (for the prefetch)
+  bool own_done = false;
+  if constexpr (STEAL) {
+    if (lane == 0) rng[warp] = (u64)(uint32_t)w0 | ((u64)(uint32_t)(w0 + left) << 32);
+    ahead = left;
+    left = 0;
+    __syncthreads();  // every share is published before anyone may look for a victim
+  }
   const int soft_limit = P.cap - WARPS * 32;
   volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
   const int pf = P.pf_blocks;
@@ -618,9 +636,9 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
     if (pf_lane) {
       pfp = stream_base(pi, b_start) + (size_t)pf * pf_stride;  // steady state: block (current + pf)
       // head of the NEXT list this warp will walk (its first blocks have no steady-state prefetch)
-      if (left > bl && j + 1 < np_s) {
+      if (left + (STEAL ? ahead : 0) > bl && j + 1 < np_s) {
         const ProbeInfo pn = S.pinfo[j + 1];
-        const int nb = min(min((pn.len + 31) >> 5, pf), left - bl);
+        const int nb = min(min((pn.len + 31) >> 5, pf), left + (STEAL ? ahead : 0) - bl);
         const char *h = stream_base(pn, 0);
 #pragma unroll 1
   #pragma unroll 1
@@ -639,6 +657,78 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
     }
     open_list(pj, w0 - S.blk_prefix[pj]);
   }
+  // STEAL: claim the next chunk — from the front of my own share (contiguous with what I walked, no re-open), else
+  // from the back of the fullest share (re-open there).  Warp-uniform; returns false when the CTA has no blocks left.
+  bool first_claim = true;
+  auto claim = [&]() -> bool {
+    int b0 = 0, nb = 0;
+    bool stolen = false;
+    if (!own_done) {
+      if (lane == 0) {
+        u64 old = *((volatile u64 *)&rng[warp]);
+        for (;;) {
+          const uint32_t f = (uint32_t)old, b = (uint32_t)(old >> 32);
+          if (f >= b) break;
+          const uint32_t c = min((uint32_t)STEAL_CH, b - f);
+          const u64 seen = atomicCAS(reinterpret_cast<unsigned long long *>(&rng[warp]), old,
+                                     (u64)(f + c) | ((u64)b << 32));
+          if (seen == old) {
+            b0 = (int)f, nb = (int)c;
+            ahead = (int)(b - f - c);
+            break;
+          }
+          old = seen;
+        }
+      }
+      nb = __shfl_sync(GB_FULL, nb, 0);
+      b0 = __shfl_sync(GB_FULL, b0, 0);
+      ahead = __shfl_sync(GB_FULL, ahead, 0);
+      if (nb == 0) {
+        own_done = true;
+        ahead = 0;
+      }
+    }
+    if (nb == 0) {  // look for a victim: the share with the most unclaimed blocks
+      for (;;) {
+        u64 w = lane < WARPS ? *((volatile u64 *)&rng[lane]) : 0ull;
+        int rem = (int)(uint32_t)(w >> 32) - (int)(uint32_t)w;
+        rem = rem > 0 ? rem : 0;
+        const int best = __reduce_max_sync(GB_FULL, rem);
+        if (best == 0) return false;  // nothing left anywhere
+        const int victim = __ffs(__ballot_sync(GB_FULL, rem == best)) - 1;
+        if (lane == 0) {
+          u64 old = *((volatile u64 *)&rng[victim]);
+          const uint32_t f = (uint32_t)old, b = (uint32_t)(old >> 32);
+          if (f < b) {
+            const uint32_t c = min((uint32_t)STEAL_CH, b - f);
+            const u64 seen = atomicCAS(reinterpret_cast<unsigned long long *>(&rng[victim]), old,
+                                       (u64)f | ((u64)(b - c) << 32));
+            if (seen == old) b0 = (int)(b - c), nb = (int)c;
+          }
+        }
+        nb = __shfl_sync(GB_FULL, nb, 0);
+        b0 = __shfl_sync(GB_FULL, b0, 0);
+        if (nb > 0) break;  // else: lost the race, look again
+      }
+      stolen = true;
+    }
+    left = nb;
+    if (stolen || first_claim) {  // position the list walk at block b0 (own chunks after the first continue in place)
+      pj = 0;
+      while (S.blk_prefix[pj + 1] <= b0) pj++;
+      if (pf_lane) {
+        const ProbeInfo pi = S.pinfo[pj];
+        const int bs = b0 - S.blk_prefix[pj];
+        const int nh = min(min(((pi.len + 31) >> 5) - bs, pf), left);
+        const char *h = stream_base(pi, bs);
+#pragma unroll 1
+        for (int b = 0; b < nh; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
+      }
+      open_list(pj, b0 - S.blk_prefix[pj]);
+      first_claim = false;
+    }
+    return true;
+  };
 
   // the block in flight (per lane): 32 pre-rotated code bytes, vid, t(p), list dis0, scan-order word
   uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
@@ -646,6 +736,9 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
   float nrm_n = 0.f, base_n = 0.f;
   uint32_t seq_n = 0xffffffffu;
   auto issue_loads = [&]() {
+    if constexpr (STEAL) {
+      if (left == 0) claim();
+    }
     if (left > 0) {  // warp-uniform
       while (bl == 0) open_list(++pj, 0);
       const uint4 v0 = ldg_nc_v4(cptr);
@@ -781,7 +874,7 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
   }
 }
 
-template <bool IP, int THREADS, int MINB, int PER>
+template <bool IP, int THREADS, int MINB, int PER, bool STEAL = false>
 __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanParams P) {
   constexpr int WARPS = THREADS / 32;
   long long t_last = clock64();
@@ -831,8 +924,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanPa
   mbar_wait(&S.mbar[0], 0);
   GB_TICK(0);  // wait for the tables
   const int total_blocks = S.blk_prefix[np_s];
-  if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER>(P, S, topr, total_blocks, np_s);
-  else scan_loop_m32_v2<IP, false, WARPS, PER>(P, S, topr, total_blocks, np_s);
+  if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER, STEAL>(P, S, topr, total_blocks, np_s);
+  else scan_loop_m32_v2<IP, false, WARPS, PER, STEAL>(P, S, topr, total_blocks, np_s);
   GB_TICK(2);  // scan loop incl. in-loop prunes
   write_survivors<PER>(topr, P, q, split);
   if (split == 0)  // an unsplit (or less split) query leaves the other slots of its [S][R] candidate row empty
@@ -1069,6 +1162,11 @@ static cudaError_t launch_m32_v2(const ScanParams &P, cudaStream_t st) {
   static size_t conf[2] = {0, 0};
   return P.is_ip ? launch_kernel(ivfpq_scan_m32_v2_kernel<true, T, MINB, 4>, P, 1, T, &conf[0], st)
                  : launch_kernel(ivfpq_scan_m32_v2_kernel<false, T, MINB, 4>, P, 1, T, &conf[1], st);
+}
+static cudaError_t launch_m32_v2_steal(const ScanParams &P, cudaStream_t st) {  // opt-in, 256 threads x 3 CTAs only
+  static size_t conf[2] = {0, 0};
+  return P.is_ip ? launch_kernel(ivfpq_scan_m32_v2_kernel<true, 256, 3, 4, true>, P, 1, 256, &conf[0], st)
+                 : launch_kernel(ivfpq_scan_m32_v2_kernel<false, 256, 3, 4, true>, P, 1, 256, &conf[1], st);
 }
 
 // v2 needs: cap <= 1024 (4 keys per thread in the select), the probe tables, and dynamic shared memory at
@@ -1376,6 +1474,7 @@ cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
   if (mode == 2) return P.cap <= 4 * 384 ? launch_m64<4>(P, st) : launch_m64<16>(P, st);
   if (mode == 1) {
+    if (P.variant == 2 && scan_m32_v2_usable(P) && P.steal && P.m32_threads == 256) return launch_m32_v2_steal(P, st);
     if (P.variant == 2 && scan_m32_v2_usable(P))
       return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)
              : P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);

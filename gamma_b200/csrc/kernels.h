@@ -42,6 +42,7 @@ struct ScanParams {
   int force_sym;            // debug: take the symbol-addressed LDS path even when the raw one is valid
   int variant;              // M = 32: 2 = v2 kernel (precomputed probe tables, in-place prefetch), 1 = v1
   int pf_blocks;            // v2 loop: L2 prefetch distance in 32-posting blocks (0 = off)
+  int steal;                // v2 loop, 256-thread shape: intra-CTA work stealing (opt-in, GB200_SCAN_STEAL=1)
   unsigned char *probe_g;   // v2: [items][scan_probe_bytes(max_np_s)] from launch_probe_setup
   const int4 *items;        // v2: work plan (query, split, splits of that query, 0) from launch_plan_items, or nullptr
   int n_items;              //     > 0: grid = n_items work items; S is then the row count of cand per query.  With items ==

@@ -302,3 +302,23 @@ def test_m64_conflict_free_kernel_parity(metric, monkeypatch):
     rc, D, I = ix.Search(f.xq, 10, nprobe=16, recall_num=700, metric=metric, has_rank=True)
     assert rc == 0
     assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-6, atol=0.0, max_bad_frac=0.002)
+
+
+@pytest.mark.skipif(os.environ.get("GB200_TEST_STEAL") != "1",
+                    reason="opt-in intra-CTA work stealing (GB200_SCAN_STEAL=1): written after the round's GPU budget was spent, "
+                           "to be validated on hardware with GB200_TEST_STEAL=1 (and scripts/stress_v2.py) before it becomes the default")
+def test_work_stealing_scan_matches_static_split(monkeypatch):
+    from gamma_b200 import synth
+    f = fx_l2_m32()
+    ix = f.mirror()
+    xq = synth.mixture(1100, f.d, synth.SEED_QUERY + 5, n_clusters=128)
+    flags = (synth.filter_field(f.N) < 30).astype(np.uint8)
+    for filt in ([], [(0, f.N - 1, False, flags)]):
+        for R, rank in ((100, True), (50, False), (500, True)):
+            rc, D, I = ix.Search(xq, 10, nprobe=16, recall_num=R, metric="L2", has_rank=rank, filters=filt)
+            assert rc == 0
+            monkeypatch.setenv("GB200_SCAN_STEAL", "1")
+            for _ in range(20):  # the steal order is timing dependent, the result must not be
+                rc, D2, I2 = ix.Search(xq, 10, nprobe=16, recall_num=R, metric="L2", has_rank=rank, filters=filt)
+                assert rc == 0 and np.array_equal(I2, I) and np.array_equal(D2, D)
+            monkeypatch.delenv("GB200_SCAN_STEAL")
