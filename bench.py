@@ -556,7 +556,9 @@ def main():
     scan_avg_ms = float(np.mean(scan_ms))
     achieved = alg_bytes / (scan_avg_ms / 1e3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel=("ivfpq_scan_m32_v2_kernel" if w["M"] == 32 else "ivfpq_scan_generic_kernel") + " (CUDA events around that one launch on the search stream)",
+                    kernel=("ivfpq_scan_m32_v2_kernel" if w["M"] == 32 else
+                            "ivfpq_scan_m64_kernel" if (w["M"] == 64 and os.environ.get("GB200_SCAN_M64") == "1") else
+                            "ivfpq_scan_generic_kernel") + " (CUDA events around that one launch on the search stream)",
                     algorithmic_bytes_per_launch=alg_bytes,
                     scanned_postings_per_launch=scanned, kernel_ms=scan_avg_ms, peak_source=peak_src,
                     stage_ms=stage_acc)
