@@ -64,3 +64,22 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_packed_topk_buffer_roundtrip():
+    """one buffer per rank ([n*k] f32 then [n*k] i64): what a rank searches into is what the all-gather ships"""
+    import torch
+    from gamma_b200 import dist as gdist
+    world, n, k = 3, 5, 4
+    bufs = []
+    for r in range(world):
+        buf, D, I = gdist.packed_topk_buffer(n, k, "cpu")
+        D.copy_(torch.arange(n * k, dtype=torch.float32).view(n, k) + 100 * r)
+        I.copy_(torch.arange(n * k, dtype=torch.int64).view(n, k) + 1000 * r)
+        assert buf.numel() == n * k * 12 and D.data_ptr() == buf.data_ptr()
+        bufs.append(buf)
+    D_all, I_all = gdist.unpack_topk(torch.cat(bufs), world, n, k)
+    assert D_all.shape == (world * n, k) and I_all.dtype == torch.int64
+    for r in range(world):
+        assert torch.equal(D_all[r * n:(r + 1) * n], torch.arange(n * k, dtype=torch.float32).view(n, k) + 100 * r)
+        assert torch.equal(I_all[r * n:(r + 1) * n], torch.arange(n * k, dtype=torch.int64).view(n, k) + 1000 * r)
