@@ -559,13 +559,6 @@ __device__ __forceinline__ uint32_t prmt_v(uint32_t a, uint32_t b, uint32_t sel)
   asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
 }
-__device__ __forceinline__ uint4 lds_volatile_v4(const void *p) {
-  uint4 r;
-  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "r"(smem_u32(p)));
-  return r;
-}
 template <int S0>
 __device__ __forceinline__ float lds_raw(uint32_t off) {
   float v;
@@ -825,21 +818,11 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
 #undef GB_ADDR4
 #undef GB_LOOK4
       // ---- D: filter, key, admission
-#ifndef GB_OVER_MODE
-#define GB_OVER_MODE 2
-#endif
-#if GB_OVER_MODE == 1
-      // {tau, cnt} in one 16-byte read: every warp notices within one block that a prune is wanted, whether
-      // or not it has anything to append itself
-      const uint4 tc = lds_volatile_v4(S.misc);
-      const uint32_t tau_hi = tc.y;
-      over = (int)tc.z > soft_limit;  // view from before this block's own append: enough to notice a wanted prune
-#elif GB_OVER_MODE == 2
+      // every warp reads the counter once per block so that all of them notice a wanted prune within one block, whether
+      // or not they append anything themselves.  Two 32-bit loads on purpose: fetching {tau, cnt} with one
+      // ld.volatile.shared.v4 hung this kernel on B200.
       const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
       over = *((volatile int *)topr.cnt) > soft_limit;
-#else
-      const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
-#endif
       const float dis = nb + ((s0 + s1) + (s2 + s3));
       bool ok = id >= 0;
       if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
