@@ -10,7 +10,7 @@ if [ "$STEAL_OK" = "0" ]; then
   step "pytest, work stealing";   GB200_TEST_STEAL=1 timeout 300 python -m pytest tests/test_ivfpq_gpu.py -x -q -m gpu --timeout 120 -k stealing 2>&1 | tail -3
 fi
 step "pytest, M=64 kernel";       GB200_TEST_M64=1 timeout 300 python -m pytest tests/test_ivfpq_gpu.py -x -q -m gpu --timeout 120 -k m64 2>&1 | tail -3; M64_OK=${PIPESTATUS[0]}
-VARS="GB200_SCAN_THREADS=512"
+VARS="GB200_COARSE_TIGHT=1;GB200_SCAN_THREADS=512"
 [ "$STEAL_OK" = "0" ] && VARS="GB200_SCAN_STEAL=1;GB200_SCAN_STEAL=1,GB200_SCAN_TAIL=2;$VARS"
 step "headline A/B: $VARS"
 ( timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --variants "$VARS" ) > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err
