@@ -498,10 +498,11 @@ def main():
         kv = dict(x.split("=") for x in var.split(","))
         for k_, v_ in kv.items():
             os.environ[k_] = v_
+        ix.reload_tuning()
         for _ in range(3):
             step_dev()
         torch.cuda.synchronize()
-        sc = []
+        sc, sk = [], []
         t_ev = []
         for i in range(args.steps):
             flush.fill_(i & 0xff)
@@ -511,11 +512,14 @@ def main():
             b_.record(stream)
             ix.sync()
             sc.append(ix.last_stage_ms()["scan"])
+            sk.append(ix.last_scan_kernel_ms())
             t_ev.append(a_.elapsed_time(b_))
         ok_ = bool(np.array_equal(I_d.cpu().numpy(), I_ours))
-        log("variant %s: ms/step %.4f scan %.4f same_ids=%s" % (var, float(np.mean(t_ev)), float(np.mean(sc)), ok_))
+        log("variant %s: ms/step %.4f scan stage %.4f scan kernel %.4f same_ids=%s" % (
+            var, float(np.mean(t_ev)), float(np.mean(sc)), float(np.mean(sk)), ok_))
         for k_ in kv:
             os.environ.pop(k_, None)
+        ix.reload_tuning()
 
     # ---- e2e: public host call, pinned host buffers, H2D + D2H inside the timed region
     xq_pin = torch.from_numpy(xq).pin_memory()
@@ -556,8 +560,8 @@ def main():
     scan_avg_ms = float(np.mean(scan_ms))
     achieved = alg_bytes / (scan_avg_ms / 1e3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel=("ivfpq_scan_m32_v2_kernel" if w["M"] == 32 else
-                            "ivfpq_scan_m64_kernel" if (w["M"] == 64 and os.environ.get("GB200_SCAN_M64") == "1") else
+                    kernel=("ivfpq_scan_m32_v%s_kernel" % os.environ.get("GB200_SCAN_VARIANT", "3") if w["M"] == 32 else
+                            "ivfpq_scan_m64_kernel" if w["M"] == 64 else
                             "ivfpq_scan_generic_kernel") + " (CUDA events around that one launch on the search stream)",
                     algorithmic_bytes_per_launch=alg_bytes,
                     scanned_postings_per_launch=scanned, kernel_ms=scan_avg_ms, peak_source=peak_src,

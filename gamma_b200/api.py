@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.gb200_launch_count.argtypes = [C.c_void_p]
         L.gb200_last_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.gb200_reload_tuning.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
@@ -200,6 +201,10 @@ class _Base:
 
     def set_profiling(self, on=True):
         lib().gb200_set_profiling(self.h, 1 if on else 0)
+
+    def reload_tuning(self):
+        """Re-read the GB200_* tuning environment variables (they are read once at index creation)."""
+        lib().gb200_reload_tuning(self.h)
 
     def last_stage_ms(self):
         out = (C.c_float * 4)()

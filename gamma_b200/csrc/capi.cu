@@ -74,11 +74,53 @@ inline long long roundup32(long long v) { return (v + 31) & ~31LL; }
 
 }  // namespace
 
+// Tuning knobs: environment variables read ONCE at index creation (gb200_reload_tuning re-reads them, for A/B runs);
+// defaults are the measured best.
+struct Tuning {
+  int scan_variant = 3;   // GB200_SCAN_VARIANT: M = 32 scan: 3 = persistent kernel with dynamic items (default), 2 = one CTA per (query, split)
+  int scan_threads = 256; // GB200_SCAN_THREADS: 256 (3 CTAs / SM), 384 or 512 (2 CTAs / SM)
+  int pf_blocks = 4;      // GB200_SCAN_PF: L2 prefetch distance in 32-posting blocks
+  int ch_blocks = 8;      // GB200_SCAN_CH: blocks per item (v3)
+  int help_min = 8;       // GB200_SCAN_HELP_MIN: idle CTAs join a query that has >= this many unclaimed items (v3)
+  int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
+  int splits = 0;         // GB200_SCAN_SPLITS: v2 / M = 64 / generic: CTAs per query, 0 = automatic
+  int tail = 0;           // GB200_SCAN_TAIL: v2 plan: splits of the last partial wave, 0 = automatic
+  int no_plan = 0;        // GB200_SCAN_NOPLAN: v2 without the positional work plan
+  int steal = 0;          // GB200_SCAN_STEAL: v2, 256 threads: intra-CTA work stealing
+  int scan_timing = 0;    // GB200_SCAN_TIMING: per-phase cycle counters of the v2 kernel on stderr
+  int coarse_simt = 0;    // GB200_COARSE=simt: CUDA-core fp32 coarse distances instead of the tcgen05 GEMM
+  int lut_inline = 0;     // GB200_LUT_INLINE: build the tables on the main stream
+  int flat_mode = 0;      // GB200_FLAT: 0 automatic, 1 = exact (per-query scan), 2 = tc (tensor-core path for any batch)
+  long long flat_chunk_rows = 0;  // GB200_FLAT_CHUNK_ROWS: database rows per tensor-core chunk (tests: force many chunks)
+  void read() {
+    *this = Tuning();
+    auto geti = [](const char *k, int d) { const char *e = getenv(k); return e && *e ? atoi(e) : d; };
+    scan_variant = geti("GB200_SCAN_VARIANT", scan_variant);
+    scan_threads = geti("GB200_SCAN_THREADS", scan_threads);
+    if (scan_threads != 256 && scan_threads != 384 && scan_threads != 512) scan_threads = 256;
+    pf_blocks = std::max(0, geti("GB200_SCAN_PF", pf_blocks));
+    ch_blocks = std::max(1, geti("GB200_SCAN_CH", ch_blocks));
+    help_min = std::max(1, geti("GB200_SCAN_HELP_MIN", help_min));
+    max_rows = std::max(0, geti("GB200_SCAN_ROWS", 0));
+    splits = std::max(0, geti("GB200_SCAN_SPLITS", 0));
+    tail = std::max(0, geti("GB200_SCAN_TAIL", 0));
+    no_plan = geti("GB200_SCAN_NOPLAN", 0);
+    steal = geti("GB200_SCAN_STEAL", 0);
+    scan_timing = geti("GB200_SCAN_TIMING", 0);
+    lut_inline = geti("GB200_LUT_INLINE", 0);
+    if (const char *e = getenv("GB200_COARSE")) coarse_simt = !strcmp(e, "simt");
+    if (const char *e = getenv("GB200_FLAT")) flat_mode = !strcmp(e, "exact") ? 1 : !strcmp(e, "tc") ? 2 : 0;
+    if (const char *e = getenv("GB200_FLAT_CHUNK_ROWS")) flat_chunk_rows = atoll(e);
+  }
+};
+
 struct gb200_index {
   int kind = 0;  // 0 = IVFPQ, 1 = FLAT
+  Tuning tune;
   gb200_ivfpq_params p{};
   int dsub = 0, chunk = 0, layout = 0, mode = 0;
   int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the v2 scan's LDS immediates assume 1024)
+  int num_sms = 0;        // cudaDeviceProp::multiProcessorCount (grid sizing of the persistent scan, work plans)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: per-query lookup tables are built while the coarse quantiser runs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -114,7 +156,7 @@ struct gb200_index {
   DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
   bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe, ws_items, ws_nsplit;
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe, ws_items, ws_nsplit, ws_ctl;
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
   long long last_scanned = 0, launches = 0;
@@ -157,6 +199,8 @@ static int common_create(gb200_index *ix) {
     return GB200_EUNSUPPORTED;
   }
   ix->smem_reserved = (int)prop.reservedSharedMemPerBlock;
+  ix->tune.read();
+  ix->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
@@ -187,22 +231,20 @@ int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
   ix->dsub = p->d / p->nsubvector;
   int M = p->nsubvector;
   ix->chunk = (M % 16 == 0) ? 16 : (M % 8 == 0 ? 8 : 4);
-  const char *force = getenv("GB200_FORCE_GENERIC");
-  bool generic = force && force[0] == '1';
-  ix->layout = (M == 32 && !generic) ? LAYOUT_M32_ROT : LAYOUT_PLAIN;
-  ix->mode = ix->layout == LAYOUT_M32_ROT ? 1 : 0;
-  // opt-in (not yet validated on hardware): conflict-free M = 64 scan, fixed at creation because it decides the
-  // posting layout.  Default for M = 64 stays the generic kernel.
-  if (const char *m64 = getenv("GB200_SCAN_M64"))
-    if (M == 64 && m64[0] == '1' && !generic && p->d <= 1024) {
-      ix->layout = LAYOUT_M64_ROT;
-      ix->mode = 2;
-    }
   int rc = common_create(ix);
   if (rc != GB200_OK) {
     delete ix;
     return rc;
   }
+  // posting layout / scan kernel, fixed at creation: M = 32 and M = 64 have conflict-free kernels over a pre-rotated
+  // layout (LAYOUT_M32_ROT / LAYOUT_M64_ROT); every other M % 4 == 0 runs the generic kernel over the plain layout
+  // (GB200_FORCE_GENERIC=1 forces that one, for A/B and parity tests).
+  const char *force = getenv("GB200_FORCE_GENERIC");
+  const bool generic = (force && force[0] == '1') || p->d > 1024 || ix->smem_reserved != 1024;  // the kernels' LDS immediates
+  ix->layout = LAYOUT_PLAIN;
+  ix->mode = 0;
+  if (M == 32 && !generic) ix->layout = LAYOUT_M32_ROT, ix->mode = 1;
+  if (M == 64 && !generic) ix->layout = LAYOUT_M64_ROT, ix->mode = 2;
   ix->h_off.assign(p->nlist, 0);
   ix->h_len.assign(p->nlist, 0);
   ix->h_cap.assign(p->nlist, 0);
@@ -246,7 +288,7 @@ int gb200_destroy(gb200_index *ix) {
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
                     &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe, &ix->ws_items, &ix->ws_nsplit};
+                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe, &ix->ws_items, &ix->ws_nsplit, &ix->ws_ctl};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 6; i++)
     if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
@@ -679,8 +721,7 @@ static int coarse_dev(gb200_index *ix, int n, const float *d_xq, int nprobe, int
   CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
   CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
   // distance producer: tcgen05 3xTF32 GEMM (default) or the CUDA-core fp32 kernel (GB200_COARSE=simt)
-  const char *cmode = getenv("GB200_COARSE");
-  const bool use_tc = !(cmode && !strcmp(cmode, "simt")) && (d % 4 == 0) && (nlist % 4 == 0);
+  const bool use_tc = !ix->tune.coarse_simt && (d % 4 == 0) && (nlist % 4 == 0);
   if (use_tc) {
     CKI(ix->ws_xs.ensure((size_t)n * d * sizeof(float)));
     CK(launch_tf32_residual(d_xq, ix->ws_xs.as<float>(), (size_t)n * d, ix->stream));
@@ -743,6 +784,7 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
                            const int *d_keys, const float *d_cdis, const uint32_t *d_valid, float *d_out_d,
                            long long *d_out_i) {
   const int M = ix->p.nsubvector;
+  const Tuning &T = ix->tune;
   int R = sp->recall_num < k ? k : sp->recall_num;  // gamma_index_ivfpq.cc:762-765
   const bool ip = sp->metric == GB200_METRIC_INNER_PRODUCT;
   if (R > 2048) {
@@ -754,57 +796,27 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     set_err("has_rank search but no raw vectors uploaded");
     return GB200_EINVAL;
   }
-  // M = 32 kernel version and shape (tuning knobs are environment variables; defaults are the measured best)
-  int variant = 2, m32_threads = 256, pf_blocks = 4;
-  if (const char *e = getenv("GB200_SCAN_VARIANT")) variant = atoi(e);
-  if (const char *e = getenv("GB200_SCAN_THREADS")) m32_threads = atoi(e);
-  if (const char *e = getenv("GB200_SCAN_PF")) pf_blocks = atoi(e);
-  if (m32_threads != 256 && m32_threads != 384 && m32_threads != 512) m32_threads = 256;
-  // candidate buffer: the v2 kernel with 512 threads keeps 2048 keys (its 16 warps admit up to 512 per round)
-  int cap = scan_buffer_cap(R);
-  if (variant == 2 && m32_threads == 512 && cap < 2048) cap = 2048;
-  if (ix->mode == 2) {  // M = 64 kernel: 384 threads, 2 CTAs per SM, same work plan as v2
-    if (ix->smem_reserved != 1024) {
-      set_err("M=64 scan needs 1 KB of driver-reserved shared memory per block (found %d)", ix->smem_reserved);
-      return GB200_EUNSUPPORTED;
-    }
-    variant = 2;
-    m32_threads = 384;
-    cap = scan_buffer_cap(R);
+  // ---- kernel, CTA shape, candidate buffer.
+  //  mode 1 (M = 32): v3 persistent kernel (default) or v2 (one CTA per (query, split), GB200_SCAN_VARIANT=2, R <= 512);
+  //  mode 2 (M = 64): 384 threads, 2 CTAs per SM, v2-style work plan;  mode 0: generic kernel.
+  int variant = ix->mode == 1 ? T.scan_variant : ix->mode == 2 ? 2 : 0;
+  int threads = T.scan_threads;
+  int cap = scan_buffer_cap(R);  // power of two >= R + 512, >= 1024
+  if (ix->mode == 1) {
+    if (variant != 2 && variant != 3) variant = 3;
+    if (variant == 2 && (cap > 2048 || (cap > 1024 && threads != 512))) variant = 3;  // v2 keeps 4 keys per thread in its select
+    if (variant == 2 && threads == 512 && cap < 2048) cap = 2048;
+    if (variant == 3 && cap > 4 * threads) threads = 512;           // R > 512: 2048 / 4096 keys (4 / 8 per thread)
+    if (variant == 3 && threads == 512 && cap < 2048) cap = 2048;   // room for one block of each of the 16 warps
+  } else if (ix->mode == 2) {
+    threads = 384;
     if (cap < R + 384) cap *= 2;  // room for one block of every warp above the survivors
-  } else if (ix->mode != 1 || cap > 4 * m32_threads || cap > 2048 || ix->smem_reserved != 1024) {
-    variant = 1;
-    cap = scan_buffer_cap(R);
   }
-  // splits: each query is scanned by S CTAs (probes dealt round-robin).  v1: ~2 waves of 148 x 3 resident CTAs.
-  // v2: the S in 1..8 that best fills whole waves of resident CTAs, charging ~4 % of a CTA per extra split
-  // for the table load / final select, merge buffer <= 8192 keys
-  int S = (148 * 3 * 2 + n - 1) / n;
-  if (variant == 2) {
-    const double slots = 148.0 * (m32_threads >= 384 ? 2 : 3);
-    double best = -1.0;
-    for (int s = 1; s <= 8 && s <= nprobe; s++) {
-      const double waves = (double)n * s / slots;
-      const double eff = waves / std::ceil(waves) - 0.04 * (s - 1);
-      if (eff > best) best = eff, S = s;
-    }
-  }
-  // v2 work plan: heaviest queries first, one CTA each; only the queries of the last partial wave of resident CTAs
-  // are split (s_tail ways) so the launch ends on short items.  Batches smaller than one wave are split uniformly.
-  bool plan = variant == 2 && n <= 4096 && !getenv("GB200_SCAN_SPLITS") && !getenv("GB200_SCAN_NOPLAN");
-  int n_full = 0, s_tail = 1, n_items = 0;
-  if (plan) {
-    const int slots = 148 * (m32_threads >= 384 ? 2 : 3);
-    int tail_override = 0;
-    if (const char *e = getenv("GB200_SCAN_TAIL")) tail_override = atoi(e);
-    int rows = 1;
-    plan_work(n, slots, nprobe, R, S, tail_override, &n_full, &s_tail, &n_items, &rows);
-    S = rows;  // candidate rows per query
-  }
-  if (const char *es = getenv("GB200_SCAN_SPLITS")) S = atoi(es);  // tuning knob
-  S = std::max(1, std::min(S, nprobe));
-  while (S > 1 && (long long)S * R > 8192) S--;
+  const int ctas_per_sm = ix->mode == 0 ? 3 : (threads >= 384 ? 2 : 3);
+  const int slots = ix->num_sms * ctas_per_sm;
+
   ScanParams P;
+  memset(&P, 0, sizeof(P));
   P.xq = d_xq;
   P.keys = d_keys;
   P.coarse_dis = d_cdis;
@@ -816,69 +828,81 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   P.list_off = ix->d_off;
   P.list_len = ix->d_len;
   P.valid = d_valid;
-  CKI(ix->ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
-  P.cand = ix->ws_cand.as<u64>();
   P.scanned = ix->d_scanned;
-  P.timing = nullptr;
-  if (const char *tm = getenv("GB200_SCAN_TIMING")) {
-    if (tm[0] == '1') {
-      if (!ix->d_timing) {
-        CK(cudaMalloc(&ix->d_timing, 8 * sizeof(unsigned long long)));
-      }
-      CK(cudaMemsetAsync(ix->d_timing, 0, 8 * sizeof(unsigned long long), ix->stream));
-      P.timing = ix->d_timing;
-    }
-  }
   P.n = n;
   P.d = ix->p.d;
   P.M = M;
   P.dsub = ix->dsub;
   P.nlist = ix->p.nlist;
   P.nprobe = nprobe;
-  P.S = S;
   P.R = R;
   P.cap = cap;
   P.chunk = ix->chunk;
-  P.max_np_s = (plan && n_full > 0) ? nprobe : (nprobe + S - 1) / S;
-  P.items = nullptr;
-  P.n_items = 0;
-  P.n_full = 0;
-  P.s_tail = 1;
   P.is_ip = ip ? 1 : 0;
-  {
-    const char *fs = getenv("GB200_SCAN_FORCE_SYM");
-    P.force_sym = (fs && fs[0] == '1') ? 1 : 0;
-    const char *nt = getenv("GB200_SCAN_NO_TMA");
-    P.no_tma = (nt && nt[0] == '1') ? 1 : 0;
-    P.m32_threads = m32_threads;
-    P.variant = variant;
-    P.pf_blocks = pf_blocks;
-    P.steal = 0;
-    if (const char *e = getenv("GB200_SCAN_STEAL")) P.steal = e[0] == '1' ? 1 : 0;
-    P.probe_g = nullptr;
+  P.m32_threads = threads;
+  P.variant = variant;
+  P.pf_blocks = T.pf_blocks;
+  P.steal = T.steal;
+  P.s_tail = 1;
+
+  // ---- how the batch is cut into CTAs
+  int S = 1;  // candidate rows per query in the [n][S][R] buffer
+  bool plan = false;
+  int n_full = 0, s_tail = 1, n_items = 0, grid_v3 = 0;
+  if (variant == 3) {
+    // every query may be worked on by up to S CTAs at once (idle CTAs join running queries, ivfpq_scan_v3.cu)
+    S = T.max_rows > 0 ? T.max_rows : (n >= slots ? 4 : std::min(8, (slots + n - 1) / n));
+    S = std::max(1, std::min(S, 16));
+    while (S > 1 && (long long)S * R > 8192) S--;
+    grid_v3 = (int)std::min<long long>(slots, (long long)n * S);
+    P.ch_blocks = T.ch_blocks;
+    P.help_min = T.help_min;
+    P.help_window = std::min(n, 4 * slots);
+    P.max_np_s = nprobe;
+  } else {
+    // one CTA per (query, split), probes dealt round-robin.  Uniform S: the value in 1..8 that best fills whole waves of
+    // resident CTAs, charging ~4 % of a CTA per extra split for the table load / final select.
+    {
+      double best = -1.0;
+      for (int s = 1; s <= 8 && s <= nprobe; s++) {
+        const double waves = (double)n * s / slots;
+        const double eff = waves / std::ceil(waves) - 0.04 * (s - 1);
+        if (eff > best) best = eff, S = s;
+      }
+    }
+    // positional work plan (v2 / M = 64): whole waves unsplit, only the queries of the last partial wave are split
+    plan = variant == 2 && n <= 4096 && !T.splits && !T.no_plan;
+    if (plan) {
+      int rows = 1;
+      plan_work(n, slots, nprobe, R, S, T.tail, &n_full, &s_tail, &n_items, &rows);
+      S = rows;
+    }
+    if (T.splits) S = T.splits;
+    S = std::max(1, std::min(S, nprobe));
+    while (S > 1 && (long long)S * R > 8192) S--;
+    P.max_np_s = (plan && n_full > 0) ? nprobe : (nprobe + S - 1) / S;
   }
-  if (scan_smem_bytes(P, ix->mode) > 227 * 1024) {
-    set_err("scan needs %zu B shared memory (M=%d recall_num=%d): not implemented", scan_smem_bytes(P, ix->mode), M, R);
+  P.S = S;
+  CKI(ix->ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
+  P.cand = ix->ws_cand.as<u64>();
+  if (T.scan_timing && variant == 2 && ix->mode == 1) {
+    if (!ix->d_timing) CK(cudaMalloc(&ix->d_timing, 8 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ix->d_timing, 0, 8 * sizeof(unsigned long long), ix->stream));
+    P.timing = ix->d_timing;
+  }
+  const size_t smem_need = variant == 3 ? scan_v3_smem_bytes(nprobe, cap) : scan_smem_bytes(P, ix->mode);
+  if (smem_need > 227 * 1024) {
+    set_err("scan needs %zu B shared memory (M=%d recall_num=%d nprobe=%d): not implemented", smem_need, M, R, nprobe);
     return GB200_EUNSUPPORTED;
   }
   CK(cudaMemsetAsync(ix->d_scanned, 0, sizeof(unsigned long long), ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
-  P.lut_g = nullptr;
-  P.order = nullptr;
-  if (n <= 4096 && n > 148 && getenv("GB200_SCAN_ORDER")) {
-    CKI(ix->ws_order.ensure((size_t)n * sizeof(int)));
-    CK(launch_query_order(d_keys, ix->d_len, n, nprobe, ix->p.nlist, ix->ws_order.as<int>(), ix->stream));
-    ix->launches++;
-    P.order = ix->ws_order.as<int>();
-  }
+  const int *d_rows = nullptr;
   if (ix->mode == 1 || ix->mode == 2) {
-    if (ix->p.d > 1024) {
-      set_err("M=32/64 kernel: d=%d > 1024 not implemented", ix->p.d);
-      return GB200_EUNSUPPORTED;
-    }
+    // per-query lookup tables: built on the side stream during the coarse stage (ivfpq_search_impl), else here
     const size_t lut_bytes = ix->mode == 2 ? 98304 : 65536;
     if (ix->lut_built_n == n && ix->lut_built_ip == (ip ? 1 : 0)) {
-      CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));  // built on the side stream during the coarse stage
+      CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));
     } else {
       CKI(ix->ws_lut.ensure((size_t)n * lut_bytes));
       if (ix->mode == 2)
@@ -889,20 +913,23 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     }
     ix->lut_built_n = 0;
     P.lut_g = ix->ws_lut.as<float>();
-    if (variant == 2) {
+    if (variant == 3) {
+      // control words [next_q, pad x3][claim x n][rows x n], zeroed; per-query probe tables
+      CKI(ix->ws_ctl.ensure((size_t)(4 + 2 * (size_t)n) * sizeof(int)));
+      CK(cudaMemsetAsync(ix->ws_ctl.p, 0, (size_t)(4 + 2 * (size_t)n) * sizeof(int), ix->stream));
+      P.v3_next_q = ix->ws_ctl.as<int>();
+      P.v3_claim = ix->ws_ctl.as<int>() + 4;
+      P.v3_rows = ix->ws_ctl.as<int>() + 4 + n;
+      d_rows = P.v3_rows;
+      CKI(ix->ws_probe.ensure((size_t)n * scan_v3_probe_bytes(nprobe)));
+      P.probe_g = ix->ws_probe.as<unsigned char>();
+      CK(launch_probe_setup_v3(P, ix->stream));
+      ix->launches++;
+    } else {
       if (plan) {
         P.n_items = n_items;
         P.n_full = n_full;
         P.s_tail = s_tail;
-      }
-      if (plan && ix->mode == 1 && getenv("GB200_SCAN_SORTED")) {  // optional: heaviest queries first (costs a single-CTA sort)
-        CKI(ix->ws_items.ensure((size_t)n_items * sizeof(int4)));
-        CKI(ix->ws_nsplit.ensure((size_t)n * sizeof(int)));
-        CK(launch_plan_items(d_keys, ix->d_len, n, nprobe, ix->p.nlist, n_full, s_tail, ix->ws_items.as<int4>(),
-                             ix->ws_nsplit.as<int>(), ix->stream));
-        ix->launches++;
-        P.items = ix->ws_items.as<int4>();
-        P.n_items = n_items;
       }
       CKI(ix->ws_probe.ensure((size_t)(plan ? n_items : n * S) * scan_probe_bytes_host(P.max_np_s)));
       P.probe_g = ix->ws_probe.as<unsigned char>();
@@ -911,7 +938,8 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     }
   }
   if (ix->profiling) CK(cudaEventRecord(ix->ev[4], ix->stream));
-  CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
+  if (variant == 3) CK(launch_ivfpq_scan_v3(P, grid_v3, ix->stream));
+  else CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[5], ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));
   RerankParams Q;
@@ -935,8 +963,8 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   Q.is_ip = ip ? 1 : 0;
   Q.min_score = sp->min_score;
   Q.max_score = sp->max_score;
-  Q.nsplit = P.items ? ix->ws_nsplit.as<int>() : nullptr;
-  Q.n_full = (P.n_items > 0 && !P.items) ? P.n_full : 0;
+  Q.nsplit = d_rows;  // v3: rows handed out per query (clamped to S by the kernel)
+  Q.n_full = P.n_items > 0 ? P.n_full : 0;
   CK(launch_rerank(Q, ix->stream));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[3], ix->stream));
   ix->launches += 2;
@@ -945,7 +973,7 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
 
 static int finish_profile(gb200_index *ix) {
   unsigned long long sc = 0;
-  if (ix->d_timing && getenv("GB200_SCAN_TIMING")) {
+  if (ix->d_timing && ix->tune.scan_timing) {
     unsigned long long t[8];
     CK(cudaMemcpyAsync(t, ix->d_timing, sizeof(t), cudaMemcpyDeviceToHost, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
@@ -1006,7 +1034,7 @@ static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on
   CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
   if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
   ix->lut_built_n = 0;
-  if ((ix->mode == 1 || ix->mode == 2) && d <= 1024 && !keys_h && !getenv("GB200_LUT_INLINE")) {
+  if ((ix->mode == 1 || ix->mode == 2) && d <= 1024 && !keys_h && !ix->tune.lut_inline) {
     // K2a depends on the queries only: fork it onto the side stream so it overlaps the coarse quantiser
     const int ipm = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
     CKI(ix->ws_lut.ensure((size_t)n * (ix->mode == 2 ? 98304 : 65536)));
@@ -1150,7 +1178,7 @@ static int flat_tc_dev(gb200_index *ix, int n, const float *d_xq, int k, const g
   ix->launches += 2;
   long long nc_max = ((1LL << 26) / n) & ~127LL;  // distance tile <= 256 MB
   if (nc_max < 1024) nc_max = 1024;
-  if (const char *e = getenv("GB200_FLAT_CHUNK_ROWS")) nc_max = std::max(1024LL, (long long)atoll(e) & ~127LL);  // tests: force many chunks
+  if (ix->tune.flat_chunk_rows > 0) nc_max = std::max(1024LL, ix->tune.flat_chunk_rows & ~127LL);  // tests: force many chunks
   if (nc_max > ix->raw_n) nc_max = (ix->raw_n + 127) & ~127LL;
   CKI(ix->ws_dist.ensure((size_t)n * nc_max * sizeof(float)));
   const int Kp = flat_tc_candidates(k);
@@ -1207,9 +1235,7 @@ static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, in
     d_I = ix->ws_out_i.as<long long>();
   }
   // batches go through the tensor cores (GB200_FLAT=exact forces the per-query exact scan)
-  const char *fmode = getenv("GB200_FLAT");
-  const bool force_exact = fmode && !strcmp(fmode, "exact");
-  const bool force_tc = fmode && !strcmp(fmode, "tc");
+  const bool force_exact = ix->tune.flat_mode == 1, force_tc = ix->tune.flat_mode == 2;
   if (!force_exact && (n >= 16 || force_tc) && (d % 4 == 0) && k <= 1024) {
     if (ix->profiling) {
       CK(cudaEventRecord(ix->ev[0], ix->stream));
@@ -1345,6 +1371,12 @@ int gb200_sync(gb200_index *ix) {
   std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
   return finish_profile(ix);
+}
+int gb200_reload_tuning(gb200_index *ix) {
+  if (!ix) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->tune.read();
+  return GB200_OK;
 }
 int gb200_set_profiling(gb200_index *ix, int enable) {
   if (!ix) return GB200_EINVAL;

@@ -91,6 +91,10 @@ struct BlockTopR {
   int *warp_part;      // [2][32] shared scratch for counts
   int cap;
   int R;
+  // optional float image of tau's distance word (the v3 scan pre-tests candidates with one FSETP against it):
+  // L2: admit only dis <= *tau_f, InnerProduct: dis >= *tau_f.  nullptr = not maintained.
+  float *tau_f = nullptr;
+  int is_ip = 0;
 
   __device__ __forceinline__ void init_collective() {
     if (threadIdx.x == 0) {
@@ -282,7 +286,10 @@ struct BlockTopR {
       for (int j = 0; j < PER; j++)
         if ((keep >> j) & 1u) buf[o++] = k[j];
     }
-    if (tid == 0) *tau = tstar + 1;  // admit only strictly better than the R-th
+    if (tid == 0) {
+      *tau = tstar + 1;  // admit only strictly better than the R-th
+      if (tau_f) *tau_f = key32_to_dist((uint32_t)((tstar + 1) >> 32), is_ip != 0);
+    }
     __syncthreads();
   }
 

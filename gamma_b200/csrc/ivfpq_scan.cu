@@ -23,12 +23,7 @@
 // posting mirror stores each posting's code bytes pre-rotated by its lane so the byte for
 // step s sits at a compile-time register position; one PRMT builds (code << 8 | lane*4) and
 // the LDS carries 4*s as an immediate:  PRMT + LDS + FADD per lookup.
-#include "common.cuh"
-#include "kernels.h"
-
-// dynamic shared memory at file scope so PTX can name it: its shared-window address is a link-time
-// constant that ptxas folds into the LDS immediate (no per-lookup base add).
-extern __shared__ __align__(16) unsigned char gb_scan_smem[];
+#include "scan_common.cuh"
 
 namespace gb {
 
@@ -39,13 +34,6 @@ constexpr int SCAN_U = 2;  // 32-posting blocks per warp per round
 constexpr int SCAN_ROUND_POSTINGS = SCAN_WARPS * SCAN_U * 32;
 // M = 32 kernel: 12 warps, 3 CTAs per SM (36 resident warps), sync point every M32_U blocks per warp
 constexpr int M32_U = 8;
-
-struct ProbeInfo {
-  long long off;  // first posting of the list in the pools
-  int len;        // postings visible to the scan (retrieve_idx_pos_)
-  int rank;       // probe rank in the query's coarse ordering (tie-break order)
-  float dis0;
-};
 
 // shared-memory carve-up (host mirrors this in scan_smem_bytes)
 //  [lut][buf u64 cap][qs d floats][probe infos][blk prefix][misc]
@@ -266,276 +254,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_generic_kernel(ScanPa
   write_survivors<PER>(topr, P, q, split);
 }
 
-// =============================================================================================
-// M = 32 kernel: conflict-free table, TMA-staged codebook, software-pipelined posting loads
-// =============================================================================================
-// ---- mbarrier / TMA bulk-copy wrappers (cp.async.bulk -> UBLKCP in SASS)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
-                                             unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-struct Pre {  // one prefetched 32-posting block, per lane
-  uint4 c0, c1;
-  int id;        // vid, < 0 = padding / dead / beyond the list end
-  float nrm;     // t(p)  (L2 only) — consumed one block later, never at load time
-  float base;    // dis0 of the list
-  uint32_t seq;  // (probe rank << 21) | position ; 0xffffffff = no block
-};
-
-// LDS addressing of the table.  RAW: the table's shared-window address is the constant
-// GB_SMEM_RESERVED (dynamic shared memory starts right after the 1 KB the driver reserves per CTA on
-// sm_90+, cudaDevAttrReservedSharedMemoryPerBlock), so "prmt + const + 4*s" is the complete address and
-// the lookup is PRMT + LDS + FADD.  The kernel verifies the assumption at run time and otherwise takes
-// the SYM path (address through the symbol: one extra integer add per lookup).
-#define GB_SMEM_RESERVED 1024
-template <bool RAW, int S0>
-__device__ __forceinline__ float lut_at(uint32_t off) {
-  if (RAW) {
-    float v;
-    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(GB_SMEM_RESERVED + 4 * S0));
-    return v;
-  } else {
-    return *reinterpret_cast<const float *>(gb_scan_smem + off + 4 * S0);
-  }
-}
-template <bool RAW, int S0>
-__device__ __forceinline__ void adc_m32_word(uint32_t word, uint32_t lane4, float &a0, float &a1, float &a2,
-                                             float &a3) {
-  // selector nibbles [3]=5 (zero) [2]=5 (zero) [1]=code byte j [0]=4 (lane4)
-  a0 += lut_at<RAW, S0 + 0>(__byte_perm(word, lane4, 0x5504));
-  a1 += lut_at<RAW, S0 + 1>(__byte_perm(word, lane4, 0x5514));
-  a2 += lut_at<RAW, S0 + 2>(__byte_perm(word, lane4, 0x5524));
-  a3 += lut_at<RAW, S0 + 3>(__byte_perm(word, lane4, 0x5534));
-}
-template <bool RAW>
-__device__ __forceinline__ float adc_m32(uint32_t lane4, const uint4 &c0, const uint4 &c1) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  adc_m32_word<RAW, 0>(c0.x, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 4>(c0.y, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 8>(c0.z, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 12>(c0.w, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 16>(c1.x, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 20>(c1.y, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 24>(c1.z, lane4, a0, a1, a2, a3);
-  adc_m32_word<RAW, 28>(c1.w, lane4, a0, a1, a2, a3);
-  return (a0 + a1) + (a2 + a3);
-}
-
-// main loop of the M = 32 kernel.
-//  * every warp owns a CONTIGUOUS range of the query's 32-posting blocks: per-list state lives in
-//    registers, a new list costs one shared-memory read; selection does not depend on the order in which
-//    warps see postings (ties are broken by seq);
-//  * the next block's codes/id/t(p) are in flight while the current block is looked up;
-//  * warps run free for up to M32_U blocks between CTA-wide sync points.  A warp whose append does not fit
-//    in the candidate buffer keeps the unwritten candidates in registers ("stalled"), asks for a prune
-//    at the sync point and retries afterwards — so no headroom has to be reserved per round.
-template <bool IP, bool HAS_VALID, bool RAW, int M32_WARPS, int PER>
-__device__ __forceinline__ void scan_loop_m32(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
-                                              int total_blocks) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lane4 = lane * 4;
-  const int per_warp = (total_blocks + M32_WARPS - 1) / M32_WARPS;
-  const int w0 = min(total_blocks, warp * per_warp);
-  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
-  const int soft_limit = P.cap - M32_WARPS * 32;
-  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
-
-  int pj = 0;
-  if (left > 0)  // blk_prefix[pj] <= w0 < blk_prefix[pj + 1]; terminates because w0 < total_blocks
-    while (S.blk_prefix[pj + 1] <= w0) pj++;
-  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
-  uint32_t seq0 = 0;
-  float dis0 = 0.f;
-  const uint8_t *cptr = nullptr;
-  const int *iptr = nullptr;
-  const float *nptr = nullptr;
-  auto open_list = [&](int j, int b_start) {
-    const ProbeInfo pi = S.pinfo[j];
-    bl = ((pi.len + 31) >> 5) - b_start;
-    dis0 = pi.dis0;
-    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
-    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
-    const long long first = pi.off + (long long)b_start * 32;
-    cptr = P.codes + (size_t)first * 32 + lane * 16;
-    iptr = P.ids + first + lane;
-    nptr = P.norms + first + lane;
-  };
-  if (left > 0) open_list(pj, w0 - S.blk_prefix[pj]);
-
-  auto load_block = [&]() -> Pre {
-    Pre x;
-    x.seq = 0xffffffffu;
-    x.id = -1;
-    x.base = 0.f;
-    x.nrm = 0.f;
-    x.c0 = make_uint4(0, 0, 0, 0);
-    x.c1 = x.c0;
-    if (left > 0) {  // warp-uniform
-      while (bl == 0) open_list(++pj, 0);
-      // 32-posting block = 2 chunks of 512 B: chunk j of posting `lane` at (j*32 + lane)*16
-      x.c0 = ldg_nc_v4(cptr);
-      x.c1 = ldg_nc_v4(cptr + 512);
-      x.seq = seq0;
-      x.base = dis0;
-      if (len > 0) {
-        x.id = ldg_nc_s32(iptr);
-        if (!IP) x.nrm = ldg_nc_f32(nptr);
-      }
-      cptr += 1024;
-      iptr += 32;
-      nptr += 32;
-      seq0 += 32;
-      len -= 32;
-      bl--;
-      left--;
-    }
-    return x;
-  };
-
-  // append what passes; returns true when some lane of the warp could not be written (buffer full)
-  u64 skey = 0;
-  bool spend = false;
-  auto try_append = [&](bool pass, u64 key) -> bool {
-    const unsigned m = __ballot_sync(GB_FULL, pass);
-    if (m == 0) return false;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
-    base = __shfl_sync(GB_FULL, base, leader);
-    const int slot = base + __popc(m & ((1u << lane) - 1u));
-    bool pending = pass;
-    if (pass && slot < topr.cap) {
-      topr.buf[slot] = key;
-      pending = false;
-    }
-    spend = pending;
-    skey = key;
-    return __any_sync(GB_FULL, pending);
-  };
-
-  bool stalled = false;
-  // look up one prefetched block and append what passes (sets `stalled` when the buffer is full)
-  auto process = [&](const Pre &cur) {
-    uint32_t vw = 0xffffffffu;
-    if (HAS_VALID) vw = cur.id >= 0 ? __ldg(P.valid + (cur.id >> 5)) : 0u;  // latency hidden by the lookups
-    const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
-    const float dis = (cur.base + cur.nrm) + adc_m32<RAW>(lane4, cur.c0, cur.c1);
-    bool ok = cur.id >= 0;
-    if (HAS_VALID) ok = ok && ((vw >> (cur.id & 31)) & 1u);
-    const uint32_t k32 = dist_to_key32<IP>(dis);
-    bool pass = ok && (dis == dis) && k32 <= tau_hi;  // cheap pre-test on the distance word
-    if (__any_sync(GB_FULL, pass)) {
-      const u64 key = ((u64)k32 << 32) | cur.seq;
-      stalled = try_append(pass && key < topr.threshold(), key);
-    }
-  };
-
-  // One block per iteration, next block's loads issued before the current block's lookups.  The body is
-  // kept to ~300 instructions (4.8 KB) on purpose: unrolled / ping-pong variants measured 25 % slower
-  // because the loop no longer fits the L0 instruction cache.
-  Pre nxt = load_block();
-  int round = 0;
-  for (;;) {
-    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
-    int done = 0;
-    while (!stalled && done < M32_U && nxt.seq != 0xffffffffu) {  // warp-uniform
-      const Pre cur = nxt;
-      nxt = load_block();
-      process(cur);
-      done++;
-    }
-    const bool more = stalled || nxt.seq != 0xffffffffu;
-    const bool over = stalled || *((volatile int *)topr.cnt) > soft_limit;
-    const int slot = round % 3;
-    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
-    __syncthreads();
-    const int v = flags[slot];
-    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
-    round++;
-    if (v & 1) {
-      long long tp0 = clock64();
-      topr.prune_collective<PER>();
-      if (P.timing && threadIdx.x == 0) {
-        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
-        atomicAdd(P.timing + 5, 1ull);
-      }
-    }
-    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
-    if (!(v & 2)) break;
-  }
-}
-
 #define GB_TICK(slot)                                                   \
   if (P.timing && threadIdx.x == 0) {                                   \
     long long t_now = clock64();                                        \
     atomicAdd(P.timing + (slot), (unsigned long long)(t_now - t_last)); \
     t_last = t_now;                                                     \
   }
-
-template <bool IP, int M32_THREADS, int PER>
-__global__ void __launch_bounds__(M32_THREADS, PER == 4 ? 3 : 1) ivfpq_scan_m32_kernel(ScanParams P) {
-  constexpr int M32_WARPS = M32_THREADS / 32;
-  long long t_last = clock64();
-  // heaviest queries first (longest-processing-time order) so the last wave is filled with light ones
-  const int q = P.order ? P.order[blockIdx.y] : blockIdx.y;
-  const int split = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  const int d = P.d;
-  ScanSmem S = carve(gb_scan_smem, P, 1);
-  BlockTopR topr = make_topr(S, P);
-  const float *xq = P.xq + (size_t)q * d;
-  if (tid == 0) {
-    *topr.cnt = 0;
-    *topr.tau = GB_KEY_MAX;
-    S.misc[68] = S.misc[69] = S.misc[70] = 0;
-    mbar_init(&S.mbar[0], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // ---- the query's lookup table [256][64] (built once per query by lut_build_kernel, L2-resident) is
-  // pulled into shared memory by four 16 KB TMA bulk copies; the probe setup below overlaps the transfer.
-  if (tid == 0) {
-    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
-    mbar_expect_tx(&S.mbar[0], 65536u);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
-  }
-  const int total_blocks = setup_probes<IP>(P, S, xq, q, split);
-  GB_TICK(1);  // probe setup
-  mbar_wait(&S.mbar[0], 0);
-  GB_TICK(0);  // wait for the table
-  const bool raw_ok = smem_u32(gb_scan_smem) == GB_SMEM_RESERVED && !P.force_sym;  // CTA-uniform
-  if (P.valid) {
-    if (raw_ok) scan_loop_m32<IP, true, true, M32_WARPS, PER>(P, S, topr, total_blocks);
-    else scan_loop_m32<IP, true, false, M32_WARPS, PER>(P, S, topr, total_blocks);
-  } else {
-    if (raw_ok) scan_loop_m32<IP, false, true, M32_WARPS, PER>(P, S, topr, total_blocks);
-    else scan_loop_m32<IP, false, false, M32_WARPS, PER>(P, S, topr, total_blocks);
-  }
-  GB_TICK(2);  // scan loop incl. in-loop prunes
-  write_survivors<PER>(topr, P, q, split);
-  GB_TICK(3);  // final prune + write
-  if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
-}
 
 // =============================================================================================
 // M = 32 kernel, v2.  Same data structures and selection as above; what changed and why (profiles/r01a):
@@ -551,21 +275,6 @@ __global__ void __launch_bounds__(M32_THREADS, PER == 4 ? 3 : 1) ivfpq_scan_m32_
 //  * the posting stream is pulled towards L2 `pf` blocks ahead with prefetch.global.L2 (one
 //    instruction per block, one 128 B line per lane), so the register prefetch only has to cover L2 latency.
 // =============================================================================================
-__device__ __forceinline__ void l2_prefetch_line(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ uint32_t prmt_v(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-template <int S0>
-__device__ __forceinline__ float lds_raw(uint32_t off) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(GB_SMEM_RESERVED + 4 * S0));
-  return v;
-}
-
 // STEAL (opt-in, GB200_SCAN_STEAL=1, not yet validated on hardware): intra-CTA work stealing.  Every warp still owns a
 // contiguous share of the CTA's blocks and walks it front to back, but claims it STEAL_CH blocks at a time from a
 // shared (front, back) word; a warp whose share is empty takes chunks from the BACK of the share with the most
@@ -868,17 +577,14 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanPa
   size_t item;
   if (P.n_items > 0) {
     item = blockIdx.x;
-    if (P.items) {
-      const int4 it = P.items[blockIdx.x];
-      q = it.x, split = it.y, nsp = it.z;
-    } else if ((int)blockIdx.x < P.n_full) {
+    if ((int)blockIdx.x < P.n_full) {
       q = blockIdx.x, split = 0, nsp = 1;
     } else {
       const int t = blockIdx.x - P.n_full;
       q = P.n_full + t / P.s_tail, split = t % P.s_tail, nsp = P.s_tail;
     }
   } else {
-    q = P.order ? P.order[blockIdx.y] : blockIdx.y;
+    q = blockIdx.y;
     split = blockIdx.x, nsp = P.S;
     item = (size_t)q * P.S + split;
   }
@@ -925,10 +631,7 @@ __global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (item >= (P.n_items > 0 ? P.n_items : P.n * P.S)) return;
   int q, split, nsp;
-  if (P.items) {
-    const int4 it = P.items[item];
-    q = it.x, split = it.y, nsp = it.z;
-  } else if (P.n_items > 0) {
+  if (P.n_items > 0) {
     if (item < P.n_full) {
       q = item, split = 0, nsp = 1;
     } else {
@@ -1035,81 +738,6 @@ cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_
   return cudaGetLastError();
 }
 
-// work[q] = postings the query will scan; order = queries by descending work (single CTA, n <= 4096)
-__global__ void __launch_bounds__(1024) query_order_kernel(const int *__restrict__ keys, const int *__restrict__ list_len,
-                                                           int n, int nprobe, int nlist, int p2, int *__restrict__ order) {
-  extern __shared__ __align__(16) unsigned char osm[];
-  u64 *k = reinterpret_cast<u64 *>(osm);
-  for (int q = threadIdx.x; q < p2; q += blockDim.x) {
-    u64 key = GB_KEY_MAX;
-    if (q < n) {
-      unsigned w = 0;
-      for (int p = 0; p < nprobe; p++) {
-        int key_l = keys[(size_t)q * nprobe + p];
-        if (key_l >= 0 && key_l < nlist) w += (unsigned)list_len[key_l];
-      }
-      key = ((u64)(~w) << 32) | (unsigned)q;
-    }
-    k[q] = key;
-  }
-  __syncthreads();
-  block_bitonic_sort(k, p2);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = (int)(unsigned)k[i];
-}
-
-// K2c — work plan of one batch (single CTA, n <= 4096): queries sorted by the number of postings they will scan,
-// heaviest first (longest-processing-time order); the first n_full of them become one work item each, the
-// remaining n - n_full (the last, partial wave of resident CTAs) are cut into s_tail items each so that the
-// tail of the launch is made of short items that fill the machine.  nsplit[q] tells the re-rank how many
-// candidate rows the query has.
-__global__ void __launch_bounds__(1024) plan_items_kernel(const int *__restrict__ keys, const int *__restrict__ list_len,
-                                                          int n, int nprobe, int nlist, int p2, int n_full, int s_tail,
-                                                          int4 *__restrict__ items, int *__restrict__ nsplit) {
-  extern __shared__ __align__(16) unsigned char osm[];
-  u64 *k = reinterpret_cast<u64 *>(osm);
-  for (int q = threadIdx.x; q < p2; q += blockDim.x) {
-    u64 key = GB_KEY_MAX;
-    if (q < n) {
-      unsigned w = 0;
-      for (int p = 0; p < nprobe; p++) {
-        int key_l = keys[(size_t)q * nprobe + p];
-        if (key_l >= 0 && key_l < nlist) w += (unsigned)list_len[key_l];
-      }
-      key = ((u64)(~w) << 32) | (unsigned)q;
-    }
-    k[q] = key;
-  }
-  __syncthreads();
-  block_bitonic_sort(k, p2);
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    const int q = (int)(unsigned)k[r];
-    if (r < n_full) {
-      items[r] = make_int4(q, 0, 1, 0);
-      nsplit[q] = 1;
-    } else {
-      for (int s = 0; s < s_tail; s++) items[n_full + (r - n_full) * s_tail + s] = make_int4(q, s, s_tail, 0);
-      nsplit[q] = s_tail;
-    }
-  }
-}
-
-cudaError_t launch_plan_items(const int *keys, const int *list_len, int n, int nprobe, int nlist, int n_full, int s_tail,
-                              int4 *items, int *nsplit, cudaStream_t st) {
-  int p2 = next_pow2(n);
-  if (p2 > 4096) return cudaErrorInvalidValue;
-  plan_items_kernel<<<1, 1024, (size_t)p2 * sizeof(u64), st>>>(keys, list_len, n, nprobe, nlist, p2, n_full, s_tail, items,
-                                                               nsplit);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_query_order(const int *keys, const int *list_len, int n, int nprobe, int nlist, int *order,
-                               cudaStream_t st) {
-  int p2 = next_pow2(n);
-  if (p2 > 4096) return cudaErrorInvalidValue;
-  query_order_kernel<<<1, 1024, (size_t)p2 * sizeof(u64), st>>>(keys, list_len, n, nprobe, nlist, p2, order);
-  return cudaGetLastError();
-}
-
 int scan_buffer_cap(int R) {
   // room for R survivors + one full round of admissions (generic kernel's lock-step rounds)
   int need = R + SCAN_ROUND_POSTINGS;
@@ -1131,13 +759,6 @@ static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int th
   if (P.n_items > 0) grid = dim3(P.n_items, 1);
   kernel<<<grid, threads, smem, st>>>(P);
   return cudaGetLastError();
-}
-
-template <int T, int PER>
-static cudaError_t launch_m32(const ScanParams &P, cudaStream_t st) {
-  static size_t conf[2] = {0, 0};
-  return P.is_ip ? launch_kernel(ivfpq_scan_m32_kernel<true, T, PER>, P, 1, T, &conf[0], st)
-                 : launch_kernel(ivfpq_scan_m32_kernel<false, T, PER>, P, 1, T, &conf[1], st);
 }
 
 template <int T, int MINB>
@@ -1456,17 +1077,11 @@ static cudaError_t launch_m64(const ScanParams &P, cudaStream_t st) {
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
   if (mode == 2) return P.cap <= 4 * 384 ? launch_m64<4>(P, st) : launch_m64<16>(P, st);
-  if (mode == 1) {
-    if (P.variant == 2 && scan_m32_v2_usable(P) && P.steal && P.m32_threads == 256) return launch_m32_v2_steal(P, st);
-    if (P.variant == 2 && scan_m32_v2_usable(P))
-      return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)
-             : P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
-    if (P.cap > 4 * 256) return launch_m32<256, 16>(P, st);  // large recall_num: 16 keys per thread in the select
-    switch (P.m32_threads) {
-      case 384: return launch_m32<384, 4>(P, st);
-      case 320: return launch_m32<320, 4>(P, st);
-      default: return launch_m32<256, 4>(P, st);
-    }
+  if (mode == 1) {  // M = 32, v2 (the default v3 kernel is launched through launch_ivfpq_scan_v3)
+    if (!scan_m32_v2_usable(P)) return cudaErrorInvalidValue;
+    if (P.steal && P.m32_threads == 256) return launch_m32_v2_steal(P, st);
+    return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)
+           : P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
   }
   if (P.cap > 4 * SCAN_THREADS)
     return P.is_ip ? launch_kernel(ivfpq_scan_generic_kernel<true, 16>, P, 0, SCAN_THREADS, &conf[0], st)

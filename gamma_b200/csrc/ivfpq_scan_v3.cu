@@ -1,0 +1,531 @@
+// K2 (v3) — the IVFPQ ADC scan for M = 32 as a PERSISTENT kernel with dynamic work distribution.
+// Same arithmetic, table layout, posting layout and selection (BlockTopR) as ivfpq_scan.cu; what changed, and why
+// (profiles/r01c_scan_m32_v2_ncu_summary.txt: issue slots 67.7 % busy, 211 issued instructions per 32-posting block,
+// 17 % of warp time at the CTA's final barrier, 12 % of the launch is tail):
+//
+//  * one CTA per resident slot (SMs x CTAs/SM) instead of one CTA per (query, split).  A CTA takes the next query
+//    from a global counter, loads its table (TMA bulk copy, one mbarrier reused with alternating parity) and scans;
+//    no wave quantisation, no host-side plan.
+//  * inside a query the unit of work is an ITEM = up to ch_blocks consecutive 32-posting blocks of ONE probed list.
+//    Every warp claims items one at a time with an atomicAdd on the query's counter (the claim for the next item is
+//    in flight while the current one is scanned), so warps of a CTA finish within one item of each other — there is
+//    no static split to be unlucky with;
+//  * the counter lives in global memory, so several CTAs can work on ONE query: when the query queue is empty a
+//    CTA that would otherwise idle looks for the running query with the most unclaimed items, takes a candidate row
+//    of it (rows[q]), loads the same table and claims from the same counter.  The tail of the launch is split
+//    exactly as far as the idle CTAs allow; K3 merges the rows.  (Batches smaller than the machine are spread the
+//    same way from the first cycle.)
+//  * the loop itself: all per-block addressing derives from ONE incrementing block index (three IMAD.WIDE against
+//    per-lane constant bases; existence of the lane's posting, L2-prefetch bound and scan-order word are compares /
+//    adds against per-item constants), and the 32 table words are accumulated with packed adds
+//    (add.f32x2 -> FADD2): ~115 issued instructions per block instead of ~165.
+//
+// Reference being replaced (file:line): GammaIVFPQScanner::scan_list_with_table index/impl/gamma_index_ivfpq.h:576-601,
+// KnnSearchResults::add :351-370, scan_one_list / the probe loop index/impl/gamma_index_ivfpq.cc:597-640, 790-818,
+// RTInvertIndex::GetIvtList realtime/realtime_invert_index.cc:77-81.
+#include "scan_common.cuh"
+
+namespace gb {
+
+// shared-memory carve-up (host mirrors it in scan_v3_smem_bytes).  Everything the hot loop touches sits at a
+// COMPILE-TIME shared-window address (table at GB_SMEM_RESERVED, control words right behind it), so those accesses need
+// no address registers; only the candidate buffer and the item prefix depend on run-time sizes.
+//   [lut 64 KB][misc 96 ints][mbar 16 B][ProbeInfo x nprobe][item prefix x (nprobe + 1), padded to 16][buf u64 cap]
+// misc: [0..1] tau, [2] cnt, [3] tau_f, [4..67] scratch, [68..70] round flags, [72] q, [73] row
+constexpr int V3_MISC_OFF = 65536;
+constexpr int V3_MBAR_OFF = V3_MISC_OFF + 96 * 4;
+constexpr int V3_PINFO_OFF = V3_MBAR_OFF + 16;
+struct V3Smem {
+  u64 *buf;
+  ProbeInfo *pinfo;
+  int *item_prefix;
+  int *misc;
+  unsigned long long *mbar;
+};
+
+__host__ __device__ inline size_t v3_probe_bytes(int nprobe) {
+  size_t b = (size_t)nprobe * sizeof(ProbeInfo) + (size_t)(nprobe + 1) * sizeof(int);
+  return (b + 15) & ~(size_t)15;
+}
+size_t scan_v3_probe_bytes(int nprobe) { return v3_probe_bytes(nprobe); }
+size_t scan_v3_smem_bytes(int nprobe, int cap) { return V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64); }
+
+__device__ __forceinline__ V3Smem v3_carve(unsigned char *smem, int nprobe) {
+  V3Smem S;
+  S.misc = reinterpret_cast<int *>(smem + V3_MISC_OFF);
+  S.mbar = reinterpret_cast<unsigned long long *>(smem + V3_MBAR_OFF);
+  S.pinfo = reinterpret_cast<ProbeInfo *>(smem + V3_PINFO_OFF);
+  S.item_prefix = reinterpret_cast<int *>(smem + V3_PINFO_OFF + (size_t)nprobe * sizeof(ProbeInfo));
+  S.buf = reinterpret_cast<u64 *>(smem + V3_PINFO_OFF + v3_probe_bytes(nprobe));
+  return S;
+}
+
+// volatile reads of a control word at a compile-time offset from a shared-window address held in a register
+template <int OFF>
+__device__ __forceinline__ int lds_ctl_s32(uint32_t base) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(base), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_ctl_f32(uint32_t base) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+// base + a * B as one IMAD.WIDE (a: block index, B: bytes per block)
+template <int B>
+__device__ __forceinline__ const unsigned char *wide_at(const void *base, uint32_t a) {
+  const unsigned char *r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "n"(B), "l"(base));
+  return r;
+}
+__device__ __forceinline__ const unsigned char *wide_at_r(const void *base, uint32_t a, uint32_t b) {
+  const unsigned char *r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(base));
+  return r;
+}
+// keep a kernel-lifetime per-lane constant in registers (stops the compiler from re-deriving it inside the loop)
+template <typename T>
+__device__ __forceinline__ T *pin_ptr(T *p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
+__device__ __forceinline__ int ld_volatile_s32(const int *p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2b (v3) — per-query probe table in the scan's shared-memory layout: list extents, dis0, exclusive prefix of the
+// per-list ITEM counts (ceil(blocks / ch_blocks)).  One warp per query.  scan_one_list's list lookup
+// (gamma_index_ivfpq.cc:597-640) and dis0 of precompute_list_tables (gamma_index_ivfpq.h:216-230, 236-299).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= P.n) return;
+  const int np = P.nprobe, ch = P.ch_blocks;
+  unsigned char *dst = P.probe_g + (size_t)q * v3_probe_bytes(np);
+  ProbeInfo *pinfo = reinterpret_cast<ProbeInfo *>(dst);
+  int *prefix = reinterpret_cast<int *>(dst + (size_t)np * sizeof(ProbeInfo));
+  const float *xq = P.xq + (size_t)q * P.d;
+  int carry = 0;
+  unsigned my_postings = 0;
+  for (int j0 = 0; j0 < np; j0 += 32) {
+    const int j = j0 + lane;
+    ProbeInfo pi;
+    pi.off = 0, pi.len = 0, pi.rank = j, pi.dis0 = 0.f;
+    if (j < np) {
+      const int key = P.keys[(size_t)q * np + j];
+      if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
+        pi.off = P.list_off[key];
+        pi.len = P.list_len[key];
+        if (P.is_ip) {  // dis0 = <q, centroid>
+          const float *cen = P.centroids + (size_t)key * P.d;
+          float s = 0.f;
+          for (int i = 0; i < P.d; i++) s = fmaf(__ldg(xq + i), __ldg(cen + i), s);
+          pi.dis0 = s;
+        } else {
+          pi.dis0 = P.coarse_dis[(size_t)q * np + j];
+        }
+      }
+      pinfo[j] = pi;
+    }
+    const int nb = (pi.len + 31) >> 5;
+    const int ni = (nb + ch - 1) / ch;
+    int incl = ni;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(GB_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (j < np) prefix[j] = carry + incl - ni;
+    carry += __shfl_sync(GB_FULL, incl, 31);
+    my_postings += (unsigned)pi.len;
+  }
+  my_postings = __reduce_add_sync(GB_FULL, my_postings);
+  if (lane == 0) {
+    prefix[np] = carry;
+    if (P.scanned) atomicAdd(P.scanned, (unsigned long long)my_postings);
+  }
+}
+
+cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st) {
+  probe_setup_v3_kernel<<<(P.n + 7) / 8, 256, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the scan of one (query, row) by one CTA
+// ---------------------------------------------------------------------------------------------------------------
+template <bool IP, bool HAS_VALID, int WARPS, int PER>
+__device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Smem &S, BlockTopR &topr, const int q,
+                                                 const int it_first) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lane4 = lane * 4;
+  const int np = P.nprobe;
+  const int n_items = S.item_prefix[np];
+  const int ch = P.ch_blocks;
+  const int pf = P.pf_blocks;
+  // lane * 0 (a run-time zero the compiler cannot see through): with a provably warp-uniform address ptxas rewrites the
+  // claim below into its warp-aggregated form, whose broadcast shuffle waits for the atomic at the point of issue
+  int *const claim = P.v3_claim + q + lane * P.v3_zero;
+  const int soft_limit = (int)pin_u32((uint32_t)(P.cap - WARPS * 32));
+  const uint32_t ctl = pin_u32(smem_u32(S.misc));  // shared-window address of the control words
+  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
+
+  // per-lane bases, constant for the whole kernel: a block is addressed by its index in the pool (bi = posting / 32)
+  //   codes: 1 KB per block, this lane's 16 B of chunk 0 at lane * 16, of chunk 1 at 512 + lane * 16
+  const unsigned char *const codes_lane = pin_ptr(P.codes + lane * 16);
+  const int *const ids_lane = pin_ptr(P.ids + lane);
+  const float *const nrm_lane = pin_ptr(P.norms + lane);
+
+  // ---- item state.  bi / bi_stop / bi_end are warp-uniform; bil, seqc differ per lane
+  uint32_t bi = 0, bi_end = 0;  // next block to LOAD / end of the current item
+  uint32_t bi_stop = 0;         // next block index at which the slow path below has something to do
+  uint32_t bil = 0;             // this lane's posting of block b exists  <=>  b < bil
+  uint32_t seqc = 0;            // scan-order word of this lane's posting in block b = seqc + 32 * (b + 1)
+  float dis0 = 0.f;
+  int it_next = it_first;       // lane 0: the claim in flight (the first one was issued by the caller)
+  bool claim_pending = true;    // a claim has been issued and not consumed yet
+  bool nx_valid = false;        // (nx_j, nx_c) = the located, L2-prefetched item this warp scans next
+  int nx_j = 0, nx_c = 0;
+
+  // One claim per item: an atomic add on the query's counter by lane 0.  The result stays in lane 0's register until
+  // the slow path consumes it one block later (the aggregated form waited for it at the point of issue —
+  // profiles/r02a: long-scoreboard stall 4.9 per issue).
+  auto claim_issue = [&]() {
+    if (lane == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_next) : "l"(claim) : "memory");
+    claim_pending = true;
+  };
+  // Slow path, run when bi == bi_stop (warp-uniform), i.e. after the FIRST block of an item and at its END:
+  //  A. a claim is in flight: take its result, locate that item (list j, c-th item of the list) and pull ALL of its
+  //     blocks towards L2 with three bulk prefetches (codes, ids, t(p)) — a whole item (ch_blocks blocks) of lead
+  //     time before this warp gets there.  Items of one list are scanned by different warps at the same time, so a
+  //     stream prefetch "k blocks ahead in the list" would mostly request what somebody else is already loading.
+  //  B. the current item is finished: open the located one and issue the claim for the one after it.
+  auto slow_path = [&]() {
+    if (claim_pending) {
+      claim_pending = false;
+      const int it = __shfl_sync(GB_FULL, it_next, 0);
+      nx_valid = it < n_items;
+      if (nx_valid) {
+        int j = -1;  // list that holds item `it`: last j with item_prefix[j] <= it
+#pragma unroll 1
+        for (int j0 = 0; j0 < np; j0 += 32) {
+          const int v = (j0 + lane < np) ? S.item_prefix[j0 + lane] : 0x7fffffff;
+          j += __popc(__ballot_sync(GB_FULL, v <= it));
+        }
+        nx_j = j;
+        nx_c = it - S.item_prefix[j];
+        if (pf > 0) {
+          const ProbeInfo pi = S.pinfo[j];
+          const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
+          const uint32_t b0 = (uint32_t)nx_c * (uint32_t)ch;
+          const uint32_t nb = min((uint32_t)ch, nblk - b0);
+          const size_t first = (size_t)pi.off + (size_t)b0 * 32;  // first posting of the item
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.codes + first * 32), "r"(nb * 1024u));
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.ids + first), "r"(nb * 128u));
+            if (!IP) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.norms + first), "r"(nb * 128u));
+          }
+        }
+      }
+    }
+    if (bi == bi_end) {
+      if (nx_valid) {
+        nx_valid = false;
+        const ProbeInfo pi = S.pinfo[nx_j];
+        const uint32_t offb = (uint32_t)(pi.off >> 5);  // lists start on block boundaries
+        const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
+        const uint32_t b0 = (uint32_t)nx_c * (uint32_t)ch;
+        bi = offb + b0;
+        bi_end = offb + min(b0 + (uint32_t)ch, nblk);
+        bil = offb + ((uint32_t)(pi.len - lane + 31) >> 5);
+        seqc = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)lane - (offb << 5) - 32u;
+        dis0 = pi.dis0;
+        claim_issue();
+        bi_stop = bi + 1;  // consume that claim after the first block of this item (== bi_end for one-block items)
+      }                    // else: the query has no unclaimed item left; bi == bi_end == bi_stop stays
+    } else {
+      bi_stop = bi_end;
+    }
+  };
+
+  // ---- the block in flight (per lane): 32 pre-rotated code bytes, vid, t(p)
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+  int id_n = -1;
+  float nrm_n = 0.f;
+  bool have_n = false;
+  auto issue_loads = [&]() {
+    if (bi == bi_stop) slow_path();  // warp-uniform, twice per item
+    have_n = bi != bi_end;
+    if (have_n) {
+      const unsigned char *cp = wide_at<1024>(codes_lane, bi);
+      const uint4 v0 = ldg_nc_v4(cp);
+      const uint4 v1 = ldg_nc_v4(cp + 512);
+      c0 = v0.x, c1 = v0.y, c2 = v0.z, c3 = v0.w, c4 = v1.x, c5 = v1.y, c6 = v1.z, c7 = v1.w;
+      id_n = -1;
+      nrm_n = 0.f;
+      if (bi < bil) {
+        id_n = ldg_nc_s32(wide_at<128>(ids_lane, bi));
+        if (!IP) nrm_n = ldg_nc_f32(wide_at<128>(nrm_lane, bi));
+      }
+      bi++;
+    }
+  };
+
+  u64 skey = 0;
+  bool spend = false;
+  auto try_append = [&](bool pass, u64 key) -> bool {
+    const unsigned m = __ballot_sync(GB_FULL, pass);
+    if (m == 0) return false;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
+    base = __shfl_sync(GB_FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    bool pending = pass;
+    if (pass && slot < topr.cap) {
+      topr.buf[slot] = key;
+      pending = false;
+    }
+    spend = pending;
+    skey = key;
+    return __any_sync(GB_FULL, pending);
+  };
+
+  bool stalled = false;
+  issue_loads();  // the first claim of this query was issued before the table wait (claim_pending == true)
+  int round = 0;
+  for (;;) {
+    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
+    bool over = false;
+    if (!stalled) {
+      while (have_n) {  // warp-uniform
+        // ---- table addresses (code << 8 | lane * 4) 16 at a time; the second half's addresses kill the code registers,
+        // which are then refilled with the NEXT block.  32 conflict-free lookups, accumulated as two packed pairs.
+        uint32_t a[16];
+        u64 s01, s23;
+#define GB_ADDR4(W, I)                     \
+  a[I + 0] = prmt_v(W, lane4, 0x5504);     \
+  a[I + 1] = prmt_v(W, lane4, 0x5514);     \
+  a[I + 2] = prmt_v(W, lane4, 0x5524);     \
+  a[I + 3] = prmt_v(W, lane4, 0x5534);
+#define GB_LOOK4(I, O)                                                          \
+  s01 = f2_add(s01, f2_pack(lds_raw<O + 0>(a[I + 0]), lds_raw<O + 1>(a[I + 1]))); \
+  s23 = f2_add(s23, f2_pack(lds_raw<O + 2>(a[I + 2]), lds_raw<O + 3>(a[I + 3])));
+        GB_ADDR4(c0, 0) GB_ADDR4(c1, 4) GB_ADDR4(c2, 8) GB_ADDR4(c3, 12)
+        s01 = f2_pack(lds_raw<0>(a[0]), lds_raw<1>(a[1]));
+        s23 = f2_pack(lds_raw<2>(a[2]), lds_raw<3>(a[3]));
+        GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
+        GB_ADDR4(c4, 0) GB_ADDR4(c5, 4) GB_ADDR4(c6, 8) GB_ADDR4(c7, 12)
+        // what the admission test needs of the block in flight, evaluated NOW (asm volatile pins the order) so that
+        // its registers can be reused by the next block's loads
+        float nb;
+        uint32_t seq;
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(nb) : "f"(dis0), "f"(nrm_n));
+        asm volatile("mad.lo.u32 %0, %1, 32, %2;" : "=r"(seq) : "r"(bi), "r"(seqc));
+        bool ok = id_n >= 0;
+        uint32_t vw = 0xffffffffu, vbit = 1u;
+        if (HAS_VALID) {
+          vw = ok ? __ldg(P.valid + (id_n >> 5)) : 0u;  // latency hidden by the lookups
+          asm volatile("shf.l.wrap.b32 %0, 1, 1, %1;" : "=r"(vbit) : "r"(id_n));  // 1 << (id & 31)
+        }
+        // ---- next block straight into the registers just freed
+        issue_loads();
+        GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
+#undef GB_ADDR4
+#undef GB_LOOK4
+        // ---- filter, pre-test, admission.  Every warp reads the counter once per block so that all of them notice a
+        // wanted prune within one block, whether or not they append anything themselves.  The pre-test is one float
+        // compare against the float image of tau's distance word (NaN fails it, as in the reference's heap compare).
+        const float tau_f = lds_ctl_f32<12>(ctl);
+        const int cnt_now = lds_ctl_s32<8>(ctl);
+        float s0, s1, s2, s3;
+        f2_unpack(s01, s0, s1);
+        f2_unpack(s23, s2, s3);
+        const float dis = nb + ((s0 + s1) + (s2 + s3));
+        if (HAS_VALID) ok = ok && (vw & vbit);
+        const bool pass = ok && (IP ? dis >= tau_f : dis <= tau_f);
+        if (__any_sync(GB_FULL, pass || cnt_now > soft_limit)) {  // rare
+          if (__any_sync(GB_FULL, pass)) {
+            const u64 key = ((u64)dist_to_key32<IP>(dis) << 32) | seq;
+            stalled = try_append(pass && key < topr.threshold(), key);
+          }
+          // appenders re-read the counter after their own atomicAdd: a warp starts a block only while
+          // cnt <= cap - 32 * WARPS, so the buffer cannot overflow between sync points
+          over = *((volatile int *)topr.cnt) > soft_limit;
+          if (stalled || over) break;
+        }
+      }
+    }
+    const bool more = stalled || have_n;
+    over = over || stalled;
+    const int slot = round % 3;
+    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
+    __syncthreads();
+    const int v = flags[slot];
+    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
+    round++;
+    if (v & 1) topr.prune_collective<PER>();
+    if (!(v & 2)) break;
+  }
+}
+
+// a CTA without a query looks for the running query with the most unclaimed items among the last help_window queries
+// and takes a candidate row of it.  Collective; returns false when nothing worth joining is left.
+template <int THREADS>
+__device__ __forceinline__ bool v3_pick_victim(const ScanParams &P, const V3Smem &S, int &q_out, int &row_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t pbytes = v3_probe_bytes(P.nprobe);
+  const size_t total_off = (size_t)P.nprobe * sizeof(ProbeInfo) + (size_t)P.nprobe * sizeof(int);
+  const int w0 = max(0, P.n - min(P.help_window, 65536));
+  for (;;) {
+    uint32_t best = 0;
+    for (int qq = P.n - 1 - tid; qq >= w0; qq -= THREADS) {
+      const int tot = *reinterpret_cast<const int *>(P.probe_g + (size_t)qq * pbytes + total_off);
+      const int cl = ld_volatile_s32(P.v3_claim + qq);
+      const int rw = ld_volatile_s32(P.v3_rows + qq);
+      const int rem = rw < P.S ? tot - cl : 0;
+      if (rem > 0) best = max(best, ((uint32_t)min(rem, 65535) << 16) | (uint32_t)(qq - w0));
+    }
+    best = __reduce_max_sync(GB_FULL, best);
+    if (lane == 0) S.misc[4 + warp] = (int)best;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t b = 0;
+      for (int w = 0; w < THREADS / 32; w++) b = max(b, (uint32_t)S.misc[4 + w]);
+      int q = -1, row = 0;
+      if ((int)(b >> 16) >= P.help_min) {
+        q = w0 + (int)(b & 0xffffu);
+        row = atomicAdd(P.v3_rows + q, 1);
+        if (row >= P.S) q = -2;  // lost the race for the last row: look again (the query is excluded now)
+      }
+      S.misc[72] = q;
+      S.misc[73] = row;
+    }
+    __syncthreads();
+    const int q = S.misc[72];
+    if (q == -1) return false;
+    if (q >= 0) {
+      q_out = q;
+      row_out = S.misc[73];
+      return true;
+    }
+  }
+}
+
+template <bool IP, int THREADS, int MINB, int PER>
+__global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanParams P) {
+  constexpr int WARPS = THREADS / 32;
+  const int tid = threadIdx.x;
+  const V3Smem S = v3_carve(gb_scan_smem, P.nprobe);
+  BlockTopR topr;
+  topr.buf = S.buf;
+  topr.tau = reinterpret_cast<u64 *>(S.misc);
+  topr.cnt = S.misc + 2;
+  topr.warp_part = S.misc + 4;
+  topr.cap = P.cap;
+  topr.R = P.R;
+  topr.tau_f = reinterpret_cast<float *>(S.misc + 3);
+  topr.is_ip = IP ? 1 : 0;
+  if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
+  const uint32_t pbytes = (uint32_t)v3_probe_bytes(P.nprobe);
+  if (tid == 0) {
+    mbar_init(&S.mbar[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  bool helper = false;
+  for (;;) {
+    // ---- the next (query, candidate row) of this CTA
+    int q = -1, row = 0;
+    if (!helper) {
+      if (tid == 0) {
+        int qn = atomicAdd(P.v3_next_q, 1);
+        int rw = 0;
+        if (qn < P.n) rw = atomicAdd(P.v3_rows + qn, 1);
+        else qn = -1;
+        S.misc[72] = qn;
+        S.misc[73] = rw;
+      }
+      __syncthreads();
+      q = S.misc[72];
+      row = S.misc[73];
+      __syncthreads();  // misc[72..73] are rewritten by the victim search
+      if (q < 0) helper = true;
+    }
+    if (helper && !v3_pick_victim<THREADS>(P, S, q, row)) break;
+    if (row >= P.S) continue;  // every row of this query is taken: the CTAs holding them scan all of its items
+    // ---- the query's table [256][64] (lut_build_m32_kernel, L2 resident) and its probe table land in shared memory
+    // through one mbarrier; every warp is past its last table read of the previous query (barrier below)
+    if (tid == 0) {
+      *topr.cnt = 0;
+      *topr.tau = GB_KEY_MAX;
+      *topr.tau_f = IP ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);  // everything finite is admitted
+      S.misc[68] = S.misc[69] = S.misc[70] = 0;
+      const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
+      mbar_expect_tx(&S.mbar[0], 65536u + pbytes);
+      tma_bulk_g2s(S.pinfo, P.probe_g + (size_t)q * pbytes, pbytes, &S.mbar[0]);
+#pragma unroll
+      for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
+    }
+    __syncthreads();
+    // every warp's first claim travels to L2 and back while the tables arrive
+    int it_first = 0;
+    int *const claim0 = P.v3_claim + q + (tid & 31) * P.v3_zero;  // address formed outside the branch (see scan_loop_m32_v3)
+    if ((tid & 31) == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_first) : "l"(claim0) : "memory");
+    mbar_wait(&S.mbar[0], parity);
+    parity ^= 1u;
+    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER>(P, S, topr, q, it_first);
+    else scan_loop_m32_v3<IP, false, WARPS, PER>(P, S, topr, q, it_first);
+    // ---- survivors of this CTA -> cand[q][row][0..R)
+    topr.prune_collective<PER>();
+    const int n_out = min(*((volatile int *)topr.cnt), P.R);
+    u64 *out = P.cand + ((size_t)q * P.S + row) * P.R;
+    for (int i = tid; i < P.R; i += THREADS) out[i] = i < n_out ? topr.buf[i] : GB_KEY_MAX;
+    __syncthreads();
+  }
+}
+
+// cudaFuncSetAttribute is per device and cheap: called on every launch instead of caching per process (an index may live
+// on any device)
+template <int T, int MINB, int PER>
+static cudaError_t launch_v3_shape(const ScanParams &P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (P.is_ip) {
+    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<true, T, MINB, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivfpq_scan_m32_v3_kernel<true, T, MINB, PER><<<grid, T, smem, st>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<false, T, MINB, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivfpq_scan_m32_v3_kernel<false, T, MINB, PER><<<grid, T, smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
+// shapes: 256 threads x 3 CTAs per SM (candidate buffer <= 1024 keys), 384 / 512 threads x 2 CTAs per SM; the 512-thread
+// shape also serves recall_num > 1536 with a 4096-key buffer (8 keys per thread in the select)
+int scan_v3_ctas_per_sm(int threads) { return threads >= 384 ? 2 : 3; }
+
+cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st) {
+  const size_t smem = scan_v3_smem_bytes(P.nprobe, P.cap);
+  if (P.M != 32 || P.nprobe > 2048 || P.cap > 8 * P.m32_threads || (P.cap > 4 * P.m32_threads && P.m32_threads != 512))
+    return cudaErrorInvalidValue;
+  switch (P.m32_threads) {
+    case 512: return P.cap > 2048 ? launch_v3_shape<512, 2, 8>(P, grid, smem, st) : launch_v3_shape<512, 2, 4>(P, grid, smem, st);
+    case 384: return launch_v3_shape<384, 2, 4>(P, grid, smem, st);
+    default: return launch_v3_shape<256, 3, 4>(P, grid, smem, st);
+  }
+}
+
+}  // namespace gb

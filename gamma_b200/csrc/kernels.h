@@ -25,7 +25,6 @@ struct ScanParams {
   const float *coarse_dis;  // [n][nprobe]
   const float *centroids;   // [nlist][d]
   const float *pq_t;        // [256][M][dsub] code-major PQ codebook
-  const int *order;         // optional [n] query order (heaviest first) or nullptr
   const float *lut_g;       // M = 32 kernel: [n][256][64] per-query tables from launch_lut_build_m32
   const uint8_t *codes;     // posting pool (layout above)
   const int *ids;           // [pool] vid, -1 = padding / moved (kDelIdxMask)
@@ -38,18 +37,27 @@ struct ScanParams {
   unsigned long long *timing;   // optional [8] phase cycle counters (GB200_SCAN_TIMING=1), else nullptr
   int n, d, M, dsub, nlist, nprobe, S, R, cap, chunk, max_np_s, is_ip;
   int m32_threads;          // tuning: CTA size of the M = 32 kernel (256 / 320 / 384)
-  int no_tma;               // tuning: build the table with plain LDG instead of TMA-staged chunks
-  int force_sym;            // debug: take the symbol-addressed LDS path even when the raw one is valid
-  int variant;              // M = 32: 2 = v2 kernel (precomputed probe tables, in-place prefetch), 1 = v1
+  int variant;              // M = 32: 3 = persistent kernel (ivfpq_scan_v3.cu), 2 = one CTA per (query, split)
   int pf_blocks;            // v2 loop: L2 prefetch distance in 32-posting blocks (0 = off)
   int steal;                // v2 loop, 256-thread shape: intra-CTA work stealing (opt-in, GB200_SCAN_STEAL=1)
   unsigned char *probe_g;   // v2: [items][scan_probe_bytes(max_np_s)] from launch_probe_setup
-  const int4 *items;        // v2: work plan (query, split, splits of that query, 0) from launch_plan_items, or nullptr
-  int n_items;              //     > 0: grid = n_items work items; S is then the row count of cand per query.  With items ==
-  int n_full, s_tail;       //     nullptr the plan is positional: query q < n_full is one item, the others s_tail items each
+  int n_items;              // v2: > 0: grid = n_items work items; S is then the row count of cand per query.  The plan is
+  int n_full, s_tail;       //     positional: query q < n_full is one item, the others s_tail items each
+  // v3 (persistent kernel, ivfpq_scan_v3.cu): control words, zeroed before every launch.  S = candidate rows per query.
+  int *v3_next_q;           // [1] next query without an owner CTA
+  int *v3_claim;            // [n] next unclaimed item of the query (warps of every CTA working on it claim here)
+  int *v3_rows;             // [n] candidate rows handed out for the query (>= S: no row left)
+  int ch_blocks;            // 32-posting blocks per item
+  int v3_zero;              // always 0 (keeps the claim address opaque to the compiler, see scan_loop_m32_v3)
+  int help_min;             // an idle CTA joins a running query that still has >= help_min unclaimed items ...
+  int help_window;          // ... looking at the last help_window queries
 };
-cudaError_t launch_plan_items(const int *keys, const int *list_len, int n, int nprobe, int nlist, int n_full, int s_tail,
-                              int4 *items, int *nsplit, cudaStream_t st);
+// v3 launchers (ivfpq_scan_v3.cu)
+size_t scan_v3_probe_bytes(int nprobe);
+size_t scan_v3_smem_bytes(int nprobe, int cap);
+int scan_v3_ctas_per_sm(int threads);
+cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st);
+cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st);
 size_t scan_probe_bytes_host(int max_np_s);
 cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st);
 bool scan_m32_v2_usable(const ScanParams &P);
@@ -57,8 +65,6 @@ int scan_m32_v2_ctas_per_sm(const ScanParams &P);
 size_t scan_smem_bytes(const ScanParams &P, int mode);
 int scan_buffer_cap(int R);
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);
-cudaError_t launch_query_order(const int *keys, const int *list_len, int n, int nprobe, int nlist, int *order,
-                               cudaStream_t st);
 cudaError_t launch_lut_build_m32(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,
                                  cudaStream_t st);
 cudaError_t launch_lut_build_m64(const float *xq, const float *pq_t, float *lut_g, int n, int d, int dsub, int is_ip,

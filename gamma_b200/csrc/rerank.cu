@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
   float *qs = reinterpret_cast<float *>(vids + p2_r);             // [raw_d]
   const int q = blockIdx.x, tid = threadIdx.x;
   // rows of this query in the [S][R] candidate block; sort only what is there
-  const int total = (P.nsplit ? P.nsplit[q] : (q < P.n_full ? 1 : P.S)) * P.R;
+  const int total = (P.nsplit ? min(P.nsplit[q], P.S) : (q < P.n_full ? 1 : P.S)) * P.R;
   const u64 *cand = P.cand + (size_t)q * P.S * P.R;
   p2_all = next_pow2(total);
   for (int i = tid; i < p2_all; i += RR_THREADS) keys[i] = i < total ? cand[i] : GB_KEY_MAX;

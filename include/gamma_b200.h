@@ -173,6 +173,9 @@ int gb200_set_profiling(gb200_index *ix, int enable);
 float gb200_last_scan_kernel_ms(gb200_index *ix);
 /* wait for the index's stream (after *_dev calls) and refresh the counters above.          */
 int gb200_sync(gb200_index *ix);
+/* Tuning knobs (GB200_* environment variables) are read once when an index is created; this re-reads
+ * them for an existing index (A/B runs in bench.py and the tests).                           */
+int gb200_reload_tuning(gb200_index *ix);
 
 /* ---- test hook (not used by the plugin): run the streaming top-R selection primitive the scan
  * kernels use (append + radix-select prune, one CTA of `threads`) on caller-provided 64-bit keys fed

@@ -68,6 +68,46 @@ def assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-6, max_bad_frac=0.
     return r
 
 
+def assert_rerank_parity(f, ix, xq, k, nprobe, R, metric, D, I, filters=None, keys=None, coarse_dis=None):
+    """Parity of a has_rank=True search with NO unexplained slack.  Re-ranked distances are bit-identical where ids
+    agree.  An id may differ from the reference only for one reason: the two engines nominate slightly different
+    recall sets, because their ADC sums round differently (1e-4 relative contract) and the recall set is
+    cut at its recall_num-th ADC distance.  Every differing id must therefore sit within the ADC tolerance of that
+    cut: the reference's extra id at the boundary of the REFERENCE's recall set (has_rank=False, k=recall_num), ours at
+    the boundary of OUR recall set.  Returns the fraction of identical id slots."""
+    pj = json.dumps({"nprobe": nprobe, "recall_num": R, "metric_type": metric})
+    kw = dict(filters=filters or [])
+    if keys is not None:
+        kw.update(keys=keys, coarse_dis=coarse_dis)
+    D_ref, I_ref = f.ref.search(xq, k, pj, has_rank=True, **kw)
+    same = I_ref == I
+    assert np.array_equal(D_ref[same], D[same]), "re-ranked distances must be bit-identical where ids agree"
+    diff_q = np.nonzero((~same).any(axis=1))[0]
+    if diff_q.size:
+        Ra = max(R, k)
+        Da_ref, Ia_ref = f.ref.search(xq[diff_q], Ra, pj, has_rank=False, **kw)
+        rc, Da, Ia = ix.Search(xq[diff_q], Ra, nprobe=nprobe, recall_num=R, metric=metric, has_rank=False, **kw)
+        assert rc == 0
+        for t, q in enumerate(diff_q):
+            # exact-distance (near-)ties at the k boundary or inside the list are ordering freedom, not a difference
+            if compare_topk(D_ref[q:q + 1], I_ref[q:q + 1], D[q:q + 1], I[q:q + 1], rtol=1e-6, atol=0.0)[
+                    "n_id_mismatch_unexplained"] == 0:
+                continue
+            for (ids_mine, ids_other, Dset, Iset, who) in ((I_ref[q], I[q], Da_ref[t], Ia_ref[t], "reference"),
+                                                           (I[q], I_ref[q], Da[t], Ia[t], "ours")):
+                filled = Iset >= 0
+                assert filled.all(), "a recall set that is not full has no boundary: ids must be identical (q=%d)" % q
+                cut = float(Dset[filled][-1])
+                for v in set(ids_mine[ids_mine >= 0].tolist()) - set(ids_other.tolist()):
+                    pos = np.nonzero(Iset == v)[0]
+                    assert pos.size == 1, "id %d of %s result is not in its own recall set (q=%d)" % (v, who, q)
+                    tol = 1e-4 * max(abs(cut), abs(float(Dset[pos[0]]))) + 1e-6
+                    assert abs(float(Dset[pos[0]]) - cut) <= tol, (
+                        "q=%d id=%d differs but is not at the recall-set boundary of %s (adc %.7g, cut %.7g)" % (
+                            q, v, who, float(Dset[pos[0]]), cut))
+    return float(same.mean())
+
+
 # ----------------------------------------------------------------------------------------------
 # small reference-built indexes shared by the GPU parity tests
 # ----------------------------------------------------------------------------------------------

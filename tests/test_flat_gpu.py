@@ -76,7 +76,8 @@ def test_flat_empty_store_and_k_gt_n():
     assert np.array_equal(I[0], [0, 1, 2, -1, -1]) and np.all(D[0, :3] == 1.0)
 
 
-@pytest.mark.parametrize("metric,d,N,nq", [("InnerProduct", 64, 150000, 64), ("L2", 96, 70000, 40)])
+@pytest.mark.parametrize("metric,d,N,nq", [("InnerProduct", 64, 150000, 64), ("L2", 96, 70000, 40),
+                                           ("InnerProduct", 768, 30000, 48)])  # d = 768: BASELINE config 4 (24 k-blocks)
 def test_flat_batch_tensor_core_path_is_exact(metric, d, N, nq, monkeypatch):
     """Batches (n >= 16) take the tcgen05 GEMM -> candidate select -> exact re-score route; the result
     must still be bit-identical to the CPU engine (ids and distances), including across database chunks."""
@@ -94,6 +95,7 @@ def test_flat_batch_tensor_core_path_is_exact(metric, d, N, nq, monkeypatch):
     for env in ({"GB200_FLAT_CHUNK_ROWS": "4096"}, {"GB200_FLAT_CHUNK_ROWS": "8192", "GB200_FLAT_SELECT_V1": "1"}):
         for kk, vv in env.items():
             monkeypatch.setenv(kk, vv)
+        ix.reload_tuning()
         rc, D3, I3 = ix.Search(xq, 10, metric=metric)
         assert rc == 0 and np.array_equal(I_ref, I3) and np.array_equal(D_ref, D3), env
         rc, D4, I4 = ix.Search(xq, 10, metric=metric, filters=filt)
@@ -102,5 +104,6 @@ def test_flat_batch_tensor_core_path_is_exact(metric, d, N, nq, monkeypatch):
             monkeypatch.delenv(kk)
     # the per-query exact scan (GB200_FLAT=exact) gives the same answer
     monkeypatch.setenv("GB200_FLAT", "exact")
+    ix.reload_tuning()
     rc, D2, I2 = ix.Search(xq, 10, metric=metric)
     assert np.array_equal(I, I2) and np.array_equal(D, D2)
