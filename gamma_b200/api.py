@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.gb200_last_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.gb200_reload_tuning.argtypes = [C.c_void_p]
+        L.gb200_ivfpq_compact.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
@@ -264,6 +265,12 @@ class B200IVFPQ(_Base):
     def update(self, vid, new_list, code):
         c = np.ascontiguousarray(code, dtype=np.uint8)
         return lib().gb200_ivfpq_update(self.h, int(vid), int(new_list), c.ctypes.data)
+
+    def compact(self, list_no=-1):
+        """RealTimeMemData::CompactBucket on the device; returns the number of postings dropped."""
+        dropped = C.c_int64(0)
+        _check(lib().gb200_ivfpq_compact(self.h, int(list_no), C.byref(dropped)), "compact")
+        return int(dropped.value)
 
     def list_sizes(self):
         out = np.empty(self.nlist, np.int64)

@@ -1,7 +1,18 @@
 // extern "C" shim of include/gamma_b200.h: owns the device mirror of one RetrievalModel
-// (quantizers, realtime posting pools, raw vectors, deleted bitmap) and sequences the
-// kernels of a Search call on one CUDA stream.  No CPU fallback exists anywhere in here:
-// every data-path step is a kernel launch; the host only moves bytes and keeps list extents.
+// (quantizers, realtime posting pools, raw vectors, live-docs bitmap) and sequences the
+// kernels of a Search call.  No CPU fallback exists anywhere in here: every data-path step
+// is a kernel launch; the host only moves bytes and keeps list extents.
+//
+// Threading (reference: Search is called concurrently from many request threads while one thread
+// Adds / Updates and others Delete — SURVEY §8b, tests/test.h:1033-1062, search/gamma_engine.cc:74-97):
+//   * every Search call takes a SearchCtx (own stream, side stream, events, all workspaces) from a
+//     small pool, so concurrent callers overlap on the device instead of queueing behind one mutex;
+//   * searches hold data_mu SHARED.  Writers (append / update / raw upload / delete) are serialised
+//     among themselves by writer_mu and also hold data_mu shared: they write behind the published
+//     list lengths on their own stream and publish extents with release semantics
+//     (postings.cu publish_lists_kernel), so a search never waits for a writer;
+//   * only operations that free or replace device arrays (pool / raw store / bitmap growth, set_quantizers,
+//     full compaction, destroy) take data_mu EXCLUSIVE, after draining the device.
 #include <cuda_runtime.h>
 #include <float.h>
 #include <math.h>
@@ -10,7 +21,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -49,7 +64,7 @@ struct DevBuf {  // grow-only device scratch
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return GB200_OK;
-    if (p) cudaFree(p);
+    if (p) cudaFree(p);  // synchronises with the device: nothing can still be reading the old buffer
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
@@ -72,14 +87,12 @@ struct DevBuf {  // grow-only device scratch
 
 inline long long roundup32(long long v) { return (v + 31) & ~31LL; }
 
-}  // namespace
-
 // Tuning knobs: environment variables read ONCE at index creation (gb200_reload_tuning re-reads them, for A/B runs);
 // defaults are the measured best.
 struct Tuning {
   int scan_variant = 3;   // GB200_SCAN_VARIANT: M = 32 scan: 3 = persistent kernel with dynamic items (default), 2 = one CTA per (query, split)
-  int scan_threads = 256; // GB200_SCAN_THREADS: 256 (3 CTAs / SM), 384 or 512 (2 CTAs / SM)
-  int pf_blocks = 4;      // GB200_SCAN_PF: L2 prefetch distance in 32-posting blocks
+  int scan_threads = 0;   // GB200_SCAN_THREADS: v3: 384 (default) / 320 / 256 (2 CTAs / SM, ring 2 / 3 / 4), 512; v2: 256 (default) / 384 / 512
+  int pf_blocks = 4;      // GB200_SCAN_PF: v2 / M = 64: L2 prefetch distance in 32-posting blocks
   int ch_blocks = 8;      // GB200_SCAN_CH: blocks per item (v3)
   int help_min = 8;       // GB200_SCAN_HELP_MIN: idle CTAs join a query that has >= this many unclaimed items (v3)
   int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
@@ -91,13 +104,14 @@ struct Tuning {
   int coarse_simt = 0;    // GB200_COARSE=simt: CUDA-core fp32 coarse distances instead of the tcgen05 GEMM
   int lut_inline = 0;     // GB200_LUT_INLINE: build the tables on the main stream
   int flat_mode = 0;      // GB200_FLAT: 0 automatic, 1 = exact (per-query scan), 2 = tc (tensor-core path for any batch)
+  int max_contexts = 8;   // GB200_MAX_CONTEXTS: Search calls in flight per index (each owns streams + workspaces)
   long long flat_chunk_rows = 0;  // GB200_FLAT_CHUNK_ROWS: database rows per tensor-core chunk (tests: force many chunks)
   void read() {
     *this = Tuning();
     auto geti = [](const char *k, int d) { const char *e = getenv(k); return e && *e ? atoi(e) : d; };
     scan_variant = geti("GB200_SCAN_VARIANT", scan_variant);
     scan_threads = geti("GB200_SCAN_THREADS", scan_threads);
-    if (scan_threads != 256 && scan_threads != 384 && scan_threads != 512) scan_threads = 256;
+    if (scan_threads != 256 && scan_threads != 320 && scan_threads != 384 && scan_threads != 512) scan_threads = 0;
     pf_blocks = std::max(0, geti("GB200_SCAN_PF", pf_blocks));
     ch_blocks = std::max(1, geti("GB200_SCAN_CH", ch_blocks));
     help_min = std::max(1, geti("GB200_SCAN_HELP_MIN", help_min));
@@ -108,29 +122,86 @@ struct Tuning {
     steal = geti("GB200_SCAN_STEAL", 0);
     scan_timing = geti("GB200_SCAN_TIMING", 0);
     lut_inline = geti("GB200_LUT_INLINE", 0);
+    max_contexts = std::max(1, std::min(64, geti("GB200_MAX_CONTEXTS", max_contexts)));
     if (const char *e = getenv("GB200_COARSE")) coarse_simt = !strcmp(e, "simt");
     if (const char *e = getenv("GB200_FLAT")) flat_mode = !strcmp(e, "exact") ? 1 : !strcmp(e, "tc") ? 2 : 0;
     if (const char *e = getenv("GB200_FLAT_CHUNK_ROWS")) flat_chunk_rows = atoll(e);
   }
 };
 
+// Everything one in-flight Search call owns.  All uses of its buffers are ordered on `stream` (the side stream joins
+// through events), so a context can be handed to the next call while its last kernels still run.
+struct SearchCtx {
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: per-query lookup tables are built while the coarse quantiser runs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_user = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4, 5 bracket the scan kernel alone
+  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_flat, ws_lut, ws_xs, ws_fstate, ws_probe,
+      ws_ctl;
+  DevBuf valid_filt, filt_bytes, filt_desc;  // per-call range filters -> validity bitmap
+  unsigned long long *d_scanned = nullptr;
+  unsigned long long *d_timing = nullptr;
+  int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
+  long long launches = 0;
+  bool timed = false;  // the events of the last call were recorded
+
+  int init() {
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_user, cudaEventDisableTiming));
+    for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
+    CK(cudaMalloc(&d_scanned, sizeof(unsigned long long)));
+    CK(cudaMemset(d_scanned, 0, sizeof(unsigned long long)));
+    return GB200_OK;
+  }
+  void destroy() {
+    if (stream) cudaStreamSynchronize(stream);
+    DevBuf *bufs[] = {&ws_xq,  &ws_xn, &ws_dist,   &ws_keys,  &ws_cdis, &ws_cand,    &ws_out_d,   &ws_out_i, &ws_flat,
+                      &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc};
+    for (DevBuf *b : bufs) b->release();
+    if (d_scanned) cudaFree(d_scanned);
+    if (d_timing) cudaFree(d_timing);
+    for (int i = 0; i < 6; i++)
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_user) cudaEventDestroy(ev_user);
+    if (stream2) cudaStreamDestroy(stream2);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+}  // namespace
+
 struct gb200_index {
   int kind = 0;  // 0 = IVFPQ, 1 = FLAT
   Tuning tune;
   gb200_ivfpq_params p{};
   int dsub = 0, chunk = 0, layout = 0, mode = 0;
-  int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the v2 scan's LDS immediates assume 1024)
+  int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the M = 32 / 64 kernels' LDS immediates assume 1024)
   int num_sms = 0;        // cudaDeviceProp::multiProcessorCount (grid sizing of the persistent scan, work plans)
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // side stream: per-query lookup tables are built while the coarse quantiser runs
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
-  std::mutex mu;
-  bool trained = false;
 
+  // ---- locking (see the header comment)
+  std::shared_mutex data_mu;
+  std::mutex writer_mu;
+  std::mutex ctx_mu;
+  std::condition_variable ctx_cv;
+  std::vector<SearchCtx *> ctx_all, ctx_free;
+  SearchCtx *last_ctx = nullptr;  // most recently used context (gb200_sync / profiling read-out)
+  std::mutex stats_mu;
+
+  // ---- writer side: own stream + staging
+  cudaStream_t wstream = nullptr;
+  DevBuf w_stage, w_pub;
+  long long *d_woff = nullptr;  // the writer's view of the list offsets (regions being filled before they are published)
+
+  std::atomic<bool> trained{false};
   float *d_cent = nullptr, *d_cent_norm = nullptr, *d_pq = nullptr, *d_pq_t = nullptr;
   float *d_cent_small = nullptr;  // centroid - tf32(centroid): second operand of the 3xTF32 tensor-core GEMM
 
+  // posting pools: bump allocation, lists grow by allocate-copy-swap at the tail (host tables are writer-only)
   long long pool_cap = 0, pool_used = 0, pool_live_cap = 0;
   uint8_t *d_codes = nullptr;
   int *d_ids = nullptr;
@@ -140,38 +211,95 @@ struct gb200_index {
   long long *d_off = nullptr;
   int *d_len = nullptr;
   std::vector<long long> vid_loc;
-  long long max_vid = -1;
+  std::atomic<long long> max_vid{-1};
 
   float *d_raw = nullptr;
-  long long raw_cap = 0, raw_n = 0;
+  long long raw_cap = 0;
+  std::atomic<long long> raw_n{0};
   // lazily built companions of the raw store for the tensor-core flat path: x - tf32(x) and |x|^2
   float *d_raw_small = nullptr, *d_raw_norm = nullptr;
-  long long aux_cap = 0, aux_n = 0;
+  long long aux_cap = 0;
+  std::atomic<long long> aux_n{0};
+  std::mutex aux_mu;
 
+  // live-docs bitmap: bit = 1 <=> NOT deleted (the complement of bitmap::BitmapManager's bits); words beyond the
+  // highest doc ever touched are all ones.  h_deleted is the writer's shadow of the reference bitmap.  While any doc is
+  // deleted the bitmap covers at least doc_bits() docs (writers grow it BEFORE they publish new docs).
   std::vector<uint32_t> h_deleted;
-  uint32_t *d_deleted = nullptr;
-  long long deleted_words_dev = 0;
-  bool any_deleted = false;
-  bool nodel_valid_dirty = true;       // cached "~deleted" bitmap needs rebuilding
-  DevBuf valid_nodel, valid_filt, filt_bytes, filt_desc;
-  bool dev_filter_active = false;      // installed by gb200_set_filters for *_dev calls
+  uint32_t *d_live = nullptr;
+  long long live_words = 0;  // capacity of d_live in words
+  std::atomic<long long> deleted_count{0};
+  // range filters installed for the *_dev calls (gb200_set_filters): host copy + the bitmap built from it
+  struct Installed {
+    bool active = false;
+    std::vector<gb200_range_filter> desc;
+    std::vector<std::vector<uint8_t>> bytes;
+    DevBuf valid, filt_bytes, filt_desc;
+    long long bits = 0;
+  } inst;
 
-  DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_stage, ws_flat, ws_lut, ws_order, ws_xs, ws_fstate, ws_probe, ws_items, ws_nsplit, ws_ctl;
-  unsigned long long *d_scanned = nullptr;
-  unsigned long long *d_timing = nullptr;
-  long long last_scanned = 0, launches = 0;
+  // last-call statistics
   bool profiling = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4, 5 bracket the scan kernel alone
+  long long last_scanned = 0;
+  std::atomic<long long> launches{0};
   float stage_ms[4] = {0, 0, 0, 0};
   float scan_kernel_ms = 0;
 
-  long long doc_bits() const { return std::max(max_vid + 1, raw_n); }
+  long long doc_bits() const { return std::max(max_vid.load() + 1, raw_n.load()); }
 };
 
 static int use_device(gb200_index *ix) {
   CK(cudaSetDevice(ix->p.device));
   return GB200_OK;
 }
+
+// ---- search contexts ------------------------------------------------------------------------------------
+static SearchCtx *acquire_ctx(gb200_index *ix) {
+  std::unique_lock<std::mutex> g(ix->ctx_mu);
+  for (;;) {
+    if (!ix->ctx_free.empty()) {
+      SearchCtx *c = ix->ctx_free.back();
+      ix->ctx_free.pop_back();
+      return c;
+    }
+    if ((int)ix->ctx_all.size() < ix->tune.max_contexts) {
+      SearchCtx *c = new SearchCtx;
+      if (c->init() != GB200_OK) {
+        c->destroy();
+        delete c;
+        return nullptr;
+      }
+      ix->ctx_all.push_back(c);
+      return c;
+    }
+    ix->ctx_cv.wait(g);
+  }
+}
+static void release_ctx(gb200_index *ix, SearchCtx *c) {
+  {
+    std::lock_guard<std::mutex> g(ix->ctx_mu);
+    ix->ctx_free.push_back(c);
+    ix->last_ctx = c;
+  }
+  ix->ctx_cv.notify_one();
+}
+namespace {
+struct SearchScope {  // shared hold on the index data + one context, for the duration of a Search entry point
+  gb200_index *ix;
+  std::shared_lock<std::shared_mutex> lk;
+  SearchCtx *c;
+  explicit SearchScope(gb200_index *ix_) : ix(ix_), lk(ix_->data_mu), c(acquire_ctx(ix_)) {}
+  ~SearchScope() {
+    if (c) release_ctx(ix, c);
+  }
+};
+// exclusive hold: every search has left its entry point; kernels they enqueued (the *_dev calls return before their
+// work is done) are drained before anything is freed or replaced
+struct ExclusiveScope {
+  std::unique_lock<std::shared_mutex> lk;
+  explicit ExclusiveScope(gb200_index *ix) : lk(ix->data_mu) { cudaDeviceSynchronize(); }
+};
+}  // namespace
 
 extern "C" {
 
@@ -199,16 +327,28 @@ static int common_create(gb200_index *ix) {
     return GB200_EUNSUPPORTED;
   }
   ix->smem_reserved = (int)prop.reservedSharedMemPerBlock;
-  ix->tune.read();
   ix->num_sms = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
-  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ix->ev[i]));
-  CK(cudaMalloc(&ix->d_scanned, sizeof(unsigned long long)));
-  CK(cudaMemset(ix->d_scanned, 0, sizeof(unsigned long long)));
+  ix->tune.read();
+  CK(cudaStreamCreateWithFlags(&ix->wstream, cudaStreamNonBlocking));
   return GB200_OK;
+}
+
+static void free_index(gb200_index *ix) {
+  cudaSetDevice(ix->p.device);
+  cudaDeviceSynchronize();
+  for (SearchCtx *c : ix->ctx_all) {
+    c->destroy();
+    delete c;
+  }
+  void *ptrs[] = {ix->d_raw_small, ix->d_raw_norm, ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq,   ix->d_pq_t, ix->d_codes,
+                  ix->d_ids,       ix->d_norms,    ix->d_off,        ix->d_len,  ix->d_woff,      ix->d_raw,  ix->d_live};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  DevBuf *bufs[] = {&ix->w_stage, &ix->w_pub, &ix->inst.valid, &ix->inst.filt_bytes, &ix->inst.filt_desc};
+  for (DevBuf *b : bufs) b->release();
+  if (ix->wstream) cudaStreamDestroy(ix->wstream);
+  cudaGetLastError();
+  delete ix;
 }
 
 int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
@@ -233,7 +373,7 @@ int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
   ix->chunk = (M % 16 == 0) ? 16 : (M % 8 == 0 ? 8 : 4);
   int rc = common_create(ix);
   if (rc != GB200_OK) {
-    delete ix;
+    free_index(ix);
     return rc;
   }
   // posting layout / scan kernel, fixed at creation: M = 32 and M = 64 have conflict-free kernels over a pre-rotated
@@ -249,12 +389,14 @@ int gb200_ivfpq_create(const gb200_ivfpq_params *p, gb200_index **out) {
   ix->h_len.assign(p->nlist, 0);
   ix->h_cap.assign(p->nlist, 0);
   if (cudaMalloc(&ix->d_off, sizeof(long long) * p->nlist) != cudaSuccess ||
+      cudaMalloc(&ix->d_woff, sizeof(long long) * p->nlist) != cudaSuccess ||
       cudaMalloc(&ix->d_len, sizeof(int) * p->nlist) != cudaSuccess) {
     set_err("alloc list tables");
-    delete ix;
+    free_index(ix);
     return GB200_ENOMEM;
   }
   cudaMemset(ix->d_off, 0, sizeof(long long) * p->nlist);
+  cudaMemset(ix->d_woff, 0, sizeof(long long) * p->nlist);
   cudaMemset(ix->d_len, 0, sizeof(int) * p->nlist);
   *out = ix;
   return GB200_OK;
@@ -271,7 +413,7 @@ int gb200_flat_create(int device, int raw_d, int metric, gb200_index **out) {
   ix->p.store_raw = 1;
   int rc = common_create(ix);
   if (rc != GB200_OK) {
-    delete ix;
+    free_index(ix);
     return rc;
   }
   *out = ix;
@@ -280,30 +422,22 @@ int gb200_flat_create(int device, int raw_d, int metric, gb200_index **out) {
 
 int gb200_destroy(gb200_index *ix) {
   if (!ix) return GB200_OK;
-  cudaSetDevice(ix->p.device);
-  if (ix->stream) cudaStreamSynchronize(ix->stream);
-  void *ptrs[] = {ix->d_raw_small, ix->d_raw_norm, ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq, ix->d_pq_t, ix->d_codes, ix->d_ids, ix->d_norms,
-                  ix->d_off,  ix->d_len,       ix->d_raw, ix->d_deleted, ix->d_scanned};
-  for (void *p : ptrs)
-    if (p) cudaFree(p);
-  DevBuf *bufs[] = {&ix->valid_nodel, &ix->valid_filt, &ix->filt_bytes, &ix->filt_desc, &ix->ws_xq, &ix->ws_xn,
-                    &ix->ws_dist,     &ix->ws_keys,    &ix->ws_cdis,    &ix->ws_cand,   &ix->ws_out_d, &ix->ws_out_i,
-                    &ix->ws_stage,    &ix->ws_flat,   &ix->ws_lut,   &ix->ws_order,  &ix->ws_xs,    &ix->ws_fstate, &ix->ws_probe, &ix->ws_items, &ix->ws_nsplit, &ix->ws_ctl};
-  for (DevBuf *b : bufs) b->release();
-  for (int i = 0; i < 6; i++)
-    if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
-  if (ix->stream2) cudaStreamDestroy(ix->stream2);
-  if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
-  if (ix->ev_join) cudaEventDestroy(ix->ev_join);
-  if (ix->stream) cudaStreamDestroy(ix->stream);
-  delete ix;
+  {
+    // searches and writers that are inside the library drain first; a caller that enters after this point is using a
+    // destroyed handle (its bug, as with any destructor)
+    std::lock_guard<std::mutex> w(ix->writer_mu);
+    cudaSetDevice(ix->p.device);
+    ExclusiveScope x(ix);
+  }
+  free_index(ix);
   return GB200_OK;
 }
 
 int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse, const float *pq) {
   if (!ix || ix->kind != 0 || !coarse || !pq) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
+  ExclusiveScope x(ix);
   const int d = ix->p.d, nlist = ix->p.nlist, M = ix->p.nsubvector, dsub = ix->dsub;
   size_t cb = (size_t)nlist * d * sizeof(float), pb = (size_t)M * 256 * dsub * sizeof(float);
   if (!ix->d_cent) {
@@ -312,26 +446,53 @@ int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse, const float
     CK(cudaMalloc(&ix->d_pq, pb));
     CK(cudaMalloc(&ix->d_pq_t, pb));
   }
-  CK(cudaMemcpyAsync(ix->d_cent, coarse, cb, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaMemcpyAsync(ix->d_pq, pq, pb, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(ix->d_cent, coarse, cb, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(ix->d_pq, pq, pb, cudaMemcpyHostToDevice, ix->wstream));
   // code-major copy [256][M][dsub] for the table build
   std::vector<float> t((size_t)M * 256 * dsub);
   for (int m = 0; m < M; m++)
     for (int c = 0; c < 256; c++)
       memcpy(&t[((size_t)c * M + m) * dsub], &pq[((size_t)m * 256 + c) * dsub], dsub * sizeof(float));
-  CK(cudaMemcpyAsync(ix->d_pq_t, t.data(), pb, cudaMemcpyHostToDevice, ix->stream));
-  CK(launch_row_norms(ix->d_cent, nlist, d, ix->d_cent_norm, ix->stream));
+  CK(cudaMemcpyAsync(ix->d_pq_t, t.data(), pb, cudaMemcpyHostToDevice, ix->wstream));
+  CK(launch_row_norms(ix->d_cent, nlist, d, ix->d_cent_norm, ix->wstream));
   if (!ix->d_cent_small) CK(cudaMalloc(&ix->d_cent_small, cb));
-  CK(launch_tf32_residual(ix->d_cent, ix->d_cent_small, (size_t)nlist * d, ix->stream));
-  ix->launches++;
-  ix->launches++;
-  CK(cudaStreamSynchronize(ix->stream));
+  CK(launch_tf32_residual(ix->d_cent, ix->d_cent_small, (size_t)nlist * d, ix->wstream));
+  ix->launches += 2;
+  CK(cudaStreamSynchronize(ix->wstream));
   ix->trained = true;
   return GB200_OK;
 }
 
+// ---- live-docs bitmap: capacity ------------------------------------------------------------
+// make d_live hold at least `words` words (new words = all ones).  May replace the array: the caller holds writer_mu and
+// NO hold on data_mu.
+static int live_reserve(gb200_index *ix, long long words) {
+  if (words <= ix->live_words) return GB200_OK;
+  ExclusiveScope x(ix);
+  long long cap = words + words / 2 + 1024;
+  uint32_t *nl = nullptr;
+  CK(cudaMalloc(&nl, (size_t)cap * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(nl, 0xff, (size_t)cap * sizeof(uint32_t), ix->wstream));
+  if (ix->live_words > 0)
+    CK(cudaMemcpyAsync(nl, ix->d_live, (size_t)ix->live_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ix->wstream));
+  CK(cudaStreamSynchronize(ix->wstream));
+  if (ix->d_live) cudaFree(ix->d_live);
+  ix->d_live = nl;
+  ix->live_words = cap;
+  return GB200_OK;
+}
+static int rebuild_installed_filter(gb200_index *ix);  // below
+// A writer is about to publish docs up to new_doc_bits: the bitmaps a search may index with those ids must cover them
+// first.  Caller holds writer_mu and no hold on data_mu.
+static int bitmaps_follow_growth(gb200_index *ix, long long new_doc_bits) {
+  if (ix->d_live) CKI(live_reserve(ix, (new_doc_bits + 31) / 32));
+  if (ix->inst.active && new_doc_bits > ix->inst.bits) CKI(rebuild_installed_filter(ix));
+  return GB200_OK;
+}
+
 // ---- posting pools ---------------------------------------------------------------------
-static int pool_reserve(gb200_index *ix, long long need_total) {
+// grow the pools to hold need_total postings.  Replaces the arrays: the caller holds data_mu exclusively.
+static int pool_reserve_exclusive(gb200_index *ix, long long need_total) {
   if (need_total <= ix->pool_cap) return GB200_OK;
   long long ncap = std::max(need_total, ix->pool_cap * 2);
   ncap = roundup32(ncap);
@@ -339,15 +500,21 @@ static int pool_reserve(gb200_index *ix, long long need_total) {
   uint8_t *nc = nullptr;
   int *ni = nullptr;
   float *nn = nullptr;
-  CK(cudaMalloc(&nc, (size_t)ncap * M));
-  CK(cudaMalloc(&ni, (size_t)ncap * sizeof(int)));
-  CK(cudaMalloc(&nn, (size_t)ncap * sizeof(float)));
-  if (ix->pool_used > 0) {
-    CK(cudaMemcpyAsync(nc, ix->d_codes, (size_t)ix->pool_used * M, cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaMemcpyAsync(ni, ix->d_ids, (size_t)ix->pool_used * sizeof(int), cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaMemcpyAsync(nn, ix->d_norms, (size_t)ix->pool_used * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+  if (cudaMalloc(&nc, (size_t)ncap * M) != cudaSuccess || cudaMalloc(&ni, (size_t)ncap * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&nn, (size_t)ncap * sizeof(float)) != cudaSuccess) {
+    if (nc) cudaFree(nc);
+    if (ni) cudaFree(ni);
+    if (nn) cudaFree(nn);
+    cudaGetLastError();
+    set_err("posting pool: cannot allocate %lld postings", ncap);
+    return GB200_ENOMEM;
   }
-  CK(cudaStreamSynchronize(ix->stream));
+  if (ix->pool_used > 0) {
+    CK(cudaMemcpyAsync(nc, ix->d_codes, (size_t)ix->pool_used * M, cudaMemcpyDeviceToDevice, ix->wstream));
+    CK(cudaMemcpyAsync(ni, ix->d_ids, (size_t)ix->pool_used * sizeof(int), cudaMemcpyDeviceToDevice, ix->wstream));
+    CK(cudaMemcpyAsync(nn, ix->d_norms, (size_t)ix->pool_used * sizeof(float), cudaMemcpyDeviceToDevice, ix->wstream));
+  }
+  CK(cudaStreamSynchronize(ix->wstream));
   if (ix->d_codes) cudaFree(ix->d_codes);
   if (ix->d_ids) cudaFree(ix->d_ids);
   if (ix->d_norms) cudaFree(ix->d_norms);
@@ -358,26 +525,21 @@ static int pool_reserve(gb200_index *ix, long long need_total) {
   return GB200_OK;
 }
 
-static int sync_list_tables(gb200_index *ix) {
-  CK(cudaMemcpyAsync(ix->d_off, ix->h_off.data(), sizeof(long long) * ix->p.nlist, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * ix->p.nlist, cudaMemcpyHostToDevice, ix->stream));
-  return GB200_OK;
-}
-
-// place n postings (already assigned list/pos) on the device; pos may address existing slots (update in place)
+// place n postings (already assigned list/pos) on the device; pos may address existing slots (update in place).
+// Regions are resolved through the writer's own offsets table (lists being moved are not published yet).
 static int write_postings(gb200_index *ix, long long n, const int *list_no, const int *pos, const int *vid32,
                           const uint8_t *codes) {
   const int M = ix->p.nsubvector;
   size_t b_int = (size_t)n * sizeof(int);
   size_t total = 3 * b_int + (size_t)n * M;
-  CKI(ix->ws_stage.ensure(total));
-  char *base = ix->ws_stage.as<char>();
+  CKI(ix->w_stage.ensure(total));
+  char *base = ix->w_stage.as<char>();
   int *d_list = (int *)base, *d_pos = (int *)(base + b_int), *d_vid = (int *)(base + 2 * b_int);
   uint8_t *d_aos = (uint8_t *)(base + 3 * b_int);
-  CK(cudaMemcpyAsync(d_list, list_no, b_int, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaMemcpyAsync(d_pos, pos, b_int, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaMemcpyAsync(d_vid, vid32, b_int, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaMemcpyAsync(d_aos, codes, (size_t)n * M, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemcpyAsync(d_list, list_no, b_int, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(d_pos, pos, b_int, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(d_vid, vid32, b_int, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(d_aos, codes, (size_t)n * M, cudaMemcpyHostToDevice, ix->wstream));
   AppendParams A;
   A.list_no = d_list;
   A.pos = d_pos;
@@ -385,7 +547,7 @@ static int write_postings(gb200_index *ix, long long n, const int *list_no, cons
   A.codes_aos = d_aos;
   A.centroids = ix->d_cent;
   A.pq = ix->d_pq;
-  A.list_off = ix->d_off;
+  A.list_off = ix->d_woff;
   A.codes = ix->d_codes;
   A.ids = ix->d_ids;
   A.norms = ix->d_norms;
@@ -395,28 +557,55 @@ static int write_postings(gb200_index *ix, long long n, const int *list_no, cons
   A.dsub = ix->dsub;
   A.chunk = ix->chunk;
   A.layout = ix->layout;
-  CK(launch_append(A, ix->stream));
+  CK(launch_append(A, ix->wstream));
   ix->launches++;
   return GB200_OK;
 }
 
+// publish the extents of `lists` (host tables already updated): off first, len with release semantics; the writer's own
+// offsets table follows
+static int publish_lists(gb200_index *ix, const std::vector<int> &lists) {
+  const int n = (int)lists.size();
+  if (n == 0) return GB200_OK;
+  std::vector<long long> offs(n);
+  std::vector<int> lens(n);
+  for (int i = 0; i < n; i++) offs[i] = ix->h_off[lists[i]], lens[i] = ix->h_len[lists[i]];
+  const size_t bytes = (size_t)n * (sizeof(long long) + 2 * sizeof(int));
+  CKI(ix->w_pub.ensure(bytes));
+  long long *d_o = ix->w_pub.as<long long>();
+  int *d_l = reinterpret_cast<int *>(d_o + n), *d_n = d_l + n;
+  CK(cudaMemcpyAsync(d_o, offs.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(d_l, lists.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(d_n, lens.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ix->wstream));
+  CK(launch_publish_lists(d_l, d_o, d_n, n, ix->d_off, ix->d_len, ix->wstream));
+  ix->launches++;
+  CK(cudaStreamSynchronize(ix->wstream));  // the host vectors go out of scope
+  return GB200_OK;
+}
+
+// caller holds writer_mu and NO hold on data_mu
 static int append_locked(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids,
                          const uint8_t *codes) {
   const int nlist = ix->p.nlist, M = ix->p.nsubvector;
   std::vector<int> inc(nlist, 0);
+  long long mv = ix->max_vid.load();
   for (int64_t i = 0; i < n; i++) {
     if (list_no[i] < 0 || list_no[i] >= nlist || vids[i] < 0 || vids[i] > 0x7ffffffeLL) {
       set_err("append: posting %lld has list %d / vid %lld out of range", (long long)i, list_no[i], (long long)vids[i]);
       return GB200_EINVAL;
     }
     inc[list_no[i]]++;
+    if (vids[i] > mv) mv = vids[i];
   }
-  // grow the lists that overflow: new contiguous regions at the pool tail
-  struct Grow { int list; long long old_off; int old_cap; };
+  // growth plan into temporaries: lists that overflow get new contiguous regions at the pool tail.  Nothing of the
+  // index is touched until the pool is known to be large enough.
+  struct Grow { int list; long long old_off, new_off; int new_cap; };
   std::vector<Grow> grows;
+  std::vector<int> touched;
   long long tail = ix->pool_used;
   for (int l = 0; l < nlist; l++) {
     if (!inc[l]) continue;
+    touched.push_back(l);
     long long need = (long long)ix->h_len[l] + inc[l];
     if (need > (1LL << GB_SEQ_POS_BITS)) {
       set_err("list %d would hold %lld postings (> 2^21, bucket_max_size)", l, need);
@@ -424,38 +613,48 @@ static int append_locked(gb200_index *ix, int64_t n, const int32_t *list_no, con
     }
     if (need > ix->h_cap[l]) {
       long long ncap = roundup32(std::max(need, (long long)ix->h_cap[l] + ix->h_cap[l] / 2));
-      grows.push_back({l, ix->h_off[l], ix->h_cap[l]});
-      ix->pool_live_cap += ncap - ix->h_cap[l];
-      ix->h_off[l] = tail;
-      ix->h_cap[l] = (int)ncap;
+      grows.push_back({l, ix->h_off[l], tail, (int)ncap});
       tail += ncap;
     }
   }
+  if (tail > ix->pool_cap) {  // the arrays are replaced: drain the searches for the swap
+    ExclusiveScope x(ix);
+    CKI(pool_reserve_exclusive(ix, tail));
+  }
+  CKI(bitmaps_follow_growth(ix, std::max(mv + 1, ix->doc_bits())));
+  std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+  // commit the plan
   if (tail > ix->pool_used) {
-    CKI(pool_reserve(ix, tail));
-    CK(launch_fill_i32(ix->d_ids + ix->pool_used, tail - ix->pool_used, -1, ix->stream));
+    CK(launch_fill_i32(ix->d_ids + ix->pool_used, tail - ix->pool_used, -1, ix->wstream));
     ix->launches++;
     for (const Grow &g : grows) {
       int len = ix->h_len[g.list];
+      ix->pool_live_cap += g.new_cap - ix->h_cap[g.list];
+      ix->h_off[g.list] = g.new_off;
+      ix->h_cap[g.list] = g.new_cap;
       if (len == 0) continue;
-      long long noff = ix->h_off[g.list];
-      CK(cudaMemcpyAsync(ix->d_codes + (size_t)noff * M, ix->d_codes + (size_t)g.old_off * M,
-                         (size_t)roundup32(len) * M, cudaMemcpyDeviceToDevice, ix->stream));
-      CK(cudaMemcpyAsync(ix->d_ids + noff, ix->d_ids + g.old_off, (size_t)len * sizeof(int),
-                         cudaMemcpyDeviceToDevice, ix->stream));
-      CK(cudaMemcpyAsync(ix->d_norms + noff, ix->d_norms + g.old_off, (size_t)len * sizeof(float),
-                         cudaMemcpyDeviceToDevice, ix->stream));
+      CK(cudaMemcpyAsync(ix->d_codes + (size_t)g.new_off * M, ix->d_codes + (size_t)g.old_off * M,
+                         (size_t)roundup32(len) * M, cudaMemcpyDeviceToDevice, ix->wstream));
+      CK(cudaMemcpyAsync(ix->d_ids + g.new_off, ix->d_ids + g.old_off, (size_t)len * sizeof(int),
+                         cudaMemcpyDeviceToDevice, ix->wstream));
+      CK(cudaMemcpyAsync(ix->d_norms + g.new_off, ix->d_norms + g.old_off, (size_t)len * sizeof(float),
+                         cudaMemcpyDeviceToDevice, ix->wstream));
     }
     ix->pool_used = tail;
+    // the writer's offsets table sees the new regions now; the published one after the data is in place
+    if (grows.size() > 64) {
+      CK(cudaMemcpyAsync(ix->d_woff, ix->h_off.data(), sizeof(long long) * nlist, cudaMemcpyHostToDevice, ix->wstream));
+    } else {
+      for (const Grow &g : grows)
+        CK(cudaMemcpyAsync(ix->d_woff + g.list, &ix->h_off[g.list], sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+    }
   }
-  CK(cudaMemcpyAsync(ix->d_off, ix->h_off.data(), sizeof(long long) * nlist, cudaMemcpyHostToDevice, ix->stream));
   // positions, in arrival order (== list order == tie-break order)
   std::vector<int> pos(n), vid32(n);
   std::vector<int> run(ix->h_len);
   for (int64_t i = 0; i < n; i++) {
     pos[i] = run[list_no[i]]++;
     vid32[i] = (int)vids[i];
-    if (vids[i] > ix->max_vid) ix->max_vid = vids[i];
     if ((size_t)vids[i] >= ix->vid_loc.size()) ix->vid_loc.resize(std::max<size_t>(vids[i] + 1, ix->vid_loc.size() * 2), -1);
     ix->vid_loc[vids[i]] = ((long long)list_no[i] << 32) | (unsigned)pos[i];
   }
@@ -464,13 +663,12 @@ static int append_locked(gb200_index *ix, int64_t n, const int32_t *list_no, con
   for (int64_t s = 0; s < n; s += SLAB) {
     int64_t m = std::min(SLAB, n - s);
     CKI(write_postings(ix, m, list_no + s, pos.data() + s, vid32.data() + s, codes + (size_t)s * M));
-    CK(cudaStreamSynchronize(ix->stream));  // staging buffer is reused
+    CK(cudaStreamSynchronize(ix->wstream));  // staging buffer is reused
   }
-  ix->h_len = run;  // publish: the scan sees the new length only after the data is in place
-  CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
-  ix->nodel_valid_dirty = true;
-  return GB200_OK;
+  ix->h_len = run;
+  ix->max_vid = mv;
+  // publish: the scan sees a new length only after the data (and a moved list's new region) are in place
+  return publish_lists(ix, touched);
 }
 
 int gb200_ivfpq_append(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids,
@@ -481,55 +679,59 @@ int gb200_ivfpq_append(gb200_index *ix, int64_t n, const int32_t *list_no, const
     return GB200_ENOTTRAINED;
   }
   if (n == 0) return GB200_OK;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
   return append_locked(ix, n, list_no, vids, codes);
 }
 
 int gb200_ivfpq_update(gb200_index *ix, int64_t vid, int32_t new_list, const uint8_t *code) {
   if (!ix || ix->kind != 0 || !code || new_list < 0 || new_list >= ix->p.nlist) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
   if (vid < 0 || (size_t)vid >= ix->vid_loc.size() || ix->vid_loc[vid] < 0) return GB200_OK;  // reference: do nothing
   long long loc = ix->vid_loc[vid];
   int old_list = (int)(loc >> 32), old_pos = (int)(loc & 0xffffffff);
   if (old_list == new_list) {
+    std::shared_lock<std::shared_mutex> shared(ix->data_mu);
     int l = new_list, p = old_pos, v = (int)vid;
     CKI(write_postings(ix, 1, &l, &p, &v, code));
-    CK(cudaStreamSynchronize(ix->stream));
+    CK(cudaStreamSynchronize(ix->wstream));
     return GB200_OK;
   }
-  // mark the old posting dead: id |= sign bit  (kDelIdxMask analogue)
-  int dead = (int)((unsigned)vid | 0x80000000u);
-  CK(cudaMemcpyAsync(ix->d_ids + ix->h_off[old_list] + old_pos, &dead, sizeof(int), cudaMemcpyHostToDevice, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
+  {  // mark the old posting dead: id |= sign bit  (kDelIdxMask analogue)
+    std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+    int dead = (int)((unsigned)vid | 0x80000000u);
+    CK(cudaMemcpyAsync(ix->d_ids + ix->h_off[old_list] + old_pos, &dead, sizeof(int), cudaMemcpyHostToDevice, ix->wstream));
+    CK(cudaStreamSynchronize(ix->wstream));
+  }
   int64_t v64 = vid;
   return append_locked(ix, 1, &new_list, &v64, code);
 }
 
 int gb200_ivfpq_list_sizes(gb200_index *ix, int64_t *sizes) {
   if (!ix || ix->kind != 0 || !sizes) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   for (int l = 0; l < ix->p.nlist; l++) sizes[l] = ix->h_len[l];
   return GB200_OK;
 }
 
 int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t *codes) {
   if (!ix || ix->kind != 0 || list_no < 0 || list_no >= ix->p.nlist) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
+  std::shared_lock<std::shared_mutex> shared(ix->data_mu);
   int len = ix->h_len[list_no];
   if (len == 0) return GB200_OK;
   const int M = ix->p.nsubvector;
-  CKI(ix->ws_stage.ensure((size_t)len * (M + sizeof(int))));
-  int *d_i = ix->ws_stage.as<int>();
+  CKI(ix->w_stage.ensure((size_t)len * (M + sizeof(int))));
+  int *d_i = ix->w_stage.as<int>();
   uint8_t *d_c = reinterpret_cast<uint8_t *>(d_i + len);
-  CK(launch_gather_list(ix->d_codes, ix->d_ids, ix->h_off[list_no], len, M, ix->chunk, ix->layout, d_c, d_i, ix->stream));
+  CK(launch_gather_list(ix->d_codes, ix->d_ids, ix->h_off[list_no], len, M, ix->chunk, ix->layout, d_c, d_i, ix->wstream));
   ix->launches++;
   std::vector<int> hi(len);
-  CK(cudaMemcpyAsync(hi.data(), d_i, (size_t)len * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-  CK(cudaMemcpyAsync(codes, d_c, (size_t)len * M, cudaMemcpyDeviceToHost, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
+  CK(cudaMemcpyAsync(hi.data(), d_i, (size_t)len * sizeof(int), cudaMemcpyDeviceToHost, ix->wstream));
+  CK(cudaMemcpyAsync(codes, d_c, (size_t)len * M, cudaMemcpyDeviceToHost, ix->wstream));
+  CK(cudaStreamSynchronize(ix->wstream));
   for (int i = 0; i < len; i++) {
     unsigned u = (unsigned)hi[i];
     ids[i] = (u & 0x80000000u) ? (int64_t)((uint64_t)(u & 0x7fffffffu) | 0x8000000000000000ull) : (int64_t)u;
@@ -537,31 +739,174 @@ int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t
   return GB200_OK;
 }
 
+// Device-side compaction (RealTimeMemData::CompactBucket, realtime_mem_data.cc:354-424): drop moved (kDelIdxMask) and
+// bitmap-deleted postings, keep the survivors' order.
+//   list_no >= 0: that list is rewritten into a fresh region at the pool tail and swapped in by publication — searches
+//                 keep running (they see the old or the new extent, both consistent);
+//   list_no == -1: every list is compacted into a NEW, tightly packed pool (this also returns the regions abandoned
+//                 by list growth); the pools are replaced, so searches are drained for the swap.
+int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped) {
+  if (!ix || ix->kind != 0 || list_no < -1 || list_no >= ix->p.nlist) return GB200_EINVAL;
+  std::lock_guard<std::mutex> w(ix->writer_mu);
+  CKI(use_device(ix));
+  const int nlist = ix->p.nlist, M = ix->p.nsubvector;
+  const int n_lists = list_no >= 0 ? 1 : nlist;
+  if (dropped) *dropped = 0;
+  if (ix->pool_used == 0) return GB200_OK;
+  std::vector<int> lists(n_lists), new_len(n_lists), new_cap(n_lists);
+  std::vector<long long> new_off(n_lists);
+  for (int i = 0; i < n_lists; i++) lists[i] = list_no >= 0 ? list_no : i;
+  const size_t st_bytes = (size_t)n_lists * (sizeof(long long) + 3 * sizeof(int));
+  CompactParams C;
+  memset(&C, 0, sizeof(C));
+  C.M = M;
+  C.chunk = ix->chunk;
+  C.layout = ix->layout;
+  auto fill_sources = [&](CompactParams &c) {
+    long long *d_noff = ix->w_pub.as<long long>();
+    int *d_lists = reinterpret_cast<int *>(d_noff + n_lists);
+    c.lists = d_lists;
+    c.new_off = d_noff;
+    c.new_len = d_lists + n_lists;
+    c.new_cap = d_lists + 2 * n_lists;
+    c.list_off = ix->d_off;
+    c.list_len = ix->d_len;
+    c.codes = ix->d_codes;
+    c.ids = ix->d_ids;
+    c.norms = ix->d_norms;
+    c.live = ix->deleted_count.load() > 0 ? ix->d_live : nullptr;
+    c.live_bits = ix->live_words * 32;
+  };
+  {  // pass 0: survivors per list
+    std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+    CKI(ix->w_pub.ensure(st_bytes));
+    fill_sources(C);
+    CK(cudaMemcpyAsync(const_cast<int *>(C.lists), lists.data(), (size_t)n_lists * sizeof(int), cudaMemcpyHostToDevice, ix->wstream));
+    CK(launch_compact_lists(C, n_lists, ix->wstream));
+    ix->launches++;
+    CK(cudaMemcpyAsync(new_len.data(), C.new_len, (size_t)n_lists * sizeof(int), cudaMemcpyDeviceToHost, ix->wstream));
+    CK(cudaStreamSynchronize(ix->wstream));
+  }
+  long long drop = 0;
+  for (int i = 0; i < n_lists; i++) drop += ix->h_len[lists[i]] - new_len[i];
+  if (dropped) *dropped = drop;
+  if (drop == 0 && list_no >= 0) return GB200_OK;
+  // destination regions
+  long long tail = list_no >= 0 ? ix->pool_used : 0;
+  for (int i = 0; i < n_lists; i++) {
+    // single list: keep the old capacity, so that a search still holding the old (longer) length stays inside the
+    // region; full rebuild: tight, with the usual head-room
+    new_cap[i] = list_no >= 0 ? std::max(ix->h_cap[lists[i]], (int)roundup32(new_len[i]))
+                              : (int)roundup32(new_len[i] + new_len[i] / 8);
+    new_off[i] = tail;
+    tail += new_cap[i];
+  }
+  std::unique_ptr<ExclusiveScope> excl;
+  std::shared_lock<std::shared_mutex> shared(ix->data_mu, std::defer_lock);
+  uint8_t *nc = nullptr;
+  int *ni = nullptr;
+  float *nn = nullptr;
+  long long ncap_pool = ix->pool_cap;
+  if (list_no >= 0) {
+    if (tail > ix->pool_cap) {
+      ExclusiveScope x(ix);
+      CKI(pool_reserve_exclusive(ix, tail));
+    }
+    shared.lock();
+    nc = ix->d_codes, ni = ix->d_ids, nn = ix->d_norms;
+  } else {
+    excl.reset(new ExclusiveScope(ix));
+    ncap_pool = roundup32(std::max<long long>(tail + tail / 4, 1024));
+    if (cudaMalloc(&nc, (size_t)ncap_pool * M) != cudaSuccess || cudaMalloc(&ni, (size_t)ncap_pool * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&nn, (size_t)ncap_pool * sizeof(float)) != cudaSuccess) {
+      if (nc) cudaFree(nc);
+      if (ni) cudaFree(ni);
+      if (nn) cudaFree(nn);
+      cudaGetLastError();
+      set_err("compaction: cannot allocate the new pool (%lld postings)", ncap_pool);
+      return GB200_ENOMEM;
+    }
+  }
+  // pass 1: move the survivors
+  fill_sources(C);
+  CK(cudaMemcpyAsync(const_cast<long long *>(C.new_off), new_off.data(), (size_t)n_lists * sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(const_cast<int *>(C.new_cap), new_cap.data(), (size_t)n_lists * sizeof(int), cudaMemcpyHostToDevice, ix->wstream));
+  C.dst_codes = nc;
+  C.dst_ids = ni;
+  C.dst_norms = nn;
+  CK(launch_compact_lists(C, n_lists, ix->wstream));
+  ix->launches++;
+  CK(cudaStreamSynchronize(ix->wstream));
+  // host tables, vid -> (list, pos) of the survivors
+  std::vector<int> hid;
+  for (int i = 0; i < n_lists; i++) {
+    const int l = lists[i];
+    if (list_no >= 0) ix->pool_live_cap += new_cap[i] - ix->h_cap[l];
+    ix->h_off[l] = new_off[i];
+    ix->h_len[l] = new_len[i];
+    ix->h_cap[l] = new_cap[i];
+    if (new_len[i] == 0) continue;
+    hid.resize(new_len[i]);
+    CK(cudaMemcpy(hid.data(), ni + new_off[i], (size_t)new_len[i] * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < new_len[i]; p++)
+      if (hid[p] >= 0 && (size_t)hid[p] < ix->vid_loc.size()) ix->vid_loc[hid[p]] = ((long long)l << 32) | (unsigned)p;
+  }
+  if (list_no >= 0) {
+    ix->pool_used = tail;
+    CK(cudaMemcpyAsync(ix->d_woff + list_no, &ix->h_off[list_no], sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+    return publish_lists(ix, lists);
+  }
+  // full rebuild: swap the pools (searches are drained), publish every extent
+  cudaFree(ix->d_codes);
+  cudaFree(ix->d_ids);
+  cudaFree(ix->d_norms);
+  ix->d_codes = nc;
+  ix->d_ids = ni;
+  ix->d_norms = nn;
+  ix->pool_cap = ncap_pool;
+  ix->pool_used = tail;
+  ix->pool_live_cap = tail;
+  CK(launch_fill_i32(ix->d_ids + tail, ncap_pool - tail, -1, ix->wstream));
+  CK(cudaMemcpyAsync(ix->d_off, ix->h_off.data(), sizeof(long long) * nlist, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(ix->d_woff, ix->h_off.data(), sizeof(long long) * nlist, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaStreamSynchronize(ix->wstream));
+  return GB200_OK;
+}
+
 // ---- raw vectors -----------------------------------------------------------------------
 static int upload_raw_impl(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, cudaMemcpyKind kind) {
   if (!ix || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
   if (n == 0) return GB200_OK;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
   const int rd = ix->p.raw_d;
   long long need = first_vid + n;
   if (need > 0x7fffffffLL) return GB200_EUNSUPPORTED;
-  if (need > ix->raw_cap) {
+  const long long have = ix->raw_n.load();
+  if (need > ix->raw_cap) {  // the store is replaced: drain the searches for the swap
+    ExclusiveScope xs(ix);
     long long ncap = std::max(need, ix->raw_cap + ix->raw_cap / 2);
     float *nr = nullptr;
     CK(cudaMalloc(&nr, (size_t)ncap * rd * sizeof(float)));
-    if (ix->raw_n > 0)
-      CK(cudaMemcpyAsync(nr, ix->d_raw, (size_t)ix->raw_n * rd * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
+    if (have > 0)
+      CK(cudaMemcpyAsync(nr, ix->d_raw, (size_t)have * rd * sizeof(float), cudaMemcpyDeviceToDevice, ix->wstream));
+    CK(cudaStreamSynchronize(ix->wstream));
     if (ix->d_raw) cudaFree(ix->d_raw);
     ix->d_raw = nr;
     ix->raw_cap = ncap;
   }
-  CK(cudaMemcpyAsync(ix->d_raw + (size_t)first_vid * rd, x, (size_t)n * rd * sizeof(float), kind, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
-  if (need > ix->raw_n) ix->raw_n = need;
-  if (first_vid < ix->aux_n) ix->aux_n = first_vid;  // companions of the rewritten rows are stale
-  ix->nodel_valid_dirty = true;
+  if (need > have) CKI(bitmaps_follow_growth(ix, std::max(need, ix->doc_bits())));
+  std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+  if (first_vid > have)  // rows nobody uploaded (a gap) read as zero vectors rather than as whatever the allocation held
+    CK(cudaMemsetAsync(ix->d_raw + (size_t)have * rd, 0, (size_t)(first_vid - have) * rd * sizeof(float), ix->wstream));
+  CK(cudaMemcpyAsync(ix->d_raw + (size_t)first_vid * rd, x, (size_t)n * rd * sizeof(float), kind, ix->wstream));
+  CK(cudaStreamSynchronize(ix->wstream));
+  {
+    std::lock_guard<std::mutex> a(ix->aux_mu);
+    if (first_vid < ix->aux_n.load()) ix->aux_n = first_vid;  // companions of the rewritten rows are stale
+  }
+  if (need > have) ix->raw_n = need;  // published after the rows are in place
   return GB200_OK;
 }
 
@@ -572,87 +917,110 @@ int gb200_upload_raw_dev(gb200_index *ix, int64_t first_vid, int64_t n, const fl
   return upload_raw_impl(ix, first_vid, n, x_dev, cudaMemcpyDeviceToDevice);
 }
 
-int64_t gb200_raw_count(gb200_index *ix) { return ix ? ix->raw_n : 0; }
+int64_t gb200_raw_count(gb200_index *ix) { return ix ? ix->raw_n.load() : 0; }
 
-// ---- deleted bitmap ----------------------------------------------------------------------
-static int push_deleted(gb200_index *ix) {
-  long long words = (long long)ix->h_deleted.size();
-  if (words > ix->deleted_words_dev) {
-    if (ix->d_deleted) cudaFree(ix->d_deleted);
-    ix->d_deleted = nullptr;
-    long long cap = words + words / 2 + 1024;
-    CK(cudaMalloc(&ix->d_deleted, (size_t)cap * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(ix->d_deleted, 0, (size_t)cap * sizeof(uint32_t), ix->stream));
-    ix->deleted_words_dev = cap;
+// ---- live-docs bitmap: contents ----------------------------------------------------------------------
+// upload the words of h_deleted listed in `touched` (as ~deleted) — only what changed travels
+static int push_live_words(gb200_index *ix, const std::vector<long long> &touched) {
+  if (touched.empty()) return GB200_OK;
+  const int n = (int)touched.size();
+  std::vector<uint32_t> vals(n);
+  for (int i = 0; i < n; i++) vals[i] = ~ix->h_deleted[(size_t)touched[i]];
+  CKI(live_reserve(ix, std::max<long long>((long long)ix->h_deleted.size(), (ix->doc_bits() + 31) / 32)));
+  {
+    std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+    CKI(ix->w_stage.ensure((size_t)n * (sizeof(long long) + sizeof(uint32_t))));
+    long long *d_idx = ix->w_stage.as<long long>();
+    uint32_t *d_val = reinterpret_cast<uint32_t *>(d_idx + n);
+    CK(cudaMemcpyAsync(d_idx, touched.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+    CK(cudaMemcpyAsync(d_val, vals.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->wstream));
+    CK(launch_scatter_words(d_idx, d_val, n, ix->d_live, ix->wstream));
+    ix->launches++;
+    CK(cudaStreamSynchronize(ix->wstream));
   }
-  if (words)
-    CK(cudaMemcpyAsync(ix->d_deleted, ix->h_deleted.data(), (size_t)words * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                       ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
-  ix->nodel_valid_dirty = true;
   return GB200_OK;
 }
 
 int gb200_set_deleted(gb200_index *ix, const int64_t *docids, int64_t n, int deleted) {
   if (!ix || n < 0 || (n > 0 && !docids)) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
+  for (int64_t i = 0; i < n; i++)
+    if (docids[i] < 0 || docids[i] > 0x7ffffffeLL) return GB200_EINVAL;
+  std::vector<long long> touched;
+  long long cnt = ix->deleted_count.load();
   for (int64_t i = 0; i < n; i++) {
     int64_t doc = docids[i];
-    if (doc < 0 || doc > 0x7ffffffeLL) return GB200_EINVAL;
-    size_t w = (size_t)(doc >> 5);
-    if (w >= ix->h_deleted.size()) ix->h_deleted.resize(std::max(w + 1, ix->h_deleted.size() * 2), 0u);
-    if (deleted)
-      ix->h_deleted[w] |= 1u << (doc & 31);
-    else
-      ix->h_deleted[w] &= ~(1u << (doc & 31));
-  }
-  ix->any_deleted = false;
-  for (uint32_t w : ix->h_deleted)
-    if (w) {
-      ix->any_deleted = true;
-      break;
+    size_t wd = (size_t)(doc >> 5);
+    if (wd >= ix->h_deleted.size()) ix->h_deleted.resize(std::max(wd + 1, ix->h_deleted.size() * 2), 0u);
+    const uint32_t bit = 1u << (doc & 31), old = ix->h_deleted[wd];
+    const uint32_t nw = deleted ? (old | bit) : (old & ~bit);
+    if (nw != old) {
+      ix->h_deleted[wd] = nw;
+      cnt += deleted ? 1 : -1;
+      touched.push_back((long long)wd);
     }
-  return push_deleted(ix);
+  }
+  std::sort(touched.begin(), touched.end());
+  touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+  CKI(push_live_words(ix, touched));
+  ix->deleted_count = cnt;
+  if (!touched.empty() && ix->inst.active) CKI(rebuild_installed_filter(ix));  // the installed filter folds the deleted bits in
+  return GB200_OK;
 }
 
+// Bring the device bitmap in line with the reference's BitmapManager contents (bit = 1: deleted).  Only words that differ
+// from the shadow copy are uploaded, so calling this before every Search (the reference tests the bitmap live, and
+// some engine paths set bits without calling RetrievalModel::Delete — search/gamma_engine.cc:866) costs one memcmp.
 int gb200_upload_deleted_bitmap(gb200_index *ix, const uint8_t *bitmap, int64_t nbits) {
   if (!ix || nbits < 0 || (nbits > 0 && !bitmap)) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
-  size_t words = (size_t)((nbits + 31) / 32);
-  ix->h_deleted.assign(words, 0u);
+  const size_t words = (size_t)((nbits + 31) / 32), bytes = (size_t)((nbits + 7) / 8);
+  if (words > ix->h_deleted.size()) ix->h_deleted.resize(words, 0u);
   // byte[id>>3] & (1 << (id&7))  ==  little-endian u32 word[id>>5] bit (id&31)
-  size_t bytes = (size_t)((nbits + 7) / 8);
-  memcpy(ix->h_deleted.data(), bitmap, bytes);
-  if (nbits & 31) ix->h_deleted[words - 1] &= (1u << (nbits & 31)) - 1u;
-  ix->any_deleted = false;
-  for (uint32_t w : ix->h_deleted)
-    if (w) {
-      ix->any_deleted = true;
-      break;
+  std::vector<long long> touched;
+  long long cnt = ix->deleted_count.load();
+  const size_t full = bytes / 4;
+  const uint8_t *shadow = reinterpret_cast<const uint8_t *>(ix->h_deleted.data());
+  for (size_t w0 = 0; w0 < full; w0 += 1024) {  // compare 4 KB at a time, look closer only where something changed
+    const size_t w1 = std::min(full, w0 + 1024);
+    if (!memcmp(shadow + w0 * 4, bitmap + w0 * 4, (w1 - w0) * 4)) continue;
+    for (size_t wd = w0; wd < w1; wd++) {
+      uint32_t nw;
+      memcpy(&nw, bitmap + wd * 4, 4);
+      if (nw != ix->h_deleted[wd]) {
+        cnt += __builtin_popcount(nw) - __builtin_popcount(ix->h_deleted[wd]);
+        ix->h_deleted[wd] = nw;
+        touched.push_back((long long)wd);
+      }
     }
-  return push_deleted(ix);
+  }
+  if (full < words) {  // last, partial word
+    uint32_t nw = 0;
+    memcpy(&nw, bitmap + full * 4, bytes - full * 4);
+    if (nbits & 31) nw &= (1u << (nbits & 31)) - 1u;
+    if (nw != ix->h_deleted[full]) {
+      cnt += __builtin_popcount(nw) - __builtin_popcount(ix->h_deleted[full]);
+      ix->h_deleted[full] = nw;
+      touched.push_back((long long)full);
+    }
+  }
+  for (size_t wd = words; wd < ix->h_deleted.size(); wd++)  // docs beyond the given bitmap are not deleted
+    if (ix->h_deleted[wd]) {
+      cnt -= __builtin_popcount(ix->h_deleted[wd]);
+      ix->h_deleted[wd] = 0;
+      touched.push_back((long long)wd);
+    }
+  CKI(push_live_words(ix, touched));
+  ix->deleted_count = cnt;
+  if (!touched.empty() && ix->inst.active) CKI(rebuild_installed_filter(ix));
+  return GB200_OK;
 }
 
-// ---- validity bitmap for one search ---------------------------------------------------------
-// returns device pointer (or nullptr = everything valid) in *out
-static int prepare_valid(gb200_index *ix, const gb200_range_filter *filters, int n_filters, const uint32_t **out) {
-  *out = nullptr;
-  long long bits = roundup32(std::max<long long>(ix->doc_bits(), 32));
-  if (n_filters <= 0) {
-    if (!ix->any_deleted) return GB200_OK;
-    if (ix->nodel_valid_dirty || ix->valid_nodel.cap < (size_t)bits / 8) {
-      CKI(ix->valid_nodel.ensure((size_t)bits / 8));
-      CK(launch_build_valid(ix->d_deleted, (long long)ix->h_deleted.size() * 32, nullptr, 0,
-                            ix->valid_nodel.as<uint32_t>(), bits, ix->stream));
-      ix->launches++;
-      ix->nodel_valid_dirty = false;
-    }
-    *out = ix->valid_nodel.as<uint32_t>();
-    return GB200_OK;
-  }
-  // upload the range bitmaps back to back, then one kernel builds NOT deleted AND all ranges
+// ---- validity bitmap of one search: live AND all range filters -------------------------------------------------
+static int build_filter_bitmap(gb200_index *ix, const gb200_range_filter *filters, int n_filters, long long bits,
+                               DevBuf &out, DevBuf &fbytes, DevBuf &fdesc, cudaStream_t st) {
   std::vector<DevRangeFilter> desc(n_filters);
   size_t total = 0;
   std::vector<size_t> offs(n_filters);
@@ -667,41 +1035,94 @@ static int prepare_valid(gb200_index *ix, const gb200_range_filter *filters, int
     offs[f] = total;
     total += (nbytes + 15) & ~(size_t)15;
   }
-  CKI(ix->filt_bytes.ensure(total));
-  CKI(ix->filt_desc.ensure(sizeof(DevRangeFilter) * n_filters));
+  CKI(fbytes.ensure(total));
+  CKI(fdesc.ensure(sizeof(DevRangeFilter) * n_filters));
   for (int f = 0; f < n_filters; f++) {
     const gb200_range_filter &rf = filters[f];
     long long max_aligned = ((long long)rf.max_doc / 8 + 1) * 8 - 1;
     size_t nbytes = (size_t)((max_aligned - rf.min_aligned + 1) / 8);
-    CK(cudaMemcpyAsync(ix->filt_bytes.as<uint8_t>() + offs[f], rf.bitmap, nbytes, cudaMemcpyHostToDevice, ix->stream));
-    desc[f].bitmap = ix->filt_bytes.as<uint8_t>() + offs[f];
+    CK(cudaMemcpyAsync(fbytes.as<uint8_t>() + offs[f], rf.bitmap, nbytes, cudaMemcpyHostToDevice, st));
+    desc[f].bitmap = fbytes.as<uint8_t>() + offs[f];
     desc[f].min_doc = rf.min_doc;
     desc[f].max_doc = rf.max_doc;
     desc[f].min_aligned = rf.min_aligned;
     desc[f].not_in = rf.not_in;
   }
-  CK(cudaMemcpyAsync(ix->filt_desc.p, desc.data(), sizeof(DevRangeFilter) * n_filters, cudaMemcpyHostToDevice, ix->stream));
-  CKI(ix->valid_filt.ensure((size_t)bits / 8));
-  CK(launch_build_valid(ix->any_deleted ? ix->d_deleted : nullptr, (long long)ix->h_deleted.size() * 32,
-                        ix->filt_desc.as<DevRangeFilter>(), n_filters, ix->valid_filt.as<uint32_t>(), bits, ix->stream));
+  CK(cudaMemcpyAsync(fdesc.p, desc.data(), sizeof(DevRangeFilter) * n_filters, cudaMemcpyHostToDevice, st));
+  CKI(out.ensure((size_t)bits / 8));
+  CK(launch_build_valid(ix->deleted_count.load() > 0 ? ix->d_live : nullptr, ix->live_words * 32,
+                        fdesc.as<DevRangeFilter>(), n_filters, out.as<uint32_t>(), bits, st));
+  CK(cudaStreamSynchronize(st));  // desc / the caller's filter bytes may go away
+  return GB200_OK;
+}
+
+// returns device pointer (or nullptr = everything valid) and the number of docs it covers
+static int prepare_valid(gb200_index *ix, SearchCtx &c, const gb200_range_filter *filters, int n_filters,
+                         const uint32_t **out, long long *out_bits) {
+  *out = nullptr;
+  *out_bits = 0;
+  if (n_filters <= 0) {
+    if (ix->deleted_count.load() <= 0) return GB200_OK;
+    *out = ix->d_live;
+    *out_bits = ix->live_words * 32;
+    return GB200_OK;
+  }
+  const long long bits = roundup32(std::max<long long>(ix->doc_bits(), 32));
+  CKI(build_filter_bitmap(ix, filters, n_filters, bits, c.valid_filt, c.filt_bytes, c.filt_desc, c.stream));
+  c.launches++;
+  *out = c.valid_filt.as<uint32_t>();
+  *out_bits = bits;
+  return GB200_OK;
+}
+
+// (re)build the installed filter's bitmap from its host copy: covers every doc known now plus head-room, so that
+// postings appended later fall inside it (docs outside a range's [min, max] fail or pass by its own rule).
+// Caller holds writer_mu and no hold on data_mu.
+static int rebuild_installed_filter(gb200_index *ix) {
+  gb200_index::Installed &I = ix->inst;
+  std::vector<gb200_range_filter> f(I.desc);
+  long long top = ix->doc_bits();
+  for (size_t i = 0; i < f.size(); i++) {
+    f[i].bitmap = I.bytes[i].data();
+    top = std::max<long long>(top, (long long)f[i].max_doc + 1);
+  }
+  const long long bits = roundup32(std::max<long long>(top + top / 4, 1024));
+  ExclusiveScope x(ix);  // the bitmap the *_dev searches read is rewritten (and possibly reallocated)
+  CKI(build_filter_bitmap(ix, f.data(), (int)f.size(), bits, I.valid, I.filt_bytes, I.filt_desc, ix->wstream));
   ix->launches++;
-  CK(cudaStreamSynchronize(ix->stream));  // desc/filters host buffers may go away
-  *out = ix->valid_filt.as<uint32_t>();
+  I.bits = bits;
   return GB200_OK;
 }
 
 int gb200_set_filters(gb200_index *ix, const gb200_range_filter *filters, int n_filters) {
   if (!ix) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   CKI(use_device(ix));
+  gb200_index::Installed &I = ix->inst;
   if (n_filters <= 0) {
-    ix->dev_filter_active = false;
+    ExclusiveScope x(ix);
+    I.active = false;
+    I.desc.clear();
+    I.bytes.clear();
     return GB200_OK;
   }
-  const uint32_t *v = nullptr;
-  CKI(prepare_valid(ix, filters, n_filters, &v));
-  ix->dev_filter_active = true;
-  return GB200_OK;
+  if (!filters) return GB200_EINVAL;
+  std::vector<gb200_range_filter> desc(filters, filters + n_filters);
+  std::vector<std::vector<uint8_t>> bytes(n_filters);
+  for (int f = 0; f < n_filters; f++) {
+    const gb200_range_filter &rf = filters[f];
+    if (!rf.bitmap || rf.max_doc < rf.min_doc || rf.min_aligned > rf.min_doc || rf.min_aligned < 0) {
+      set_err("range filter %d malformed", f);
+      return GB200_EINVAL;
+    }
+    long long max_aligned = ((long long)rf.max_doc / 8 + 1) * 8 - 1;
+    bytes[f].assign(rf.bitmap, rf.bitmap + (size_t)((max_aligned - rf.min_aligned + 1) / 8));
+  }
+  I.desc.swap(desc);
+  I.bytes.swap(bytes);
+  int rc = rebuild_installed_filter(ix);
+  I.active = rc == GB200_OK;
+  return rc;
 }
 
 // ---- search ------------------------------------------------------------------------------------
@@ -712,44 +1133,44 @@ static int resolve_nprobe(gb200_index *ix, const gb200_search_params *sp, int df
   return np;
 }
 
-static int coarse_dev(gb200_index *ix, int n, const float *d_xq, int nprobe, int *d_keys, float *d_cdis) {
+static int coarse_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, int nprobe, int *d_keys, float *d_cdis) {
   const int d = ix->p.d, nlist = ix->p.nlist;
   if (nprobe > 2048) {
     set_err("nprobe=%d > 2048 not implemented", nprobe);
     return GB200_EUNSUPPORTED;
   }
-  CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
-  CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
+  CKI(c.ws_xn.ensure((size_t)n * sizeof(float)));
+  CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
   // distance producer: tcgen05 3xTF32 GEMM (default) or the CUDA-core fp32 kernel (GB200_COARSE=simt)
   const bool use_tc = !ix->tune.coarse_simt && (d % 4 == 0) && (nlist % 4 == 0);
   if (use_tc) {
-    CKI(ix->ws_xs.ensure((size_t)n * d * sizeof(float)));
-    CK(launch_tf32_residual(d_xq, ix->ws_xs.as<float>(), (size_t)n * d, ix->stream));
-    ix->launches++;
+    CKI(c.ws_xs.ensure((size_t)n * d * sizeof(float)));
+    CK(launch_tf32_residual(d_xq, c.ws_xs.as<float>(), (size_t)n * d, c.stream));
+    c.launches++;
   }
   // bound the distance matrix scratch to ~1 GiB by chunking the queries
   long long rows = std::max<long long>(1, (1LL << 28) / nlist);
   if (rows > n) rows = n;
-  CKI(ix->ws_dist.ensure((size_t)rows * nlist * sizeof(float)));
+  CKI(c.ws_dist.ensure((size_t)rows * nlist * sizeof(float)));
   for (long long r0 = 0; r0 < n; r0 += rows) {
     int m = (int)std::min<long long>(rows, n - r0);
     if (use_tc) {
-      CK(launch_tc_gemm(d_xq + (size_t)r0 * d, ix->ws_xs.as<float>() + (size_t)r0 * d, ix->ws_xn.as<float>() + r0,
-                        ix->d_cent, ix->d_cent_small, ix->d_cent_norm, m, nlist, d, ix->ws_dist.as<float>(), nlist, 1,
-                        ix->stream));
+      CK(launch_tc_gemm(d_xq + (size_t)r0 * d, c.ws_xs.as<float>() + (size_t)r0 * d, c.ws_xn.as<float>() + r0,
+                        ix->d_cent, ix->d_cent_small, ix->d_cent_norm, m, nlist, d, c.ws_dist.as<float>(), nlist, 1,
+                        c.stream));
     } else {
-      CK(launch_coarse_dist(d_xq + (size_t)r0 * d, ix->ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
-                            ix->ws_dist.as<float>(), ix->stream));
+      CK(launch_coarse_dist(d_xq + (size_t)r0 * d, c.ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
+                            c.ws_dist.as<float>(), c.stream));
     }
-    CK(launch_coarse_select(ix->ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
-                            d_cdis + (size_t)r0 * nprobe, ix->stream));
-    ix->launches += 2;
+    CK(launch_coarse_select(c.ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
+                            d_cdis + (size_t)r0 * nprobe, c.stream));
+    c.launches += 2;
   }
-  ix->launches += 1;
+  c.launches += 1;
   return GB200_OK;
 }
 
-// Positional work plan of one scan launch (DESIGN.md §4 "Work plan"): queries [0, n_full) are one work item each,
+// Positional work plan of one v2 / M = 64 scan launch: queries [0, n_full) are one work item each,
 // queries [n_full, n) are s_tail items each, rows = candidate rows per query in the [n][rows][R] buffer.
 // n >= slots: whole waves of resident CTAs stay unsplit, the last partial wave is split slots / n_tail ways;
 // n < slots: every query is split s_uniform ways (the caller's whole-wave heuristic).  Pure arithmetic (CPU-testable
@@ -780,9 +1201,9 @@ int gb200_debug_plan(int n, int slots, int nprobe, int recall_num, int s_uniform
 }
 
 // scan + rerank with probes already on the device
-static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, const gb200_search_params *sp, int nprobe,
-                           const int *d_keys, const float *d_cdis, const uint32_t *d_valid, float *d_out_d,
-                           long long *d_out_i) {
+static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, int k, const gb200_search_params *sp,
+                           int nprobe, const int *d_keys, const float *d_cdis, const uint32_t *d_valid,
+                           long long valid_bits, float *d_out_d, long long *d_out_i) {
   const int M = ix->p.nsubvector;
   const Tuning &T = ix->tune;
   int R = sp->recall_num < k ? k : sp->recall_num;  // gamma_index_ivfpq.cc:762-765
@@ -802,17 +1223,26 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   int variant = ix->mode == 1 ? T.scan_variant : ix->mode == 2 ? 2 : 0;
   int threads = T.scan_threads;
   int cap = scan_buffer_cap(R);  // power of two >= R + 512, >= 1024
+  int ctas_per_sm = 3;
   if (ix->mode == 1) {
     if (variant != 2 && variant != 3) variant = 3;
-    if (variant == 2 && (cap > 2048 || (cap > 1024 && threads != 512))) variant = 3;  // v2 keeps 4 keys per thread in its select
-    if (variant == 2 && threads == 512 && cap < 2048) cap = 2048;
-    if (variant == 3 && cap > 4 * threads) threads = 512;           // R > 512: 2048 / 4096 keys (4 / 8 per thread)
-    if (variant == 3 && threads == 512 && cap < 2048) cap = 2048;   // room for one block of each of the 16 warps
+    if (variant == 2) {
+      if (threads != 256 && threads != 384 && threads != 512) threads = 256;
+      if (cap > 2048 || (cap > 1024 && threads != 512)) variant = 3;  // v2 keeps 4 keys per thread in its select
+      else if (threads == 512 && cap < 2048) cap = 2048;
+      ctas_per_sm = threads >= 384 ? 2 : 3;
+    }
+    if (variant == 3) {
+      if (threads == 0) threads = 384;
+      if (cap > 1024) threads = 512;                 // R > 512: 2048 / 4096 keys (4 / 8 per thread in the select)
+      if (threads == 512 && cap < 2048) cap = 2048;  // room for one block of each of the 16 warps
+      ctas_per_sm = scan_v3_ctas_per_sm(threads, cap);
+    }
   } else if (ix->mode == 2) {
     threads = 384;
     if (cap < R + 384) cap *= 2;  // room for one block of every warp above the survivors
+    ctas_per_sm = 2;
   }
-  const int ctas_per_sm = ix->mode == 0 ? 3 : (threads >= 384 ? 2 : 3);
   const int slots = ix->num_sms * ctas_per_sm;
 
   ScanParams P;
@@ -828,7 +1258,8 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   P.list_off = ix->d_off;
   P.list_len = ix->d_len;
   P.valid = d_valid;
-  P.scanned = ix->d_scanned;
+  P.valid_bits = valid_bits;
+  P.scanned = c.d_scanned;
   P.n = n;
   P.d = ix->p.d;
   P.M = M;
@@ -883,65 +1314,65 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
     P.max_np_s = (plan && n_full > 0) ? nprobe : (nprobe + S - 1) / S;
   }
   P.S = S;
-  CKI(ix->ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
-  P.cand = ix->ws_cand.as<u64>();
+  CKI(c.ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
+  P.cand = c.ws_cand.as<u64>();
   if (T.scan_timing && variant == 2 && ix->mode == 1) {
-    if (!ix->d_timing) CK(cudaMalloc(&ix->d_timing, 8 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ix->d_timing, 0, 8 * sizeof(unsigned long long), ix->stream));
-    P.timing = ix->d_timing;
+    if (!c.d_timing) CK(cudaMalloc(&c.d_timing, 8 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c.d_timing, 0, 8 * sizeof(unsigned long long), c.stream));
+    P.timing = c.d_timing;
   }
-  const size_t smem_need = variant == 3 ? scan_v3_smem_bytes(nprobe, cap) : scan_smem_bytes(P, ix->mode);
+  const size_t smem_need = variant == 3 ? scan_v3_smem_bytes_for(nprobe, cap, threads) : scan_smem_bytes(P, ix->mode);
   if (smem_need > 227 * 1024) {
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d nprobe=%d): not implemented", smem_need, M, R, nprobe);
     return GB200_EUNSUPPORTED;
   }
-  CK(cudaMemsetAsync(ix->d_scanned, 0, sizeof(unsigned long long), ix->stream));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
+  CK(cudaMemsetAsync(c.d_scanned, 0, sizeof(unsigned long long), c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[1], c.stream));
   const int *d_rows = nullptr;
   if (ix->mode == 1 || ix->mode == 2) {
     // per-query lookup tables: built on the side stream during the coarse stage (ivfpq_search_impl), else here
     const size_t lut_bytes = ix->mode == 2 ? 98304 : 65536;
-    if (ix->lut_built_n == n && ix->lut_built_ip == (ip ? 1 : 0)) {
-      CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));
+    if (c.lut_built_n == n && c.lut_built_ip == (ip ? 1 : 0)) {
+      CK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
     } else {
-      CKI(ix->ws_lut.ensure((size_t)n * lut_bytes));
+      CKI(c.ws_lut.ensure((size_t)n * lut_bytes));
       if (ix->mode == 2)
-        CK(launch_lut_build_m64(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
+        CK(launch_lut_build_m64(d_xq, ix->d_pq_t, c.ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, c.stream));
       else
-        CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, ix->stream));
-      ix->launches++;
+        CK(launch_lut_build_m32(d_xq, ix->d_pq_t, c.ws_lut.as<float>(), n, ix->p.d, ix->dsub, ip ? 1 : 0, c.stream));
+      c.launches++;
     }
-    ix->lut_built_n = 0;
-    P.lut_g = ix->ws_lut.as<float>();
+    c.lut_built_n = 0;
+    P.lut_g = c.ws_lut.as<float>();
     if (variant == 3) {
       // control words [next_q, pad x3][claim x n][rows x n], zeroed; per-query probe tables
-      CKI(ix->ws_ctl.ensure((size_t)(4 + 2 * (size_t)n) * sizeof(int)));
-      CK(cudaMemsetAsync(ix->ws_ctl.p, 0, (size_t)(4 + 2 * (size_t)n) * sizeof(int), ix->stream));
-      P.v3_next_q = ix->ws_ctl.as<int>();
-      P.v3_claim = ix->ws_ctl.as<int>() + 4;
-      P.v3_rows = ix->ws_ctl.as<int>() + 4 + n;
+      CKI(c.ws_ctl.ensure((size_t)(4 + 2 * (size_t)n) * sizeof(int)));
+      CK(cudaMemsetAsync(c.ws_ctl.p, 0, (size_t)(4 + 2 * (size_t)n) * sizeof(int), c.stream));
+      P.v3_next_q = c.ws_ctl.as<int>();
+      P.v3_claim = c.ws_ctl.as<int>() + 4;
+      P.v3_rows = c.ws_ctl.as<int>() + 4 + n;
       d_rows = P.v3_rows;
-      CKI(ix->ws_probe.ensure((size_t)n * scan_v3_probe_bytes(nprobe)));
-      P.probe_g = ix->ws_probe.as<unsigned char>();
-      CK(launch_probe_setup_v3(P, ix->stream));
-      ix->launches++;
+      CKI(c.ws_probe.ensure((size_t)n * scan_v3_probe_bytes(nprobe)));
+      P.probe_g = c.ws_probe.as<unsigned char>();
+      CK(launch_probe_setup_v3(P, c.stream));
+      c.launches++;
     } else {
       if (plan) {
         P.n_items = n_items;
         P.n_full = n_full;
         P.s_tail = s_tail;
       }
-      CKI(ix->ws_probe.ensure((size_t)(plan ? n_items : n * S) * scan_probe_bytes_host(P.max_np_s)));
-      P.probe_g = ix->ws_probe.as<unsigned char>();
-      CK(launch_probe_setup(P, ix->stream));
-      ix->launches++;
+      CKI(c.ws_probe.ensure((size_t)(plan ? n_items : n * S) * scan_probe_bytes_host(P.max_np_s)));
+      P.probe_g = c.ws_probe.as<unsigned char>();
+      CK(launch_probe_setup(P, c.stream));
+      c.launches++;
     }
   }
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[4], ix->stream));
-  if (variant == 3) CK(launch_ivfpq_scan_v3(P, grid_v3, ix->stream));
-  else CK(launch_ivfpq_scan(P, ix->mode, ix->stream));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[5], ix->stream));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[2], ix->stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[4], c.stream));
+  if (variant == 3) CK(launch_ivfpq_scan_v3(P, grid_v3, c.stream));
+  else CK(launch_ivfpq_scan(P, ix->mode, c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[5], c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[2], c.stream));
   RerankParams Q;
   Q.cand = P.cand;
   Q.keys = d_keys;
@@ -949,7 +1380,7 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   Q.ids = ix->d_ids;
   Q.xq = d_xq;
   Q.raw = ix->d_raw;
-  Q.nraw = ix->raw_n;
+  Q.nraw = ix->raw_n.load();
   Q.out_dist = d_out_d;
   Q.out_ids = d_out_i;
   Q.n = n;
@@ -965,33 +1396,37 @@ static int scan_rerank_dev(gb200_index *ix, int n, const float *d_xq, int k, con
   Q.max_score = sp->max_score;
   Q.nsplit = d_rows;  // v3: rows handed out per query (clamped to S by the kernel)
   Q.n_full = P.n_items > 0 ? P.n_full : 0;
-  CK(launch_rerank(Q, ix->stream));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[3], ix->stream));
-  ix->launches += 2;
+  CK(launch_rerank(Q, c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[3], c.stream));
+  c.launches += 2;
   return GB200_OK;
 }
 
-static int finish_profile(gb200_index *ix) {
+// wait for the context's stream and publish its counters as the index's "last call" statistics
+static int finish_profile(gb200_index *ix, SearchCtx &c) {
   unsigned long long sc = 0;
-  if (ix->d_timing && ix->tune.scan_timing) {
-    unsigned long long t[8];
-    CK(cudaMemcpyAsync(t, ix->d_timing, sizeof(t), cudaMemcpyDeviceToHost, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
+  unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool timing = c.d_timing && ix->tune.scan_timing;
+  if (timing) CK(cudaMemcpyAsync(t, c.d_timing, sizeof(t), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaMemcpyAsync(&sc, c.d_scanned, sizeof(sc), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  if (timing) {
     double n = t[7] ? (double)t[7] : 1.0;
     fprintf(stderr,
             "[gb200 scan timing] ctas %llu | per-CTA cycles: table %.0f setup %.0f loop %.0f (in-loop prunes %.0f, %0.2f prunes, "
             "%.1f sync points) final %.0f\n",
             t[7], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n, t[6] / n, t[3] / n);
   }
-  CK(cudaMemcpyAsync(&sc, ix->d_scanned, sizeof(sc), cudaMemcpyDeviceToHost, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
+  std::lock_guard<std::mutex> g(ix->stats_mu);
   ix->last_scanned = (long long)sc;
-  if (ix->profiling) {
-    cudaEventElapsedTime(&ix->stage_ms[0], ix->ev[0], ix->ev[1]);
-    cudaEventElapsedTime(&ix->stage_ms[1], ix->ev[1], ix->ev[2]);
-    cudaEventElapsedTime(&ix->stage_ms[2], ix->ev[2], ix->ev[3]);
-    cudaEventElapsedTime(&ix->stage_ms[3], ix->ev[0], ix->ev[3]);
-    cudaEventElapsedTime(&ix->scan_kernel_ms, ix->ev[4], ix->ev[5]);
+  ix->launches += c.launches;
+  c.launches = 0;
+  if (c.timed) {
+    cudaEventElapsedTime(&ix->stage_ms[0], c.ev[0], c.ev[1]);
+    cudaEventElapsedTime(&ix->stage_ms[1], c.ev[1], c.ev[2]);
+    cudaEventElapsedTime(&ix->stage_ms[2], c.ev[2], c.ev[3]);
+    cudaEventElapsedTime(&ix->stage_ms[3], c.ev[0], c.ev[3]);
+    cudaEventElapsedTime(&ix->scan_kernel_ms, c.ev[4], c.ev[5]);
   }
   return GB200_OK;
 }
@@ -1007,7 +1442,7 @@ static int check_search_args(gb200_index *ix, int n, const void *xq, int k, cons
   return GB200_OK;
 }
 
-static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, int k,
+static int ivfpq_search_impl(gb200_index *ix, SearchCtx &c, int n, const float *xq, bool xq_on_dev, int k,
                              const gb200_search_params *sp, const gb200_range_filter *filters, int n_filters,
                              bool use_installed_filter, const int64_t *keys_h, const float *cdis_h, int nprobe_pre,
                              float *D, int64_t *I, bool out_on_dev) {
@@ -1019,59 +1454,76 @@ static int ivfpq_search_impl(gb200_index *ix, int n, const float *xq, bool xq_on
   const int d = ix->p.d;
   int nprobe = keys_h ? nprobe_pre : resolve_nprobe(ix, sp, ix->p.nprobe > 0 ? ix->p.nprobe : 80);
   if (nprobe <= 0) return GB200_EINVAL;
+  c.timed = ix->profiling;
   const float *d_xq = xq;
   if (!xq_on_dev) {
-    CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
-    CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-    d_xq = ix->ws_xq.as<float>();
+    CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
+    CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    d_xq = c.ws_xq.as<float>();
   }
   const uint32_t *d_valid = nullptr;
-  if (use_installed_filter && ix->dev_filter_active)
-    d_valid = ix->valid_filt.as<uint32_t>();
-  else
-    CKI(prepare_valid(ix, filters, n_filters, &d_valid));
-  CKI(ix->ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
-  CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
-  ix->lut_built_n = 0;
+  long long valid_bits = 0;
+  if (use_installed_filter && ix->inst.active) {
+    d_valid = ix->inst.valid.as<uint32_t>();
+    valid_bits = ix->inst.bits;
+  } else {
+    CKI(prepare_valid(ix, c, filters, n_filters, &d_valid, &valid_bits));
+  }
+  CKI(c.ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
+  CKI(c.ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
+  if (c.timed) CK(cudaEventRecord(c.ev[0], c.stream));
+  c.lut_built_n = 0;
   if ((ix->mode == 1 || ix->mode == 2) && d <= 1024 && !keys_h && !ix->tune.lut_inline) {
     // K2a depends on the queries only: fork it onto the side stream so it overlaps the coarse quantiser
     const int ipm = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
-    CKI(ix->ws_lut.ensure((size_t)n * (ix->mode == 2 ? 98304 : 65536)));
-    CK(cudaEventRecord(ix->ev_fork, ix->stream));
-    CK(cudaStreamWaitEvent(ix->stream2, ix->ev_fork, 0));
+    CKI(c.ws_lut.ensure((size_t)n * (ix->mode == 2 ? 98304 : 65536)));
+    CK(cudaEventRecord(c.ev_fork, c.stream));
+    CK(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
     if (ix->mode == 2)
-      CK(launch_lut_build_m64(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
+      CK(launch_lut_build_m64(d_xq, ix->d_pq_t, c.ws_lut.as<float>(), n, d, ix->dsub, ipm, c.stream2));
     else
-      CK(launch_lut_build_m32(d_xq, ix->d_pq_t, ix->ws_lut.as<float>(), n, d, ix->dsub, ipm, ix->stream2));
-    CK(cudaEventRecord(ix->ev_join, ix->stream2));
-    ix->launches++;
-    ix->lut_built_n = n;
-    ix->lut_built_ip = ipm;
+      CK(launch_lut_build_m32(d_xq, ix->d_pq_t, c.ws_lut.as<float>(), n, d, ix->dsub, ipm, c.stream2));
+    CK(cudaEventRecord(c.ev_join, c.stream2));
+    c.launches++;
+    c.lut_built_n = n;
+    c.lut_built_ip = ipm;
   }
   if (keys_h) {
     std::vector<int> k32((size_t)n * nprobe);
     for (size_t i = 0; i < k32.size(); i++) k32[i] = (keys_h[i] < 0 || keys_h[i] >= ix->p.nlist) ? -1 : (int)keys_h[i];
-    CK(cudaMemcpyAsync(ix->ws_keys.p, k32.data(), k32.size() * sizeof(int), cudaMemcpyHostToDevice, ix->stream));
-    CK(cudaMemcpyAsync(ix->ws_cdis.p, cdis_h, (size_t)n * nprobe * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
+    CK(cudaMemcpyAsync(c.ws_keys.p, k32.data(), k32.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemcpyAsync(c.ws_cdis.p, cdis_h, (size_t)n * nprobe * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
   } else {
-    CKI(coarse_dev(ix, n, d_xq, nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>()));
+    CKI(coarse_dev(ix, c, n, d_xq, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
   }
   float *d_D = D;
   long long *d_I = reinterpret_cast<long long *>(I);
   if (!out_on_dev) {
-    CKI(ix->ws_out_d.ensure((size_t)n * k * sizeof(float)));
-    CKI(ix->ws_out_i.ensure((size_t)n * k * sizeof(long long)));
-    d_D = ix->ws_out_d.as<float>();
-    d_I = ix->ws_out_i.as<long long>();
+    CKI(c.ws_out_d.ensure((size_t)n * k * sizeof(float)));
+    CKI(c.ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+    d_D = c.ws_out_d.as<float>();
+    d_I = c.ws_out_i.as<long long>();
   }
-  CKI(scan_rerank_dev(ix, n, d_xq, k, sp, nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>(), d_valid, d_D, d_I));
+  CKI(scan_rerank_dev(ix, c, n, d_xq, k, sp, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>(), d_valid, valid_bits, d_D,
+                      d_I));
   if (!out_on_dev) {
-    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-    CKI(finish_profile(ix));
+    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    CKI(finish_profile(ix, c));
   }
+  return GB200_OK;
+}
+
+// order the context's stream after the caller's stream (device-resident entry points), and back
+static int join_user_stream(SearchCtx &c, cudaStream_t cs) {
+  CK(cudaEventRecord(c.ev_user, cs));
+  CK(cudaStreamWaitEvent(c.stream, c.ev_user, 0));
+  return GB200_OK;
+}
+static int release_to_user_stream(SearchCtx &c, cudaStream_t cs) {
+  CK(cudaEventRecord(c.ev_user, c.stream));
+  CK(cudaStreamWaitEvent(cs, c.ev_user, 0));
   return GB200_OK;
 }
 
@@ -1079,9 +1531,10 @@ int gb200_ivfpq_search(gb200_index *ix, int n, const float *xq, int k, const gb2
                        const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
   CKI(check_search_args(ix, n, xq, k, sp, D, I));
   if (ix->kind != 0) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  return ivfpq_search_impl(ix, n, xq, false, k, sp, filters, n_filters, false, nullptr, nullptr, 0, D, I, false);
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  return ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, filters, n_filters, false, nullptr, nullptr, 0, D, I, false);
 }
 
 int gb200_ivfpq_search_preassigned(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
@@ -1089,29 +1542,24 @@ int gb200_ivfpq_search_preassigned(gb200_index *ix, int n, const float *xq, int 
                                    const float *coarse_dis, int nprobe, float *D, int64_t *I) {
   CKI(check_search_args(ix, n, xq, k, sp, D, I));
   if (ix->kind != 0 || !keys || !coarse_dis || nprobe <= 0) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  return ivfpq_search_impl(ix, n, xq, false, k, sp, filters, n_filters, false, keys, coarse_dis, nprobe, D, I, false);
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  return ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, filters, n_filters, false, keys, coarse_dis, nprobe, D, I, false);
 }
 
 int gb200_ivfpq_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp,
                            float *D_dev, int64_t *I_dev, void *stream) {
   CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
   if (ix->kind != 0) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  // order after the caller's stream, run on ours, and make the caller's stream wait for us
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  // order after the caller's stream, run on the context's, and make the caller's stream wait for the result
   cudaStream_t cs = (cudaStream_t)stream;
-  cudaEvent_t e;
-  CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CK(cudaEventRecord(e, cs));
-  CK(cudaStreamWaitEvent(ix->stream, e, 0));
-  int rc = ivfpq_search_impl(ix, n, xq_dev, true, k, sp, nullptr, 0, true, nullptr, nullptr, 0, D_dev, I_dev, true);
-  if (rc == GB200_OK) {
-    CK(cudaEventRecord(e, ix->stream));
-    CK(cudaStreamWaitEvent(cs, e, 0));
-  }
-  cudaEventDestroy(e);
+  CKI(join_user_stream(*s.c, cs));
+  int rc = ivfpq_search_impl(ix, *s.c, n, xq_dev, true, k, sp, nullptr, 0, true, nullptr, nullptr, 0, D_dev, I_dev, true);
+  if (rc == GB200_OK) CKI(release_to_user_stream(*s.c, cs));
   return rc;
 }
 
@@ -1120,69 +1568,85 @@ int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, floa
     return GB200_EINVAL;
   if (!ix->trained) return GB200_ENOTTRAINED;
   if (n == 0) return GB200_OK;
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  SearchCtx &c = *s.c;
   const int d = ix->p.d;
-  CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
-  CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-  CKI(ix->ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
-  CKI(ix->ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
-  CKI(coarse_dev(ix, n, ix->ws_xq.as<float>(), nprobe, ix->ws_keys.as<int>(), ix->ws_cdis.as<float>()));
+  CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
+  CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  CKI(c.ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
+  CKI(c.ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
+  CKI(coarse_dev(ix, c, n, c.ws_xq.as<float>(), nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
   std::vector<int> k32((size_t)n * nprobe);
-  CK(cudaMemcpyAsync(k32.data(), ix->ws_keys.p, k32.size() * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-  CK(cudaMemcpyAsync(coarse_dis, ix->ws_cdis.p, (size_t)n * nprobe * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
+  CK(cudaMemcpyAsync(k32.data(), c.ws_keys.p, k32.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaMemcpyAsync(coarse_dis, c.ws_cdis.p, (size_t)n * nprobe * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
   for (size_t i = 0; i < k32.size(); i++) keys[i] = k32[i];
+  ix->launches += c.launches;
+  c.launches = 0;
   return GB200_OK;
 }
 
 // ---- flat ----------------------------------------------------------------------------------------
-// x - tf32(x) and |x|^2 of the raw rows [aux_n, raw_n), kept next to the raw store once a batched flat search needs them
-static int ensure_raw_aux(gb200_index *ix) {
+// x - tf32(x) and |x|^2 of the raw rows [aux_n, rows), kept next to the raw store once a batched flat search needs them.
+// Index-level state shared by all searches: built under aux_mu on the caller's stream, which is then drained so that
+// every other context may read the rows.
+static int ensure_raw_aux(gb200_index *ix, SearchCtx &c, long long rows) {
+  if (ix->aux_n.load() >= rows && ix->aux_cap >= ix->raw_cap) return GB200_OK;
+  std::lock_guard<std::mutex> a(ix->aux_mu);
   const int d = ix->p.raw_d;
   if (ix->aux_cap < ix->raw_cap) {
+    // other searches may be reading the old companions (they hold data_mu shared like this call): allocate the new ones,
+    // copy what exists, and retire the old ones only after a device-wide drain
     float *ns = nullptr, *nn = nullptr;
     CK(cudaMalloc(&ns, (size_t)ix->raw_cap * d * sizeof(float)));
     CK(cudaMalloc(&nn, (size_t)ix->raw_cap * sizeof(float)));
-    CK(cudaStreamSynchronize(ix->stream));
+    const long long have = ix->aux_n.load();
+    if (have > 0) {
+      CK(cudaMemcpyAsync(ns, ix->d_raw_small, (size_t)have * d * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+      CK(cudaMemcpyAsync(nn, ix->d_raw_norm, (size_t)have * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    }
+    CK(cudaDeviceSynchronize());
     if (ix->d_raw_small) cudaFree(ix->d_raw_small);
     if (ix->d_raw_norm) cudaFree(ix->d_raw_norm);
     ix->d_raw_small = ns;
     ix->d_raw_norm = nn;
     ix->aux_cap = ix->raw_cap;
-    ix->aux_n = 0;
   }
-  if (ix->aux_n < ix->raw_n) {
-    const long long r0 = ix->aux_n, m = ix->raw_n - r0;
-    CK(launch_tf32_residual(ix->d_raw + (size_t)r0 * d, ix->d_raw_small + (size_t)r0 * d, (size_t)m * d, ix->stream));
+  const long long r0 = ix->aux_n.load();
+  if (r0 < rows) {
+    const long long m = rows - r0;
+    CK(launch_tf32_residual(ix->d_raw + (size_t)r0 * d, ix->d_raw_small + (size_t)r0 * d, (size_t)m * d, c.stream));
     for (long long s0 = 0; s0 < m; s0 += (1 << 30) / 8) {  // row_norms takes int rows
-      int rows = (int)std::min<long long>((1 << 30) / 8, m - s0);
-      CK(launch_row_norms(ix->d_raw + (size_t)(r0 + s0) * d, rows, d, ix->d_raw_norm + r0 + s0, ix->stream));
+      int nr = (int)std::min<long long>((1 << 30) / 8, m - s0);
+      CK(launch_row_norms(ix->d_raw + (size_t)(r0 + s0) * d, nr, d, ix->d_raw_norm + r0 + s0, c.stream));
     }
-    ix->launches += 2;
-    ix->aux_n = ix->raw_n;
+    c.launches += 2;
+    CK(cudaStreamSynchronize(c.stream));
+    ix->aux_n = rows;
   }
   return GB200_OK;
 }
 
 // batched FLAT: tcgen05 3xTF32 GEMM per database chunk -> running candidate select -> exact re-score (flat_tc.cu)
-static int flat_tc_dev(gb200_index *ix, int n, const float *d_xq, int k, const gb200_search_params *sp,
-                       const uint32_t *d_valid, float *d_D, long long *d_I) {
+static int flat_tc_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, int k, const gb200_search_params *sp,
+                       const uint32_t *d_valid, long long N, float *d_D, long long *d_I) {
   const int d = ix->p.raw_d;
   const bool ip = sp->metric == GB200_METRIC_INNER_PRODUCT;
-  CKI(ensure_raw_aux(ix));
-  CKI(ix->ws_xs.ensure((size_t)n * d * sizeof(float)));
-  CKI(ix->ws_xn.ensure((size_t)n * sizeof(float)));
-  CK(launch_tf32_residual(d_xq, ix->ws_xs.as<float>(), (size_t)n * d, ix->stream));
-  CK(launch_row_norms(d_xq, n, d, ix->ws_xn.as<float>(), ix->stream));
-  ix->launches += 2;
+  CKI(ensure_raw_aux(ix, c, N));
+  CKI(c.ws_xs.ensure((size_t)n * d * sizeof(float)));
+  CKI(c.ws_xn.ensure((size_t)n * sizeof(float)));
+  CK(launch_tf32_residual(d_xq, c.ws_xs.as<float>(), (size_t)n * d, c.stream));
+  CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
+  c.launches += 2;
   long long nc_max = ((1LL << 26) / n) & ~127LL;  // distance tile <= 256 MB
   if (nc_max < 1024) nc_max = 1024;
   if (ix->tune.flat_chunk_rows > 0) nc_max = std::max(1024LL, ix->tune.flat_chunk_rows & ~127LL);  // tests: force many chunks
-  if (nc_max > ix->raw_n) nc_max = (ix->raw_n + 127) & ~127LL;
-  CKI(ix->ws_dist.ensure((size_t)n * nc_max * sizeof(float)));
+  if (nc_max > N) nc_max = (N + 127) & ~127LL;
+  CKI(c.ws_dist.ensure((size_t)n * nc_max * sizeof(float)));
   const int Kp = flat_tc_candidates(k);
-  CKI(ix->ws_fstate.ensure((size_t)n * Kp * sizeof(u64)));
+  CKI(c.ws_fstate.ensure((size_t)n * Kp * sizeof(u64)));
   // candidates are taken with a slightly widened window; the exact window is applied after the re-score
   auto widen = [](float v, float sign) {
     if (!(fabsf(v) < 1e30f)) return v;
@@ -1190,98 +1654,98 @@ static int flat_tc_dev(gb200_index *ix, int n, const float *d_xq, int k, const g
   };
   const float lo = widen(sp->min_score, -1.f), hi = widen(sp->max_score, 1.f);
   int first = 1;
-  for (long long c0 = 0; c0 < ix->raw_n; c0 += nc_max) {
-    const int nc = (int)std::min<long long>(nc_max, ix->raw_n - c0);
-    CK(launch_tc_gemm(d_xq, ix->ws_xs.as<float>(), ix->ws_xn.as<float>(), ix->d_raw + (size_t)c0 * d,
-                      ix->d_raw_small + (size_t)c0 * d, ix->d_raw_norm + c0, n, nc, d, ix->ws_dist.as<float>(),
-                      (int)nc_max, ip ? 0 : 1, ix->stream));
-    CK(launch_flat_chunk_select(ix->ws_dist.as<float>(), (int)nc_max, nc, c0, d_valid, lo, hi, Kp, first,
-                                ix->ws_fstate.as<u64>(), n, ip ? 1 : 0, ix->stream));
-    ix->launches += 2;
+  for (long long c0 = 0; c0 < N; c0 += nc_max) {
+    const int nc = (int)std::min<long long>(nc_max, N - c0);
+    CK(launch_tc_gemm(d_xq, c.ws_xs.as<float>(), c.ws_xn.as<float>(), ix->d_raw + (size_t)c0 * d,
+                      ix->d_raw_small + (size_t)c0 * d, ix->d_raw_norm + c0, n, nc, d, c.ws_dist.as<float>(),
+                      (int)nc_max, ip ? 0 : 1, c.stream));
+    CK(launch_flat_chunk_select(c.ws_dist.as<float>(), (int)nc_max, nc, c0, d_valid, lo, hi, Kp, first,
+                                c.ws_fstate.as<u64>(), n, ip ? 1 : 0, c.stream));
+    c.launches += 2;
     first = 0;
   }
-  CK(launch_flat_rescore(ix->ws_fstate.as<u64>(), Kp, d_xq, ix->d_raw, n, d, sp->min_score, sp->max_score, k, ip ? 1 : 0,
-                         d_D, d_I, ix->stream));
-  ix->launches += 1;
+  CK(launch_flat_rescore(c.ws_fstate.as<u64>(), Kp, d_xq, ix->d_raw, n, d, sp->min_score, sp->max_score, k, ip ? 1 : 0,
+                         d_D, d_I, c.stream));
+  c.launches += 1;
   return GB200_OK;
 }
 
-static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, int k, const gb200_search_params *sp,
-                     const gb200_range_filter *filters, int n_filters, bool use_installed_filter, float *D, int64_t *I,
-                     bool out_on_dev) {
+static int flat_impl(gb200_index *ix, SearchCtx &c, int n, const float *xq, bool xq_on_dev, int k,
+                     const gb200_search_params *sp, const gb200_range_filter *filters, int n_filters,
+                     bool use_installed_filter, float *D, int64_t *I, bool out_on_dev) {
   if (n == 0) return GB200_OK;
   const int d = ix->p.raw_d;
   if (k > 2048) {
     set_err("flat k=%d > 2048 not implemented", k);
     return GB200_EUNSUPPORTED;
   }
+  const long long N = ix->raw_n.load();  // the rows this search scans (rows published later are not seen)
+  c.timed = ix->profiling;
   const float *d_xq = xq;
   if (!xq_on_dev) {
-    CKI(ix->ws_xq.ensure((size_t)n * d * sizeof(float)));
-    CK(cudaMemcpyAsync(ix->ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-    d_xq = ix->ws_xq.as<float>();
+    CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
+    CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    d_xq = c.ws_xq.as<float>();
   }
   const uint32_t *d_valid = nullptr;
-  if (use_installed_filter && ix->dev_filter_active)
-    d_valid = ix->valid_filt.as<uint32_t>();
-  else
-    CKI(prepare_valid(ix, filters, n_filters, &d_valid));
+  long long valid_bits = 0;
+  if (use_installed_filter && ix->inst.active) {
+    d_valid = ix->inst.valid.as<uint32_t>();
+    valid_bits = ix->inst.bits;
+  } else {
+    CKI(prepare_valid(ix, c, filters, n_filters, &d_valid, &valid_bits));
+  }
+  if (d_valid && valid_bits < N) {  // writers grow the bitmaps before they publish rows; never read past one
+    set_err("validity bitmap covers %lld docs, store has %lld", valid_bits, N);
+    return GB200_EINVAL;
+  }
   float *d_D = D;
   long long *d_I = reinterpret_cast<long long *>(I);
   if (!out_on_dev) {
-    CKI(ix->ws_out_d.ensure((size_t)n * k * sizeof(float)));
-    CKI(ix->ws_out_i.ensure((size_t)n * k * sizeof(long long)));
-    d_D = ix->ws_out_d.as<float>();
-    d_I = ix->ws_out_i.as<long long>();
+    CKI(c.ws_out_d.ensure((size_t)n * k * sizeof(float)));
+    CKI(c.ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+    d_D = c.ws_out_d.as<float>();
+    d_I = c.ws_out_i.as<long long>();
+  }
+  if (c.timed) {
+    CK(cudaEventRecord(c.ev[0], c.stream));
+    CK(cudaEventRecord(c.ev[1], c.stream));
+    CK(cudaEventRecord(c.ev[4], c.stream));
+    CK(cudaEventRecord(c.ev[5], c.stream));
   }
   // batches go through the tensor cores (GB200_FLAT=exact forces the per-query exact scan)
   const bool force_exact = ix->tune.flat_mode == 1, force_tc = ix->tune.flat_mode == 2;
   if (!force_exact && (n >= 16 || force_tc) && (d % 4 == 0) && k <= 1024) {
-    if (ix->profiling) {
-      CK(cudaEventRecord(ix->ev[0], ix->stream));
-      CK(cudaEventRecord(ix->ev[1], ix->stream));
-    }
-    CKI(flat_tc_dev(ix, n, d_xq, k, sp, d_valid, d_D, d_I));
-    if (ix->profiling) {
-      CK(cudaEventRecord(ix->ev[2], ix->stream));
-      CK(cudaEventRecord(ix->ev[3], ix->stream));
-    }
-    if (!out_on_dev) {
-      CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-      CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-      CKI(finish_profile(ix));
-    }
-    return GB200_OK;
+    CKI(flat_tc_dev(ix, c, n, d_xq, k, sp, d_valid, N, d_D, d_I));
+  } else {
+    FlatParams F;
+    F.xq = d_xq;
+    F.raw = ix->d_raw;
+    F.valid = d_valid;
+    F.N = N;
+    F.out_dist = d_D;
+    F.out_ids = d_I;
+    F.n = n;
+    F.d = d;
+    F.k = k;
+    F.is_ip = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
+    F.min_score = sp->min_score;
+    F.max_score = sp->max_score;
+    F.nsplit = flat_exact_splits(N, n);
+    while (F.nsplit > 1 && (long long)F.nsplit * k > 8192) F.nsplit--;
+    CKI(c.ws_flat.ensure((size_t)n * F.nsplit * k * sizeof(u64)));
+    F.scratch = c.ws_flat.as<u64>();
+    CK(launch_flat_exact(F, c.stream));
+    c.launches += 2;
   }
-  FlatParams F;
-  F.xq = d_xq;
-  F.raw = ix->d_raw;
-  F.valid = d_valid;
-  F.N = ix->raw_n;
-  F.out_dist = d_D;
-  F.out_ids = d_I;
-  F.n = n;
-  F.d = d;
-  F.k = k;
-  F.is_ip = sp->metric == GB200_METRIC_INNER_PRODUCT ? 1 : 0;
-  F.min_score = sp->min_score;
-  F.max_score = sp->max_score;
-  F.nsplit = flat_exact_splits(ix->raw_n, n);
-  while (F.nsplit > 1 && (long long)F.nsplit * k > 8192) F.nsplit--;
-  CKI(ix->ws_flat.ensure((size_t)n * F.nsplit * k * sizeof(u64)));
-  F.scratch = ix->ws_flat.as<u64>();
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[0], ix->stream));
-  if (ix->profiling) CK(cudaEventRecord(ix->ev[1], ix->stream));
-  CK(launch_flat_exact(F, ix->stream));
-  ix->launches += 2;
-  if (ix->profiling) {
-    CK(cudaEventRecord(ix->ev[2], ix->stream));
-    CK(cudaEventRecord(ix->ev[3], ix->stream));
+  if (c.timed) {
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    CK(cudaEventRecord(c.ev[3], c.stream));
   }
   if (!out_on_dev) {
-    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
-    CKI(finish_profile(ix));
+    CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(I, d_I, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    CKI(finish_profile(ix, c));
   }
   return GB200_OK;
 }
@@ -1289,35 +1753,30 @@ static int flat_impl(gb200_index *ix, int n, const float *xq, bool xq_on_dev, in
 int gb200_flat_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
                       const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
   CKI(check_search_args(ix, n, xq, k, sp, D, I));
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  if (!ix->d_raw || ix->raw_n == 0) {  // empty store: all slots unfilled
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  if (!ix->d_raw || ix->raw_n.load() == 0) {  // empty store: all slots unfilled
     for (long long i = 0; i < (long long)n * k; i++) {
       D[i] = sp->metric == GB200_METRIC_INNER_PRODUCT ? -FLT_MAX : FLT_MAX;
       I[i] = -1;
     }
     return GB200_OK;
   }
-  return flat_impl(ix, n, xq, false, k, sp, filters, n_filters, false, D, I, false);
+  return flat_impl(ix, *s.c, n, xq, false, k, sp, filters, n_filters, false, D, I, false);
 }
 
 int gb200_flat_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp,
                           float *D_dev, int64_t *I_dev, void *stream) {
   CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  if (!ix->d_raw || ix->raw_n == 0) return GB200_EINVAL;
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  if (!ix->d_raw || ix->raw_n.load() == 0) return GB200_EINVAL;
   cudaStream_t cs = (cudaStream_t)stream;
-  cudaEvent_t e;
-  CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CK(cudaEventRecord(e, cs));
-  CK(cudaStreamWaitEvent(ix->stream, e, 0));
-  int rc = flat_impl(ix, n, xq_dev, true, k, sp, nullptr, 0, true, D_dev, I_dev, true);
-  if (rc == GB200_OK) {
-    CK(cudaEventRecord(e, ix->stream));
-    CK(cudaStreamWaitEvent(cs, e, 0));
-  }
-  cudaEventDestroy(e);
+  CKI(join_user_stream(*s.c, cs));
+  int rc = flat_impl(ix, *s.c, n, xq_dev, true, k, sp, nullptr, 0, true, D_dev, I_dev, true);
+  if (rc == GB200_OK) CKI(release_to_user_stream(*s.c, cs));
   return rc;
 }
 
@@ -1347,40 +1806,49 @@ int gb200_debug_select(int device, const uint64_t *keys, int n, int R, int cap, 
 // ---- accounting ---------------------------------------------------------------------------------
 int64_t gb200_mem_bytes(gb200_index *ix) {
   if (!ix) return 0;
-  std::lock_guard<std::mutex> g(ix->mu);
+  std::lock_guard<std::mutex> w(ix->writer_mu);
   int64_t b = 0;
   if (ix->kind == 0) {
     b += (int64_t)ix->p.nlist * ix->p.d * 4 + (int64_t)ix->p.nlist * 4 + 2LL * ix->p.nsubvector * 256 * ix->dsub * 4;
-    b += ix->pool_cap * (ix->p.nsubvector + 8) + (int64_t)ix->p.nlist * 12;
+    b += ix->pool_cap * (ix->p.nsubvector + 8) + (int64_t)ix->p.nlist * 20;
   }
   b += ix->raw_cap * ix->p.raw_d * 4;
-  b += ix->deleted_words_dev * 4;
+  b += ix->live_words * 4;
   return b;
 }
 int64_t gb200_last_scanned_postings(gb200_index *ix) { return ix ? ix->last_scanned : 0; }
-int64_t gb200_launch_count(gb200_index *ix) { return ix ? ix->launches : 0; }
+int64_t gb200_launch_count(gb200_index *ix) { return ix ? ix->launches.load() : 0; }
 int gb200_last_stage_ms(gb200_index *ix, float *out4) {
   if (!ix || !out4) return GB200_EINVAL;
+  std::lock_guard<std::mutex> g(ix->stats_mu);
   for (int i = 0; i < 4; i++) out4[i] = ix->stage_ms[i];
   return GB200_OK;
 }
 float gb200_last_scan_kernel_ms(gb200_index *ix) { return ix ? ix->scan_kernel_ms : 0.f; }
 
+// wait for the most recently used search context (after *_dev calls) and refresh the counters above
 int gb200_sync(gb200_index *ix) {
   if (!ix) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
   CKI(use_device(ix));
-  return finish_profile(ix);
-}
-int gb200_reload_tuning(gb200_index *ix) {
-  if (!ix) return GB200_EINVAL;
-  std::lock_guard<std::mutex> g(ix->mu);
-  ix->tune.read();
-  return GB200_OK;
+  SearchCtx *c = nullptr;
+  {
+    std::lock_guard<std::mutex> g(ix->ctx_mu);
+    c = ix->last_ctx;
+  }
+  if (!c) return GB200_OK;
+  return finish_profile(ix, *c);
 }
 int gb200_set_profiling(gb200_index *ix, int enable) {
   if (!ix) return GB200_EINVAL;
   ix->profiling = enable != 0;
+  return GB200_OK;
+}
+int gb200_reload_tuning(gb200_index *ix) {
+  if (!ix) return GB200_EINVAL;
+  std::lock_guard<std::mutex> w(ix->writer_mu);
+  cudaSetDevice(ix->p.device);
+  ExclusiveScope x(ix);
+  ix->tune.read();
   return GB200_OK;
 }
 

@@ -129,8 +129,7 @@ __device__ __forceinline__ int setup_probes(const ScanParams &P, const ScanSmem 
     pi.len = 0;
     pi.dis0 = 0.f;
     if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
-      pi.off = P.list_off[key];
-      pi.len = P.list_len[key];
+      load_list_extent(P.list_off, P.list_len, key, pi.off, pi.len);
       if (IP) {  // dis0 = <q, centroid>  (precompute_list_tables_IP, gamma_index_ivfpq.h:216-230)
         const float *cen = P.centroids + (size_t)key * d;
         float s = 0.f;
@@ -236,7 +235,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_generic_kernel(ScanPa
         float dis = pi.dis0;
         if (ok) id = ldg_nc_s32(P.ids + pidx);
         ok = ok && id >= 0;
-        if (ok && P.valid) ok = bitmap_test(P.valid, id);
+        if (ok && P.valid) ok = (long long)id < P.valid_bits && bitmap_test(P.valid, id);
         if (ok) {
           if (!IP) dis += ldg_nc_f32(P.norms + pidx);
           long long blk_base = (pi.off + (long long)b * 32) * (long long)M;
@@ -304,6 +303,8 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
   const int soft_limit = P.cap - WARPS * 32;
   volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
   const int pf = P.pf_blocks;
+  // ids at or beyond the bitmap's size (appended after this search began) and negative ids (dead / padding) fail
+  const uint32_t valid_lim = (uint32_t)(P.valid_bits < 0x7fffffffLL ? P.valid_bits : 0x7fffffffLL);
 
   int pj = 0;
   if (left > 0)
@@ -520,7 +521,7 @@ __device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const Scan
       const uint32_t seq = seq_n;
       const float nb = base_n + nrm_n;
       uint32_t vw = 0xffffffffu;
-      if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
+      if (HAS_VALID) vw = (uint32_t)id < valid_lim ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
       // ---- B: next block straight into the registers just freed
       issue_loads();
       GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
@@ -658,8 +659,7 @@ __global__ void __launch_bounds__(256) probe_setup_kernel(ScanParams P) {
       const int key = P.keys[(size_t)q * P.nprobe + p];
       pi.rank = p;
       if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
-        pi.off = P.list_off[key];
-        pi.len = P.list_len[key];
+        load_list_extent(P.list_off, P.list_len, key, pi.off, pi.len);
         if (P.is_ip) {  // dis0 = <q, centroid>
           const float *cen = P.centroids + (size_t)key * P.d;
           float s = 0.f;
@@ -803,6 +803,8 @@ __device__ __forceinline__ void scan_loop_m64(const ScanParams &P, const ScanSme
   const int soft_limit = P.cap - WARPS * 32;
   volatile int *flags = S.misc + 68;
   const int pf = P.pf_blocks;
+  // ids at or beyond the bitmap's size (appended after this search began) and negative ids (dead / padding) fail
+  const uint32_t valid_lim = (uint32_t)(P.valid_bits < 0x7fffffffLL ? P.valid_bits : 0x7fffffffLL);
 
   int pj = 0;
   if (left > 0)
@@ -954,7 +956,7 @@ __device__ __forceinline__ void scan_loop_m64(const ScanParams &P, const ScanSme
       const uint32_t seq = seq_n;
       const float nb = base_n + nrm_n;
       uint32_t vw = 0xffffffffu;
-      if (HAS_VALID) vw = id >= 0 ? __ldg(P.valid + (id >> 5)) : 0u;
+      if (HAS_VALID) vw = (uint32_t)id < valid_lim ? __ldg(P.valid + (id >> 5)) : 0u;
       issue_lo();
       GB64_LOOK4(0, 16) GB64_LOOK4(4, 20) GB64_LOOK4(8, 24) GB64_LOOK4(12, 28)
       // quarter 2: steps 32..47 from chunk 2

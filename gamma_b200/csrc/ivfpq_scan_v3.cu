@@ -31,11 +31,14 @@ namespace gb {
 // COMPILE-TIME shared-window address (table at GB_SMEM_RESERVED, control words right behind it), so those accesses need
 // no address registers; only the candidate buffer and the item prefix depend on run-time sizes.
 //   [lut 64 KB][misc 96 ints][mbar 16 B][ProbeInfo x nprobe][item prefix x (nprobe + 1), padded to 16][buf u64 cap]
+//   [posting ring: warps x RING slots x 1280 B]
 // misc: [0..1] tau, [2] cnt, [3] tau_f, [4..67] scratch, [68..70] round flags, [72] q, [73] row
 constexpr int V3_MISC_OFF = 65536;
 constexpr int V3_MBAR_OFF = V3_MISC_OFF + 96 * 4;
 constexpr int V3_PINFO_OFF = V3_MBAR_OFF + 16;
+constexpr int V3_SLOT_BYTES = 1280;  // one 32-posting block in the ring: codes 1024 B, ids 128 B, t(p) 128 B
 struct V3Smem {
+  unsigned char *ring;
   u64 *buf;
   ProbeInfo *pinfo;
   int *item_prefix;
@@ -48,15 +51,18 @@ __host__ __device__ inline size_t v3_probe_bytes(int nprobe) {
   return (b + 15) & ~(size_t)15;
 }
 size_t scan_v3_probe_bytes(int nprobe) { return v3_probe_bytes(nprobe); }
-size_t scan_v3_smem_bytes(int nprobe, int cap) { return V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64); }
+size_t scan_v3_smem_bytes(int nprobe, int cap, int warps, int ring) {
+  return V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64) + (size_t)warps * ring * V3_SLOT_BYTES;
+}
 
-__device__ __forceinline__ V3Smem v3_carve(unsigned char *smem, int nprobe) {
+__device__ __forceinline__ V3Smem v3_carve(unsigned char *smem, int nprobe, int cap) {
   V3Smem S;
   S.misc = reinterpret_cast<int *>(smem + V3_MISC_OFF);
   S.mbar = reinterpret_cast<unsigned long long *>(smem + V3_MBAR_OFF);
   S.pinfo = reinterpret_cast<ProbeInfo *>(smem + V3_PINFO_OFF);
   S.item_prefix = reinterpret_cast<int *>(smem + V3_PINFO_OFF + (size_t)nprobe * sizeof(ProbeInfo));
   S.buf = reinterpret_cast<u64 *>(smem + V3_PINFO_OFF + v3_probe_bytes(nprobe));
+  S.ring = smem + V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64);
   return S;
 }
 
@@ -96,6 +102,19 @@ __device__ __forceinline__ T *pin_ptr(T *p) {
   return p;
 }
 
+// ---- cp.async (LDGSTS): asynchronous global -> shared copies of this lane's own bytes, tracked per thread
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ int ld_volatile_s32(const int *p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -124,8 +143,7 @@ __global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
     if (j < np) {
       const int key = P.keys[(size_t)q * np + j];
       if (key >= 0 && key < P.nlist) {  // scan_one_list: key < 0 or >= nlist => skip (gamma_index_ivfpq.cc:602-609)
-        pi.off = P.list_off[key];
-        pi.len = P.list_len[key];
+        load_list_extent(P.list_off, P.list_len, key, pi.off, pi.len);
         if (P.is_ip) {  // dis0 = <q, centroid>
           const float *cen = P.centroids + (size_t)key * P.d;
           float s = 0.f;
@@ -163,20 +181,30 @@ cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // the scan of one (query, row) by one CTA
+//
+// Posting pipeline.  profiles/r02c showed what bounds the register-prefetch + L2-hint scheme of v2 / early v3: the L2's
+// sector-lookup rate (88.8 M lookups per launch = 12.6 TB/s, its ceiling), because every posting sector is looked up
+// twice — once by the prefetch hint, once by the load — and ~40 % of the loads still miss.  Here every warp keeps RING
+// 32-posting blocks in flight as REAL asynchronous copies (cp.async, each lane copies exactly the bytes it will read:
+// 2 x 16 B of codes, its id, its t(p)) into a private ring in shared memory, plus one block in registers: one L2 lookup
+// per sector, RING + 1 blocks of latency cover per warp, no hints, no cross-lane synchronisation (a lane only ever reads
+// what it copied itself, cp.async.wait_group is per thread).  The copy engine runs ahead of the consumer across item
+// boundaries: the next item is claimed and located while the first block of the current one is scanned.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IP, bool HAS_VALID, int WARPS, int PER>
+template <bool IP, bool HAS_VALID, int WARPS, int PER, int RING>
 __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Smem &S, BlockTopR &topr, const int q,
                                                  const int it_first) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane4 = lane * 4;
   const int np = P.nprobe;
   const int n_items = S.item_prefix[np];
   const int ch = P.ch_blocks;
-  const int pf = P.pf_blocks;
   // lane * 0 (a run-time zero the compiler cannot see through): with a provably warp-uniform address ptxas rewrites the
   // claim below into its warp-aggregated form, whose broadcast shuffle waits for the atomic at the point of issue
   int *const claim = P.v3_claim + q + lane * P.v3_zero;
   const int soft_limit = (int)pin_u32((uint32_t)(P.cap - WARPS * 32));
+  // ids at or beyond the bitmap's size (appended after this search began) and negative ids (dead / padding) fail
+  const uint32_t valid_lim = (uint32_t)(P.valid_bits < 0x7fffffffLL ? P.valid_bits : 0x7fffffffLL);
   const uint32_t ctl = pin_u32(smem_u32(S.misc));  // shared-window address of the control words
   volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
 
@@ -185,17 +213,26 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   const unsigned char *const codes_lane = pin_ptr(P.codes + lane * 16);
   const int *const ids_lane = pin_ptr(P.ids + lane);
   const float *const nrm_lane = pin_ptr(P.norms + lane);
+  // this lane's bytes of ring slot 0: codes chunk 0 at +0, chunk 1 at +512; id at ring_w + 1024, t(p) at ring_w + 1152
+  const uint32_t ring_c = pin_u32(smem_u32(S.ring) + (uint32_t)warp * (RING * V3_SLOT_BYTES) + lane * 16);
+  const uint32_t ring_w = pin_u32(smem_u32(S.ring) + (uint32_t)warp * (RING * V3_SLOT_BYTES) + lane * 4);
 
-  // ---- item state.  bi / bi_stop / bi_end are warp-uniform; bil, seqc differ per lane
-  uint32_t bi = 0, bi_end = 0;  // next block to LOAD / end of the current item
+  // ---- consumer's item.  bi / bi_stop / bi_end are warp-uniform; bil, seqc differ per lane
+  uint32_t bi = 0, bi_end = 0;  // next block to TAKE from the ring / end of the current item
   uint32_t bi_stop = 0;         // next block index at which the slow path below has something to do
   uint32_t bil = 0;             // this lane's posting of block b exists  <=>  b < bil
   uint32_t seqc = 0;            // scan-order word of this lane's posting in block b = seqc + 32 * (b + 1)
   float dis0 = 0.f;
+  // ---- copy engine (producer): runs up to RING blocks ahead, at most into the next located item
+  uint32_t pbi = 0, pbi_end = 0;  // next block to REQUEST / end of the producer's item
+  bool p_ahead = false;           // the producer already works on the located next item
+  uint32_t pn = 0, cn = 0;        // blocks requested / taken so far (slot = count % RING)
+  // ---- claims
   int it_next = it_first;       // lane 0: the claim in flight (the first one was issued by the caller)
   bool claim_pending = true;    // a claim has been issued and not consumed yet
-  bool nx_valid = false;        // (nx_j, nx_c) = the located, L2-prefetched item this warp scans next
-  int nx_j = 0, nx_c = 0;
+  bool nx_valid = false;        // the located item this warp scans next: list nx_j, blocks [nx_bi, nx_bi_end)
+  int nx_j = 0;
+  uint32_t nx_bi = 0, nx_bi_end = 0;
 
   // One claim per item: an atomic add on the query's counter by lane 0.  The result stays in lane 0's register until
   // the slow path consumes it one block later (the aggregated form waited for it at the point of issue —
@@ -204,11 +241,28 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     if (lane == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_next) : "l"(claim) : "memory");
     claim_pending = true;
   };
+  // request the producer's next block into ring slot pn % RING (all lanes: each copies its own bytes)
+  auto refill_one = [&]() {
+    if (pn - cn >= (uint32_t)RING) return;
+    if (pbi == pbi_end && !p_ahead && nx_valid) {  // current item fully requested: go on with the located next one
+      pbi = nx_bi;
+      pbi_end = nx_bi_end;
+      p_ahead = true;
+    }
+    if (pbi == pbi_end) return;
+    const uint32_t so = (pn % RING) * V3_SLOT_BYTES;
+    const unsigned char *cp = wide_at<1024>(codes_lane, pbi);
+    cp_async_16(ring_c + so, cp);
+    cp_async_16(ring_c + so + 512, cp + 512);
+    cp_async_4(ring_w + so + 1024, wide_at<128>(ids_lane, pbi));
+    if (!IP) cp_async_4(ring_w + so + 1152, wide_at<128>(nrm_lane, pbi));
+    cp_async_commit();
+    pn++;
+    pbi++;
+  };
   // Slow path, run when bi == bi_stop (warp-uniform), i.e. after the FIRST block of an item and at its END:
-  //  A. a claim is in flight: take its result, locate that item (list j, c-th item of the list) and pull ALL of its
-  //     blocks towards L2 with three bulk prefetches (codes, ids, t(p)) — a whole item (ch_blocks blocks) of lead
-  //     time before this warp gets there.  Items of one list are scanned by different warps at the same time, so a
-  //     stream prefetch "k blocks ahead in the list" would mostly request what somebody else is already loading.
+  //  A. a claim is in flight: take its result and locate that item (list j, blocks) so that the copy engine can run
+  //     into it before the consumer gets there;
   //  B. the current item is finished: open the located one and issue the claim for the one after it.
   auto slow_path = [&]() {
     if (claim_pending) {
@@ -222,34 +276,31 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
           const int v = (j0 + lane < np) ? S.item_prefix[j0 + lane] : 0x7fffffff;
           j += __popc(__ballot_sync(GB_FULL, v <= it));
         }
+        const ProbeInfo pi = S.pinfo[j];
+        const uint32_t offb = (uint32_t)(pi.off >> 5);  // lists start on block boundaries
+        const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
+        const uint32_t b0 = (uint32_t)(it - S.item_prefix[j]) * (uint32_t)ch;
         nx_j = j;
-        nx_c = it - S.item_prefix[j];
-        if (pf > 0) {
-          const ProbeInfo pi = S.pinfo[j];
-          const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
-          const uint32_t b0 = (uint32_t)nx_c * (uint32_t)ch;
-          const uint32_t nb = min((uint32_t)ch, nblk - b0);
-          const size_t first = (size_t)pi.off + (size_t)b0 * 32;  // first posting of the item
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.codes + first * 32), "r"(nb * 1024u));
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.ids + first), "r"(nb * 128u));
-            if (!IP) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.norms + first), "r"(nb * 128u));
-          }
-        }
+        nx_bi = offb + b0;
+        nx_bi_end = offb + min(b0 + (uint32_t)ch, nblk);
       }
     }
     if (bi == bi_end) {
       if (nx_valid) {
         nx_valid = false;
         const ProbeInfo pi = S.pinfo[nx_j];
-        const uint32_t offb = (uint32_t)(pi.off >> 5);  // lists start on block boundaries
-        const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
-        const uint32_t b0 = (uint32_t)nx_c * (uint32_t)ch;
-        bi = offb + b0;
-        bi_end = offb + min(b0 + (uint32_t)ch, nblk);
+        const uint32_t offb = (uint32_t)(pi.off >> 5);
+        bi = nx_bi;
+        bi_end = nx_bi_end;
         bil = offb + ((uint32_t)(pi.len - lane + 31) >> 5);
         seqc = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)lane - (offb << 5) - 32u;
         dis0 = pi.dis0;
+        if (p_ahead) {
+          p_ahead = false;  // the producer is already inside this item
+        } else {
+          pbi = bi;
+          pbi_end = bi_end;
+        }
         claim_issue();
         bi_stop = bi + 1;  // consume that claim after the first block of this item (== bi_end for one-block items)
       }                    // else: the query has no unclaimed item left; bi == bi_end == bi_stop stays
@@ -258,25 +309,33 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     }
   };
 
-  // ---- the block in flight (per lane): 32 pre-rotated code bytes, vid, t(p)
+  // ---- the block in registers (per lane): 32 pre-rotated code bytes, vid, t(p)
   uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
   int id_n = -1;
   float nrm_n = 0.f;
   bool have_n = false;
-  auto issue_loads = [&]() {
+  // take the consumer's next block out of the ring into the registers
+  auto take_next = [&]() {
     if (bi == bi_stop) slow_path();  // warp-uniform, twice per item
     have_n = bi != bi_end;
     if (have_n) {
-      const unsigned char *cp = wide_at<1024>(codes_lane, bi);
-      const uint4 v0 = ldg_nc_v4(cp);
-      const uint4 v1 = ldg_nc_v4(cp + 512);
-      c0 = v0.x, c1 = v0.y, c2 = v0.z, c3 = v0.w, c4 = v1.x, c5 = v1.y, c6 = v1.z, c7 = v1.w;
-      id_n = -1;
-      nrm_n = 0.f;
-      if (bi < bil) {
-        id_n = ldg_nc_s32(wide_at<128>(ids_lane, bi));
-        if (!IP) nrm_n = ldg_nc_f32(wide_at<128>(nrm_lane, bi));
+      if (pn == cn) {  // nothing in flight (query start, or the producer could not run ahead): fill the ring now
+#pragma unroll 1
+        for (int k = 0; k < RING; k++) refill_one();
       }
+      if (pn - cn == (uint32_t)RING) cp_async_wait<RING - 1>();  // steady state: RING - 1 younger copies stay in flight
+      else cp_async_wait<0>();
+      const uint32_t so = (cn % RING) * V3_SLOT_BYTES;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(ring_c + so));
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+512];" : "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7) : "r"(ring_c + so));
+      int idv;
+      float nv = 0.f;
+      asm volatile("ld.shared.s32 %0, [%1+1024];" : "=r"(idv) : "r"(ring_w + so));
+      if (!IP) asm volatile("ld.shared.f32 %0, [%1+1152];" : "=f"(nv) : "r"(ring_w + so));
+      const bool ex = bi < bil;  // the copy engine does not look at list ends; postings beyond them are ignored here
+      id_n = ex ? idv : -1;
+      nrm_n = nv;
+      cn++;
       bi++;
     }
   };
@@ -302,15 +361,16 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   };
 
   bool stalled = false;
-  issue_loads();  // the first claim of this query was issued before the table wait (claim_pending == true)
+  take_next();  // the first claim of this query was issued before the table wait (claim_pending == true)
   int round = 0;
   for (;;) {
     if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
     bool over = false;
     if (!stalled) {
       while (have_n) {  // warp-uniform
-        // ---- table addresses (code << 8 | lane * 4) 16 at a time; the second half's addresses kill the code registers,
-        // which are then refilled with the NEXT block.  32 conflict-free lookups, accumulated as two packed pairs.
+        // ---- table addresses (code << 8 | lane * 4) 16 at a time; 32 conflict-free lookups, accumulated as two
+        // packed pairs.  The first group consumes the registers the last take_next() filled, so the ring slot they
+        // came from is free: the copy engine re-uses it right here.
         uint32_t a[16];
         u64 s01, s23;
 #define GB_ADDR4(W, I)                     \
@@ -322,28 +382,33 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   s01 = f2_add(s01, f2_pack(lds_raw<O + 0>(a[I + 0]), lds_raw<O + 1>(a[I + 1]))); \
   s23 = f2_add(s23, f2_pack(lds_raw<O + 2>(a[I + 2]), lds_raw<O + 3>(a[I + 3])));
         GB_ADDR4(c0, 0) GB_ADDR4(c1, 4) GB_ADDR4(c2, 8) GB_ADDR4(c3, 12)
+        // what the admission test needs of the block in registers, evaluated NOW (asm volatile pins the order) so that
+        // its registers are dead before the next block is taken.
+        //   nb = dis0 + t(p), or NaN when the lane has no posting (padding, beyond the list end, moved away): NaN fails
+        //   the admission compare below by itself.
+        float nb;
+        uint32_t seq;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, 0;\n\tadd.f32 %0, %1, %2;\n\t@p mov.b32 %0, 0x7fc00000;\n\t}"
+            : "=f"(nb)
+            : "f"(dis0), "f"(nrm_n), "r"(id_n));
+        asm volatile("mad.lo.u32 %0, %1, 32, %2;" : "=r"(seq) : "r"(bi), "r"(seqc));
+        uint32_t vw = 0xffffffffu, vbit = 1u;
+        if (HAS_VALID) {
+          vw = (uint32_t)id_n < valid_lim ? __ldg(P.valid + (id_n >> 5)) : 0u;  // latency hidden by the lookups
+          asm volatile("shf.l.wrap.b32 %0, 1, 1, %1;" : "=r"(vbit) : "r"(id_n));  // 1 << (id & 31)
+        }
+        refill_one();
         s01 = f2_pack(lds_raw<0>(a[0]), lds_raw<1>(a[1]));
         s23 = f2_pack(lds_raw<2>(a[2]), lds_raw<3>(a[3]));
         GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
         GB_ADDR4(c4, 0) GB_ADDR4(c5, 4) GB_ADDR4(c6, 8) GB_ADDR4(c7, 12)
-        // what the admission test needs of the block in flight, evaluated NOW (asm volatile pins the order) so that
-        // its registers can be reused by the next block's loads
-        float nb;
-        uint32_t seq;
-        asm volatile("add.f32 %0, %1, %2;" : "=f"(nb) : "f"(dis0), "f"(nrm_n));
-        asm volatile("mad.lo.u32 %0, %1, 32, %2;" : "=r"(seq) : "r"(bi), "r"(seqc));
-        bool ok = id_n >= 0;
-        uint32_t vw = 0xffffffffu, vbit = 1u;
-        if (HAS_VALID) {
-          vw = ok ? __ldg(P.valid + (id_n >> 5)) : 0u;  // latency hidden by the lookups
-          asm volatile("shf.l.wrap.b32 %0, 1, 1, %1;" : "=r"(vbit) : "r"(id_n));  // 1 << (id & 31)
-        }
-        // ---- next block straight into the registers just freed
-        issue_loads();
+        // ---- next block out of the ring, straight into the registers just freed
+        take_next();
         GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
 #undef GB_ADDR4
 #undef GB_LOOK4
-        // ---- filter, pre-test, admission.  Every warp reads the counter once per block so that all of them notice a
+        // ---- pre-test, admission.  Every warp reads the counter once per block so that all of them notice a
         // wanted prune within one block, whether or not they append anything themselves.  The pre-test is one float
         // compare against the float image of tau's distance word (NaN fails it, as in the reference's heap compare).
         const float tau_f = lds_ctl_f32<12>(ctl);
@@ -352,8 +417,8 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
         f2_unpack(s01, s0, s1);
         f2_unpack(s23, s2, s3);
         const float dis = nb + ((s0 + s1) + (s2 + s3));
-        if (HAS_VALID) ok = ok && (vw & vbit);
-        const bool pass = ok && (IP ? dis >= tau_f : dis <= tau_f);
+        bool pass = IP ? dis >= tau_f : dis <= tau_f;
+        if (HAS_VALID) pass = pass && (vw & vbit);
         if (__any_sync(GB_FULL, pass || cnt_now > soft_limit)) {  // rare
           if (__any_sync(GB_FULL, pass)) {
             const u64 key = ((u64)dist_to_key32<IP>(dis) << 32) | seq;
@@ -422,11 +487,11 @@ __device__ __forceinline__ bool v3_pick_victim(const ScanParams &P, const V3Smem
   }
 }
 
-template <bool IP, int THREADS, int MINB, int PER>
+template <bool IP, int THREADS, int MINB, int PER, int RING>
 __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanParams P) {
   constexpr int WARPS = THREADS / 32;
   const int tid = threadIdx.x;
-  const V3Smem S = v3_carve(gb_scan_smem, P.nprobe);
+  const V3Smem S = v3_carve(gb_scan_smem, P.nprobe, P.cap);
   BlockTopR topr;
   topr.buf = S.buf;
   topr.tau = reinterpret_cast<u64 *>(S.misc);
@@ -485,8 +550,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
     if ((tid & 31) == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_first) : "l"(claim0) : "memory");
     mbar_wait(&S.mbar[0], parity);
     parity ^= 1u;
-    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER>(P, S, topr, q, it_first);
-    else scan_loop_m32_v3<IP, false, WARPS, PER>(P, S, topr, q, it_first);
+    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING>(P, S, topr, q, it_first);
+    else scan_loop_m32_v3<IP, false, WARPS, PER, RING>(P, S, topr, q, it_first);
     // ---- survivors of this CTA -> cand[q][row][0..R)
     topr.prune_collective<PER>();
     const int n_out = min(*((volatile int *)topr.cnt), P.R);
@@ -498,33 +563,42 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
 
 // cudaFuncSetAttribute is per device and cheap: called on every launch instead of caching per process (an index may live
 // on any device)
-template <int T, int MINB, int PER>
-static cudaError_t launch_v3_shape(const ScanParams &P, int grid, size_t smem, cudaStream_t st) {
+template <int T, int MINB, int PER, int RING>
+static cudaError_t launch_v3_shape(const ScanParams &P, int grid, cudaStream_t st) {
+  const size_t smem = scan_v3_smem_bytes(P.nprobe, P.cap, T / 32, RING);
   cudaError_t e;
   if (P.is_ip) {
-    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<true, T, MINB, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<true, T, MINB, PER, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ivfpq_scan_m32_v3_kernel<true, T, MINB, PER><<<grid, T, smem, st>>>(P);
+    ivfpq_scan_m32_v3_kernel<true, T, MINB, PER, RING><<<grid, T, smem, st>>>(P);
   } else {
-    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<false, T, MINB, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<false, T, MINB, PER, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ivfpq_scan_m32_v3_kernel<false, T, MINB, PER><<<grid, T, smem, st>>>(P);
+    ivfpq_scan_m32_v3_kernel<false, T, MINB, PER, RING><<<grid, T, smem, st>>>(P);
   }
   return cudaGetLastError();
 }
 
-// shapes: 256 threads x 3 CTAs per SM (candidate buffer <= 1024 keys), 384 / 512 threads x 2 CTAs per SM; the 512-thread
-// shape also serves recall_num > 1536 with a 4096-key buffer (8 keys per thread in the select)
-int scan_v3_ctas_per_sm(int threads) { return threads >= 384 ? 2 : 3; }
+// CTA shapes (threads, CTAs per SM, ring slots per warp): shared memory per CTA = 64 KB table + candidate buffer + probe
+// table + warps x slots x 1280 B, two CTAs per SM:
+//   384 x 2, ring 2 (default): 24 warps per SM, 3 blocks in flight per warp (2 in the ring + 1 in registers)
+//   320 x 2, ring 3: 20 warps per SM, 4 blocks in flight per warp
+//   256 x 2, ring 4: 16 warps per SM, 5 blocks in flight per warp
+//   512 x 1, ring 2: recall_num > 512 (candidate buffers of 2048 / 4096 keys, 4 / 8 keys per thread in the select)
+int scan_v3_ctas_per_sm(int threads, int cap) { return (threads >= 512 || cap > 1024) ? 1 : 2; }
+size_t scan_v3_smem_bytes_for(int nprobe, int cap, int threads) {
+  const int ring = threads == 320 ? 3 : threads == 256 ? 4 : 2;
+  return scan_v3_smem_bytes(nprobe, cap, threads / 32, ring);
+}
 
 cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st) {
-  const size_t smem = scan_v3_smem_bytes(P.nprobe, P.cap);
   if (P.M != 32 || P.nprobe > 2048 || P.cap > 8 * P.m32_threads || (P.cap > 4 * P.m32_threads && P.m32_threads != 512))
     return cudaErrorInvalidValue;
   switch (P.m32_threads) {
-    case 512: return P.cap > 2048 ? launch_v3_shape<512, 2, 8>(P, grid, smem, st) : launch_v3_shape<512, 2, 4>(P, grid, smem, st);
-    case 384: return launch_v3_shape<384, 2, 4>(P, grid, smem, st);
-    default: return launch_v3_shape<256, 3, 4>(P, grid, smem, st);
+    case 512: return P.cap > 2048 ? launch_v3_shape<512, 1, 8, 2>(P, grid, st) : launch_v3_shape<512, 1, 4, 2>(P, grid, st);
+    case 320: return launch_v3_shape<320, 2, 4, 3>(P, grid, st);
+    case 256: return launch_v3_shape<256, 2, 4, 4>(P, grid, st);
+    default: return launch_v3_shape<384, 2, 4, 2>(P, grid, st);
   }
 }
 

@@ -32,6 +32,7 @@ struct ScanParams {
   const long long *list_off;// [nlist] first posting of the list (multiple of 32)
   const int *list_len;      // [nlist]
   const uint32_t *valid;    // validity bitmap or nullptr (everything valid)
+  long long valid_bits;     // docs the bitmap covers; ids beyond it (appended after the search began) are skipped
   u64 *cand;                // [n][S][R] surviving keys (unsorted), GB_KEY_MAX padded
   unsigned long long *scanned;  // += postings walked (may be nullptr)
   unsigned long long *timing;   // optional [8] phase cycle counters (GB200_SCAN_TIMING=1), else nullptr
@@ -54,8 +55,8 @@ struct ScanParams {
 };
 // v3 launchers (ivfpq_scan_v3.cu)
 size_t scan_v3_probe_bytes(int nprobe);
-size_t scan_v3_smem_bytes(int nprobe, int cap);
-int scan_v3_ctas_per_sm(int threads);
+size_t scan_v3_smem_bytes_for(int nprobe, int cap, int threads);
+int scan_v3_ctas_per_sm(int threads, int cap);
 cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st);
 size_t scan_probe_bytes_host(int max_np_s);
@@ -90,6 +91,30 @@ cudaError_t launch_fill_i32(int *p, long long n, int v, cudaStream_t st);
 cudaError_t launch_gather_list(const uint8_t *codes, const int *ids, long long off, int len, int M,
                                int chunk, int layout, uint8_t *out_codes, int *out_ids, cudaStream_t st);
 
+// publish list extents after an append / relocation / compaction (off, then len with release semantics)
+cudaError_t launch_publish_lists(const int *lists, const long long *offs, const int *lens, int n, long long *d_off,
+                                 int *d_len, cudaStream_t st);
+cudaError_t launch_scatter_words(const long long *idx, const uint32_t *val, int n, uint32_t *words, cudaStream_t st);
+// device-side list compaction (one CTA per entry of `lists`, or per list when lists == nullptr)
+struct CompactParams {
+  const int *lists;          // [n_lists] or nullptr = all lists 0..n_lists-1
+  const long long *list_off; // current extents
+  const int *list_len;
+  const uint8_t *codes;      // source pools
+  const int *ids;
+  const float *norms;        // may be nullptr (InnerProduct)
+  const uint32_t *live;      // live-docs bitmap (bit = 1: not deleted) or nullptr
+  long long live_bits;
+  int *new_len;              // pass 0 out: [n_lists] survivors per list
+  const long long *new_off;  // pass 1 in: [n_lists] destination region of each list
+  const int *new_cap;        //            [n_lists] its capacity (ids behind the survivors are set to -1)
+  uint8_t *dst_codes;        // pass 1: destination pools (nullptr = pass 0, count only)
+  int *dst_ids;
+  float *dst_norms;
+  int M, chunk, layout;
+};
+cudaError_t launch_compact_lists(const CompactParams &P, int n_lists, cudaStream_t st);
+
 // K1 — coarse quantiser: dist[n][nlist] = |q|^2 + |c|^2 - 2 q.c (clamped at 0), then top-nprobe
 cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st);
 cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,
@@ -97,11 +122,17 @@ cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const floa
                                cudaStream_t st);
 // tensor-core distance producer (tc_gemm.cu): out[M][ldo] = L2^2 (l2=1) or inner product of a (M x K) vs b (N x K)
 cudaError_t launch_tf32_residual(const float *x, float *small, size_t n, cudaStream_t st);
+// cmin (optional, l2 only): [M][cmin_pitch] minimum of every 32-column chunk of out, cmin_pitch >= tc_gemm_cmin_pitch(N)
 cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_norm, const float *b,
                            const float *b_small, const float *b_norm, int M, int N, int K, float *out, int ldo, int l2,
-                           cudaStream_t st);
+                           float *cmin, int cmin_pitch, cudaStream_t st);
+inline int tc_gemm_cmin_pitch(int N) { return ((N + 127) / 128) * 4; }
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys,
                                  float *coarse_dis, cudaStream_t st);
+// select that starts from the GEMM's chunk minima: reads ~nprobe chunks of the row instead of all of it
+bool coarse_select_cmin_usable(int nlist, int nprobe);
+cudaError_t launch_coarse_select_cmin(const float *dist, const float *cmin, int cmin_pitch, int n, int nlist, int nprobe,
+                                      int *keys, float *coarse_dis, cudaStream_t st);
 
 // K3 — merge the per-split survivors, optional exact re-rank, score window, top-k
 struct RerankParams {
@@ -150,12 +181,12 @@ cudaError_t launch_flat_rescore(const u64 *state, int Kp, const float *xq, const
 cudaError_t launch_select_selftest(const u64 *keys, int n, int R, int cap, int batch, int threads, u64 *out, int *out_n,
                                    cudaStream_t st);
 
-// validity bitmap = NOT deleted AND all range filters
+// validity bitmap = live (NOT deleted) AND all range filters
 struct DevRangeFilter {
   const uint8_t *bitmap;  // device bytes
   int min_doc, max_doc, min_aligned, not_in;
 };
-cudaError_t launch_build_valid(const uint32_t *deleted, long long deleted_bits, const DevRangeFilter *filters,
+cudaError_t launch_build_valid(const uint32_t *live, long long live_bits, const DevRangeFilter *filters,
                                int n_filters, uint32_t *valid, long long nbits, cudaStream_t st);
 
 }  // namespace gb

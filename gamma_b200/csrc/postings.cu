@@ -99,12 +99,13 @@ cudaError_t launch_gather_list(const uint8_t *codes, const int *ids, long long o
   return cudaGetLastError();
 }
 
-// valid[w] = ~deleted[w] & AND_f has_f(doc)   for the 32 docs of word w
-__global__ void build_valid_kernel(const uint32_t *deleted, long long deleted_words, const DevRangeFilter *filters,
+// valid[w] = live[w] & AND_f has_f(doc)   for the 32 docs of word w  (live: bit = 1 <=> the doc is NOT deleted; words the
+// live bitmap does not cover are all ones)
+__global__ void build_valid_kernel(const uint32_t *live, long long live_words, const DevRangeFilter *filters,
                                    int n_filters, uint32_t *valid, long long nwords) {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nwords) return;
-  uint32_t v = (deleted && w < deleted_words) ? ~deleted[w] : 0xffffffffu;
+  uint32_t v = (live && w < live_words) ? live[w] : 0xffffffffu;
   for (int f = 0; f < n_filters && v; f++) {
     DevRangeFilter rf = filters[f];
     uint32_t m = 0;
@@ -124,12 +125,109 @@ __global__ void build_valid_kernel(const uint32_t *deleted, long long deleted_wo
   }
   valid[w] = v;
 }
-cudaError_t launch_build_valid(const uint32_t *deleted, long long deleted_bits, const DevRangeFilter *filters,
+cudaError_t launch_build_valid(const uint32_t *live, long long live_bits, const DevRangeFilter *filters,
                                int n_filters, uint32_t *valid, long long nbits, cudaStream_t st) {
   long long nwords = (nbits + 31) / 32;
   if (nwords <= 0) return cudaSuccess;
-  build_valid_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(deleted, (deleted_bits + 31) / 32, filters,
-                                                                        n_filters, valid, nwords);
+  build_valid_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(live, (live_bits + 31) / 32, filters, n_filters,
+                                                                        valid, nwords);
+  return cudaGetLastError();
+}
+
+// ---- publication of list extents (RealTimeMemData's retrieve_idx_pos_ bump, realtime_mem_data.cc:299-301, and its
+// copy-swap of a grown bucket, :426-474).  Readers (probe setup kernels) load len with acquire semantics and THEN off;
+// the writer stores off and THEN len with release semantics: a reader can pair a new off with an old len (the new
+// region holds everything the old one did) but never an old off with a new len.
+__global__ void publish_lists_kernel(const int *lists, const long long *offs, const int *lens, int n, long long *d_off,
+                                     int *d_len) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = lists[i];
+  d_off[l] = offs[i];
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(d_len + l), "r"(lens[i]) : "memory");
+}
+cudaError_t launch_publish_lists(const int *lists, const long long *offs, const int *lens, int n, long long *d_off,
+                                 int *d_len, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  publish_lists_kernel<<<(n + 255) / 256, 256, 0, st>>>(lists, offs, lens, n, d_off, d_len);
+  return cudaGetLastError();
+}
+
+// words[idx[i]] = val[i]  (touched words of the live-docs bitmap after BitmapManager::Set / Unset)
+__global__ void scatter_words_kernel(const long long *idx, const uint32_t *val, int n, uint32_t *words) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) words[idx[i]] = val[i];
+}
+cudaError_t launch_scatter_words(const long long *idx, const uint32_t *val, int n, uint32_t *words, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  scatter_words_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, val, n, words);
+  return cudaGetLastError();
+}
+
+// ---- compaction of posting lists on the device (RealTimeMemData::CompactBucket / CompactOne,
+// realtime_mem_data.cc:98-112, 354-424): drop postings that were moved away (kDelIdxMask -> negative id here) or whose
+// doc is deleted in the bitmap, keep the order of the survivors.  One CTA per list.
+//   pass 0 (dst_codes == nullptr): new_len[l] = survivors of list l;
+//   pass 1: survivors are written, in order, to the region starting at new_off[l]; ids behind them are set to -1 up to
+//           new_cap[l].  In the rotated layouts a posting's stored bytes depend on its lane (position mod 32), so the
+//           code bytes are re-rotated for the new position.
+__device__ __forceinline__ bool posting_survives(int id, const uint32_t *live, long long live_bits) {
+  if (id < 0) return false;
+  if (live && (long long)id < live_bits) return (live[id >> 5] >> (id & 31)) & 1u;
+  return true;
+}
+__global__ void __launch_bounds__(256) compact_lists_kernel(CompactParams P) {
+  const int l = P.lists ? P.lists[blockIdx.x] : blockIdx.x;
+  const long long off = P.list_off[l];
+  const int len = P.list_len[l];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int warp_cnt[8];
+  __shared__ int run_base;
+  if (tid == 0) run_base = 0;
+  __syncthreads();
+  const int M = P.M;
+  for (int p0 = 0; p0 < len; p0 += 256) {
+    const int pos = p0 + tid;
+    int id = -1;
+    if (pos < len) id = P.ids[off + pos];
+    const bool keep = pos < len && posting_survives(id, P.live, P.live_bits);
+    const unsigned m = __ballot_sync(GB_FULL, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int before = run_base;
+    for (int w = 0; w < warp; w++) before += warp_cnt[w];
+    const int npos = before + __popc(m & ((1u << lane) - 1u));
+    if (keep && P.dst_codes) {
+      const long long noff = P.new_off[blockIdx.x];
+      P.dst_ids[noff + npos] = id;
+      if (P.dst_norms) P.dst_norms[noff + npos] = P.norms[off + pos];
+      const int i = pos & 31, ni = npos & 31;
+      const long long sb = (off + (pos & ~31)) * (long long)M, db = (noff + (npos & ~31)) * (long long)M;
+      for (int s = 0; s < M; s++) {  // destination stored byte s = logical byte (ni + s) % M (rotated) or s (plain)
+        const int logical = P.layout == LAYOUT_PLAIN ? s : (ni + s) % M;
+        const int src_s = P.layout == LAYOUT_PLAIN ? logical : (logical - i + M) % M;
+        P.dst_codes[code_byte_addr(db, ni, s, P.chunk)] = P.codes[code_byte_addr(sb, i, src_s, P.chunk)];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; w++) t += warp_cnt[w];
+      run_base += t;
+    }
+    __syncthreads();
+  }
+  const int nl = run_base;
+  if (!P.dst_codes) {
+    if (tid == 0) P.new_len[blockIdx.x] = nl;
+    return;
+  }
+  const long long noff = P.new_off[blockIdx.x];
+  for (int p = nl + tid; p < P.new_cap[blockIdx.x]; p += 256) P.dst_ids[noff + p] = -1;
+}
+cudaError_t launch_compact_lists(const CompactParams &P, int n_lists, cudaStream_t st) {
+  if (n_lists <= 0) return cudaSuccess;
+  compact_lists_kernel<<<n_lists, 256, 0, st>>>(P);
   return cudaGetLastError();
 }
 

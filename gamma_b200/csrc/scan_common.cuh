@@ -21,6 +21,16 @@ struct ProbeInfo {
   float dis0;
 };
 
+// Extent of one inverted list as the scan may use it: len (retrieve_idx_pos_) is loaded with acquire semantics, off
+// after it.  The writer publishes off first and len with release semantics (publish_lists_kernel), so a new len is
+// never paired with an old off while appends / relocations / compactions run next to searches
+// (RealTimeMemData::ExtendBucketMem's copy-swap, realtime/realtime_mem_data.cc:426-474).
+__device__ __forceinline__ void load_list_extent(const long long *list_off, const int *list_len, int key, long long &off,
+                                                 int &len) {
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(len) : "l"(list_len + key) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(off) : "l"(list_off + key) : "memory");
+}
+
 // ---- mbarrier / TMA bulk-copy wrappers (cp.async.bulk -> UBLKCP in SASS)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {

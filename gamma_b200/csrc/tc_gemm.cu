@@ -88,6 +88,8 @@ struct TcGemmParams {
   float *out;           // [M][ldo]
   int M, N, K, ldo;
   int l2;               // 1: out = an + bn - 2 acc clamped at 0 ; 0: out = acc
+  float *cmin;          // optional (l2 only): [M][cmin_pitch] minimum of every 32-column chunk of out (NaN ignored,
+  int cmin_pitch;       //   columns >= N count as +inf); the coarse select starts from these instead of the full row
 };
 
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
@@ -224,16 +226,35 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
         const int col = tile_n * TC_BN + c0 + lane;
         const float bn = (P.l2 && P.b_norm && col < P.N) ? __ldg(P.b_norm + col) : 0.f;
         float *dst = P.out + (size_t)row0 * P.ldo + col;
+        if (P.cmin) {
+          // same stores, plus the minimum of the 32 columns of every row: L2 distances are clamped at 0, so their bit
+          // patterns order like unsigned integers (NaN sorts above +inf and loses) and one REDUX per row does it
+          uint32_t mine = 0x7f800000u;
 #pragma unroll 8
-        for (int rr = 0; rr < 32; rr++) {
-          const float acc = tr[rr * 33 + lane];
-          const float an = __shfl_sync(0xffffffffu, an_mine, rr);
-          float r = acc;
-          if (P.l2) {
-            r = an + bn - 2.f * acc;
+          for (int rr = 0; rr < 32; rr++) {
+            const float acc = tr[rr * 33 + lane];
+            const float an = __shfl_sync(0xffffffffu, an_mine, rr);
+            float r = an + bn - 2.f * acc;
             r = r < 0.f ? 0.f : r;
+            const bool ok = col < P.N;
+            if (row0 + rr < P.M && ok) dst[(size_t)rr * P.ldo] = r;
+            const uint32_t m = __reduce_min_sync(0xffffffffu, ok ? __float_as_uint(r) : 0x7f800000u);
+            if (lane == rr) mine = m;
           }
-          if (row0 + rr < P.M && col < P.N) dst[(size_t)rr * P.ldo] = r;
+          if (row0 + lane < P.M)
+            P.cmin[(size_t)(row0 + lane) * P.cmin_pitch + ((tile_n * TC_BN + c0) >> 5)] = __uint_as_float(mine);
+        } else {
+#pragma unroll 8
+          for (int rr = 0; rr < 32; rr++) {
+            const float acc = tr[rr * 33 + lane];
+            const float an = __shfl_sync(0xffffffffu, an_mine, rr);
+            float r = acc;
+            if (P.l2) {
+              r = an + bn - 2.f * acc;
+              r = r < 0.f ? 0.f : r;
+            }
+            if (row0 + rr < P.M && col < P.N) dst[(size_t)rr * P.ldo] = r;
+          }
         }
         __syncwarp();
       }
@@ -301,7 +322,7 @@ static bool make_map(CUtensorMap *m, const float *ptr, int rows, int K) {
 // K % 4 == 0 and 16-byte aligned bases are required by the tensor maps.
 cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_norm, const float *b,
                            const float *b_small, const float *b_norm, int M, int N, int K, float *out, int ldo, int l2,
-                           cudaStream_t st) {
+                           float *cmin, int cmin_pitch, cudaStream_t st) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if ((K & 3) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)a_small & 15) || ((uintptr_t)b_small & 15))
     return cudaErrorInvalidValue;
@@ -311,12 +332,11 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
     return cudaErrorNotSupported;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * sizeof(uint64_t) + 16 +
                       TC_EPI_WARPS * 32 * 33 * sizeof(float) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (an index may live on any device)
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
+  if (cmin && (!l2 || cmin_pitch < ((N + TC_BN - 1) / TC_BN) * (TC_BN / 32))) return cudaErrorInvalidValue;
   TcGemmParams P;
   P.a_norm = a_norm;
   P.b_norm = b_norm;
@@ -326,6 +346,8 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
   P.K = K;
   P.ldo = ldo;
   P.l2 = l2;
+  P.cmin = cmin;
+  P.cmin_pitch = cmin_pitch;
   const int num_tiles = ((N + TC_BN - 1) / TC_BN) * ((M + TC_BM - 1) / TC_BM);
   int sms = 148;
   {

@@ -109,6 +109,13 @@ int gb200_ivfpq_list_sizes(gb200_index *ix, int64_t *sizes /* nlist */);
  * test hook mirroring RealTimeMemData::RetrieveCodes (realtime_mem_data.h:95-96).      */
 int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t *codes);
 
+/* RealTimeMemData::CompactIfNeed / CompactBucket (realtime/realtime_mem_data.cc:354-424) on the device: drop the
+ * postings that were moved away (kDelIdxMask) or whose doc is deleted in the bitmap, keep the survivors' order.
+ * list_no >= 0: that list only — it is rewritten into a fresh region and swapped in by publication, searches keep
+ * running; list_no == -1: every list, into a new tightly packed pool (also returns the regions abandoned by list
+ * growth; searches are drained for the swap).  *dropped (may be NULL) = postings removed.                          */
+int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped);
+
 /* ---- raw vectors: the read side of VectorReader::Gets / RawVector::GetVectorHeader
  * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are
  * implicit = first_vid .. first_vid+n-1; re-upload of an existing range = UpdateToStore. */
@@ -120,9 +127,17 @@ int64_t gb200_raw_count(gb200_index *ix);
 /* ---- deleted-docs bitmap: bitmap::BitmapManager::Set/Unset (util/bitmap_manager.cc),
  * bit = 1 => deleted; consulted by GammaSearchCondition::IsValid (:99-108).            */
 int gb200_set_deleted(gb200_index *ix, const int64_t *docids, int64_t n, int deleted);
+/* bring the device copy in line with the whole reference bitmap (bit = 1: deleted).  Only words that differ from the
+ * library's shadow copy travel, so a model may call this before every Search: the reference tests the bitmap live and
+ * some engine paths set bits without RetrievalModel::Delete (search/gamma_engine.cc:866).                           */
 int gb200_upload_deleted_bitmap(gb200_index *ix, const uint8_t *bitmap, int64_t nbits);
 
 /* ---- search: RetrievalModel::Search (retrieval_model.h:282-284).
+ * THREADING: every entry point may be called concurrently from any number of threads (the engine's request threads
+ * all call Search on one model, gamma_engine.cc:74-97, tests/test.h:1033-1062).  Each Search call runs on its own
+ * stream and workspaces (up to GB200_MAX_CONTEXTS calls in flight per index, further callers wait for a free one);
+ * appends / updates / deletes / raw uploads are serialised among themselves and do not block searches except for
+ * the moment a device array has to be re-allocated.  A search sees a list either before or after an append.
  * GammaIVFPQIndex::Search (gamma_index_ivfpq.cc:514-566): coarse quantizer, ADC scan of
  * the nprobe lists with the validity filter inside the scan, recall_num selection,
  * optional exact re-rank, score window, top-k.  xq: n x d f32; out: n x k.             */
