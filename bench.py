@@ -285,8 +285,16 @@ def build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele):
     return r
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_reference(r, w, xq, filters, n_queries, reps, warm=1):
     from oracle import ref
+    ref.set_threads(host_cores())
     cores = ref.max_threads()
     rj = json.dumps({"nprobe": w["nprobe"], "recall_num": RECALL_NUM, "metric_type": "L2", "parallel_on_queries": 1})
     q = xq[:n_queries]
@@ -348,6 +356,9 @@ def main():
         nq = min(args.cpu_queries, n)
         qps_list = []
         from oracle import ref
+        # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the reference engine gets every core this
+        # process may run on, whatever the launcher put in the environment
+        ref.set_threads(host_cores())
         cores = ref.max_threads()
         rj = json.dumps({"nprobe": w["nprobe"], "recall_num": RECALL_NUM, "metric_type": "L2", "parallel_on_queries": 1})
         for it in range(args.warmup + args.steps):
@@ -528,11 +539,26 @@ def main():
     sp = api._Base._sp("L2", w["nprobe"], RECALL_NUM, True, -api.FLT_MAX, api.FLT_MAX)
     farr, fkeep = api.make_filters(filters)
 
+    if world > 1:
+        out_all_pin = torch.empty(world * out_bytes, dtype=torch.uint8).pin_memory()
+        xq_stage = torch.empty_like(xq_d)
+
     def step_host():
-        rc_ = api.lib().gb200_ivfpq_search(ix.h, n, xq_pin.data_ptr(), K_TOP, ctypes.byref(sp),
-                                           ctypes.cast(farr, ctypes.c_void_p), len(filters), D_pin.data_ptr(),
-                                           I_pin.data_ptr())
+        if world == 1:
+            rc_ = api.lib().gb200_ivfpq_search(ix.h, n, xq_pin.data_ptr(), K_TOP, ctypes.byref(sp),
+                                               ctypes.cast(farr, ctypes.c_void_p), len(filters), D_pin.data_ptr(),
+                                               I_pin.data_ptr())
+            assert rc_ == 0, api.lib().gb200_last_error()
+            return
+        # N > 1: the whole query-sharded path — H2D of this rank's queries, search, the all-gather of every rank's top-k
+        # over NVLink, D2H of the gathered result — so that e2e contains the exchange
+        xq_stage.copy_(xq_pin, non_blocking=True)
+        rc_ = ix.search_dev(xq_stage.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
+                            nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
         assert rc_ == 0, api.lib().gb200_last_error()
+        dist.all_gather_into_tensor(out_all, out_d)
+        out_all_pin.copy_(out_all, non_blocking=True)
+        stream.synchronize()
 
     for _ in range(args.warmup):
         step_host()
@@ -546,7 +572,11 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = world * n * args.steps / float(te.item())
-    assert np.array_equal(I_pin.numpy(), I_ours), "host-API result differs from device-API result"
+    if world == 1:
+        assert np.array_equal(I_pin.numpy(), I_ours), "host-API result differs from device-API result"
+    else:
+        mine = out_all_pin[rank * out_bytes:(rank + 1) * out_bytes][n * K_TOP * 4:].view(torch.int64).numpy().reshape(n, K_TOP)
+        assert np.array_equal(mine, I_ours), "gathered result of this rank differs from its device-API result"
 
     if rank != 0:
         if world > 1:
@@ -600,7 +630,10 @@ def main():
                            ms_per_step_back_to_back_no_flush=ms_noflush, scaled_down=args.scale != 1.0),
                roofline=roofline, cpu_baseline=cpu,
                e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * w["d"] * 4),
-                        d2h_bytes_per_step=int(n * K_TOP * 12)),
+                        d2h_bytes_per_step=int(n * K_TOP * 12 * (world if world > 1 else 1)),
+                        path=("gb200_ivfpq_search (host C-ABI, pinned host buffers)" if world == 1 else
+                              "per rank: H2D queries, gb200_ivfpq_search_dev, NCCL all-gather of the packed top-k, D2H of "
+                              "the gathered result")),
                gpu_launches=int(launches), clocks=clocks, recall_at_10=rec_ours)
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.gb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.gb200_reload_tuning.argtypes = [C.c_void_p]
         L.gb200_ivfpq_compact.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.gb200_ivfpq_replace_list.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
@@ -265,6 +266,12 @@ class B200IVFPQ(_Base):
     def update(self, vid, new_list, code):
         c = np.ascontiguousarray(code, dtype=np.uint8)
         return lib().gb200_ivfpq_update(self.h, int(vid), int(new_list), c.ctypes.data)
+
+    def replace_list(self, list_no, ids, codes):
+        """device copy of one list := the given reference-layout content (ids with kDelIdxMask in bit 63, AoS codes)"""
+        i = np.ascontiguousarray(ids, dtype=np.int64)
+        c = np.ascontiguousarray(codes, dtype=np.uint8)
+        return lib().gb200_ivfpq_replace_list(self.h, int(list_no), int(i.size), i.ctypes.data, c.ctypes.data)
 
     def compact(self, list_no=-1):
         """RealTimeMemData::CompactBucket on the device; returns the number of postings dropped."""

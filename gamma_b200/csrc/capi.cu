@@ -96,12 +96,14 @@ struct Tuning {
   int ch_blocks = 8;      // GB200_SCAN_CH: blocks per item (v3)
   int help_min = 8;       // GB200_SCAN_HELP_MIN: idle CTAs join a query that has >= this many unclaimed items (v3)
   int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
+  int v3_tma = 0;         // GB200_SCAN_TMA: v3 posting ring fed by bulk copies (1) or per-lane cp.async (0)
   int splits = 0;         // GB200_SCAN_SPLITS: v2 / M = 64 / generic: CTAs per query, 0 = automatic
   int tail = 0;           // GB200_SCAN_TAIL: v2 plan: splits of the last partial wave, 0 = automatic
   int no_plan = 0;        // GB200_SCAN_NOPLAN: v2 without the positional work plan
   int steal = 0;          // GB200_SCAN_STEAL: v2, 256 threads: intra-CTA work stealing
   int scan_timing = 0;    // GB200_SCAN_TIMING: per-phase cycle counters of the v2 kernel on stderr
   int coarse_simt = 0;    // GB200_COARSE=simt: CUDA-core fp32 coarse distances instead of the tcgen05 GEMM
+  int coarse_full_select = 0;  // GB200_COARSE_FULL_SELECT=1: select over whole rows instead of starting from chunk minima
   int lut_inline = 0;     // GB200_LUT_INLINE: build the tables on the main stream
   int flat_mode = 0;      // GB200_FLAT: 0 automatic, 1 = exact (per-query scan), 2 = tc (tensor-core path for any batch)
   int max_contexts = 8;   // GB200_MAX_CONTEXTS: Search calls in flight per index (each owns streams + workspaces)
@@ -111,10 +113,13 @@ struct Tuning {
     auto geti = [](const char *k, int d) { const char *e = getenv(k); return e && *e ? atoi(e) : d; };
     scan_variant = geti("GB200_SCAN_VARIANT", scan_variant);
     scan_threads = geti("GB200_SCAN_THREADS", scan_threads);
-    if (scan_threads != 256 && scan_threads != 320 && scan_threads != 384 && scan_threads != 512) scan_threads = 0;
+    if (scan_threads != 256 && scan_threads != 320 && scan_threads != 384 && scan_threads != 416 && scan_threads != 448 &&
+        scan_threads != 512)
+      scan_threads = 0;
     pf_blocks = std::max(0, geti("GB200_SCAN_PF", pf_blocks));
     ch_blocks = std::max(1, geti("GB200_SCAN_CH", ch_blocks));
     help_min = std::max(1, geti("GB200_SCAN_HELP_MIN", help_min));
+    v3_tma = geti("GB200_SCAN_TMA", v3_tma);
     max_rows = std::max(0, geti("GB200_SCAN_ROWS", 0));
     splits = std::max(0, geti("GB200_SCAN_SPLITS", 0));
     tail = std::max(0, geti("GB200_SCAN_TAIL", 0));
@@ -122,6 +127,7 @@ struct Tuning {
     steal = geti("GB200_SCAN_STEAL", 0);
     scan_timing = geti("GB200_SCAN_TIMING", 0);
     lut_inline = geti("GB200_LUT_INLINE", 0);
+    coarse_full_select = geti("GB200_COARSE_FULL_SELECT", 0);
     max_contexts = std::max(1, std::min(64, geti("GB200_MAX_CONTEXTS", max_contexts)));
     if (const char *e = getenv("GB200_COARSE")) coarse_simt = !strcmp(e, "simt");
     if (const char *e = getenv("GB200_FLAT")) flat_mode = !strcmp(e, "exact") ? 1 : !strcmp(e, "tc") ? 2 : 0;
@@ -137,7 +143,7 @@ struct SearchCtx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_user = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4, 5 bracket the scan kernel alone
   DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_flat, ws_lut, ws_xs, ws_fstate, ws_probe,
-      ws_ctl;
+      ws_ctl, ws_cmin;
   DevBuf valid_filt, filt_bytes, filt_desc;  // per-call range filters -> validity bitmap
   unsigned long long *d_scanned = nullptr;
   unsigned long long *d_timing = nullptr;
@@ -159,7 +165,7 @@ struct SearchCtx {
   void destroy() {
     if (stream) cudaStreamSynchronize(stream);
     DevBuf *bufs[] = {&ws_xq,  &ws_xn, &ws_dist,   &ws_keys,  &ws_cdis, &ws_cand,    &ws_out_d,   &ws_out_i, &ws_flat,
-                      &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc};
+                      &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc, &ws_cmin};
     for (DevBuf *b : bufs) b->release();
     if (d_scanned) cudaFree(d_scanned);
     if (d_timing) cudaFree(d_timing);
@@ -212,6 +218,7 @@ struct gb200_index {
   int *d_len = nullptr;
   std::vector<long long> vid_loc;
   std::atomic<long long> max_vid{-1};
+  std::atomic<int> max_list_len{0};  // longest list ever published (upper bound; sizes the scan's per-query item table)
 
   float *d_raw = nullptr;
   long long raw_cap = 0;
@@ -667,6 +674,11 @@ static int append_locked(gb200_index *ix, int64_t n, const int32_t *list_no, con
   }
   ix->h_len = run;
   ix->max_vid = mv;
+  {
+    int mx = ix->max_list_len.load();
+    for (int l : touched) mx = std::max(mx, ix->h_len[l]);
+    ix->max_list_len = mx;
+  }
   // publish: the scan sees a new length only after the data (and a moved list's new region) are in place
   return publish_lists(ix, touched);
 }
@@ -872,6 +884,84 @@ int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped) {
   CK(cudaMemcpyAsync(ix->d_len, ix->h_len.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, ix->wstream));
   CK(cudaStreamSynchronize(ix->wstream));
   return GB200_OK;
+}
+
+int gb200_ivfpq_replace_list(gb200_index *ix, int32_t list_no, int64_t n, const int64_t *ids, const uint8_t *codes) {
+  if (!ix || ix->kind != 0 || list_no < 0 || list_no >= ix->p.nlist || n < 0 || (n > 0 && (!ids || !codes)))
+    return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n > (1LL << GB_SEQ_POS_BITS)) return GB200_EUNSUPPORTED;
+  std::lock_guard<std::mutex> w(ix->writer_mu);
+  CKI(use_device(ix));
+  const int M = ix->p.nsubvector, l = list_no;
+  long long mv = ix->max_vid.load();
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t v = ids[i] & 0x7fffffffffffffffLL;
+    if (v > 0x7ffffffeLL) {
+      set_err("replace_list: posting %lld has vid %lld out of range", (long long)i, (long long)v);
+      return GB200_EINVAL;
+    }
+    if (ids[i] >= 0 && v > mv) mv = v;
+  }
+  // vids that live in the old content lose their location
+  const int old_len = ix->h_len[l];
+  if (old_len > 0) {
+    std::vector<int> old(old_len);
+    std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+    CK(cudaMemcpyAsync(old.data(), ix->d_ids + ix->h_off[l], (size_t)old_len * sizeof(int), cudaMemcpyDeviceToHost, ix->wstream));
+    CK(cudaStreamSynchronize(ix->wstream));
+    for (int p = 0; p < old_len; p++)
+      if (old[p] >= 0 && (size_t)old[p] < ix->vid_loc.size() && ix->vid_loc[old[p]] == (((long long)l << 32) | (unsigned)p))
+        ix->vid_loc[old[p]] = -1;
+  }
+  const long long new_cap = roundup32(std::max<long long>(n + n / 8 + 1, 32));
+  const long long off = ix->pool_used, tail = off + new_cap;
+  if (tail > ix->pool_cap) {
+    ExclusiveScope x(ix);
+    CKI(pool_reserve_exclusive(ix, tail));
+  }
+  CKI(bitmaps_follow_growth(ix, std::max(mv + 1, ix->doc_bits())));
+  std::shared_lock<std::shared_mutex> shared(ix->data_mu);
+  CK(launch_fill_i32(ix->d_ids + off, new_cap, -1, ix->wstream));
+  ix->launches++;
+  // the writer's offsets table sees the new region now, the published one after the data is in place
+  CK(cudaMemcpyAsync(ix->d_woff + l, &off, sizeof(long long), cudaMemcpyHostToDevice, ix->wstream));
+  CK(cudaStreamSynchronize(ix->wstream));  // &off is a stack address
+  if (n > 0) {
+    std::vector<int> lno((size_t)n, l), pos((size_t)n), vid32((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+      const int v = (int)(ids[i] & 0x7fffffffLL);
+      pos[i] = (int)i;
+      if (ids[i] < 0) {  // kDelIdxMask: the slot stays, dead
+        vid32[i] = (int)((unsigned)v | 0x80000000u);
+        continue;
+      }
+      vid32[i] = v;
+      if ((size_t)v >= ix->vid_loc.size()) ix->vid_loc.resize(std::max<size_t>((size_t)v + 1, ix->vid_loc.size() * 2), -1);
+      const long long prev = ix->vid_loc[v];
+      if (prev >= 0 && (int)(prev >> 32) != l) {  // still alive in another list on the device: a vid lives in one place
+        const int dead = (int)((unsigned)v | 0x80000000u);
+        CK(cudaMemcpyAsync(ix->d_ids + ix->h_off[(int)(prev >> 32)] + (int)(prev & 0xffffffff), &dead, sizeof(int),
+                           cudaMemcpyHostToDevice, ix->wstream));
+        CK(cudaStreamSynchronize(ix->wstream));
+      }
+      ix->vid_loc[v] = ((long long)l << 32) | (unsigned)i;
+    }
+    const int64_t SLAB = 1 << 22;
+    for (int64_t s0 = 0; s0 < n; s0 += SLAB) {
+      const int64_t m = std::min(SLAB, n - s0);
+      CKI(write_postings(ix, m, lno.data() + s0, pos.data() + s0, vid32.data() + s0, codes + (size_t)s0 * M));
+      CK(cudaStreamSynchronize(ix->wstream));
+    }
+  }
+  ix->pool_live_cap += new_cap - ix->h_cap[l];
+  ix->h_off[l] = off;
+  ix->h_cap[l] = (int)new_cap;
+  ix->h_len[l] = (int)n;
+  ix->pool_used = tail;
+  ix->max_vid = mv;
+  ix->max_list_len = std::max(ix->max_list_len.load(), (int)n);
+  return publish_lists(ix, std::vector<int>(1, l));
 }
 
 // ---- raw vectors -----------------------------------------------------------------------
@@ -1152,18 +1242,27 @@ static int coarse_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, i
   long long rows = std::max<long long>(1, (1LL << 28) / nlist);
   if (rows > n) rows = n;
   CKI(c.ws_dist.ensure((size_t)rows * nlist * sizeof(float)));
+  // the GEMM epilogue also emits the minimum of every 32-centroid chunk; the select then reads ~nprobe chunks of a row
+  // instead of all nlist distances (coarse.cu coarse_select_cmin_kernel)
+  const bool use_cmin = use_tc && !ix->tune.coarse_full_select && coarse_select_cmin_usable(nlist, nprobe);
+  const int cmin_pitch = tc_gemm_cmin_pitch(nlist);
+  if (use_cmin) CKI(c.ws_cmin.ensure((size_t)rows * cmin_pitch * sizeof(float)));
   for (long long r0 = 0; r0 < n; r0 += rows) {
     int m = (int)std::min<long long>(rows, n - r0);
     if (use_tc) {
       CK(launch_tc_gemm(d_xq + (size_t)r0 * d, c.ws_xs.as<float>() + (size_t)r0 * d, c.ws_xn.as<float>() + r0,
                         ix->d_cent, ix->d_cent_small, ix->d_cent_norm, m, nlist, d, c.ws_dist.as<float>(), nlist, 1,
-                        c.stream));
+                        use_cmin ? c.ws_cmin.as<float>() : nullptr, cmin_pitch, c.stream));
     } else {
       CK(launch_coarse_dist(d_xq + (size_t)r0 * d, c.ws_xn.as<float>() + r0, ix->d_cent, ix->d_cent_norm, m, nlist, d,
                             c.ws_dist.as<float>(), c.stream));
     }
-    CK(launch_coarse_select(c.ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
-                            d_cdis + (size_t)r0 * nprobe, c.stream));
+    if (use_cmin)
+      CK(launch_coarse_select_cmin(c.ws_dist.as<float>(), c.ws_cmin.as<float>(), cmin_pitch, m, nlist, nprobe,
+                                   d_keys + (size_t)r0 * nprobe, d_cdis + (size_t)r0 * nprobe, c.stream));
+    else
+      CK(launch_coarse_select(c.ws_dist.as<float>(), m, nlist, nprobe, d_keys + (size_t)r0 * nprobe,
+                              d_cdis + (size_t)r0 * nprobe, c.stream));
     c.launches += 2;
   }
   c.launches += 1;
@@ -1286,8 +1385,15 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     S = std::max(1, std::min(S, 16));
     while (S > 1 && (long long)S * R > 8192) S--;
     grid_v3 = (int)std::min<long long>(slots, (long long)n * S);
-    P.ch_blocks = T.ch_blocks;
+    // per-query item table (item -> list, blocks): nprobe x items of the longest list bounds it; coarser items when a
+    // few huge lists would make it large (items beyond the table are still found, by search)
+    int ch = T.ch_blocks;
+    const long long max_blocks = std::max(1, (ix->max_list_len.load() + 31) / 32);
+    while ((long long)nprobe * ((max_blocks + ch - 1) / ch) > 512 && ch < 32768) ch *= 2;
+    P.v3_max_items = (int)std::min<long long>(512, std::max<long long>(2, (long long)nprobe * ((max_blocks + ch - 1) / ch)));
+    P.ch_blocks = ch;
     P.help_min = T.help_min;
+    P.v3_tma = T.v3_tma;
     P.help_window = std::min(n, 4 * slots);
     P.max_np_s = nprobe;
   } else {
@@ -1321,7 +1427,7 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     CK(cudaMemsetAsync(c.d_timing, 0, 8 * sizeof(unsigned long long), c.stream));
     P.timing = c.d_timing;
   }
-  const size_t smem_need = variant == 3 ? scan_v3_smem_bytes_for(nprobe, cap, threads) : scan_smem_bytes(P, ix->mode);
+  const size_t smem_need = variant == 3 ? scan_v3_smem_bytes_for(nprobe, P.v3_max_items, cap, threads) : scan_smem_bytes(P, ix->mode);
   if (smem_need > 227 * 1024) {
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d nprobe=%d): not implemented", smem_need, M, R, nprobe);
     return GB200_EUNSUPPORTED;
@@ -1352,7 +1458,7 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
       P.v3_claim = c.ws_ctl.as<int>() + 4;
       P.v3_rows = c.ws_ctl.as<int>() + 4 + n;
       d_rows = P.v3_rows;
-      CKI(c.ws_probe.ensure((size_t)n * scan_v3_probe_bytes(nprobe)));
+      CKI(c.ws_probe.ensure((size_t)n * scan_v3_probe_bytes(nprobe, P.v3_max_items)));
       P.probe_g = c.ws_probe.as<unsigned char>();
       CK(launch_probe_setup_v3(P, c.stream));
       c.launches++;
@@ -1658,7 +1764,7 @@ static int flat_tc_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, 
     const int nc = (int)std::min<long long>(nc_max, N - c0);
     CK(launch_tc_gemm(d_xq, c.ws_xs.as<float>(), c.ws_xn.as<float>(), ix->d_raw + (size_t)c0 * d,
                       ix->d_raw_small + (size_t)c0 * d, ix->d_raw_norm + c0, n, nc, d, c.ws_dist.as<float>(),
-                      (int)nc_max, ip ? 0 : 1, c.stream));
+                      (int)nc_max, ip ? 0 : 1, nullptr, 0, c.stream));
     CK(launch_flat_chunk_select(c.ws_dist.as<float>(), (int)nc_max, nc, c0, d_valid, lo, hi, Kp, first,
                                 c.ws_fstate.as<u64>(), n, ip ? 1 : 0, c.stream));
     c.launches += 2;

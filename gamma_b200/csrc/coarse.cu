@@ -378,6 +378,143 @@ __global__ void __launch_bounds__(CW_THREADS, 2) coarse_select_reg_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Select that starts from the GEMM's chunk minima (tc_gemm.cu epilogue: cmin[q][c] = min of dist[q][32c .. 32c+31]).
+//   1. 128 threads fold the row's chunk minima into 128 group minima (consecutive chunks per thread);
+//   2. tau = the nprobe-th smallest group minimum: nprobe distinct groups hold an element <= tau, so the nprobe-th
+//      smallest distance of the row is <= tau;
+//   3. only chunks whose minimum is <= tau can hold a survivor (about nprobe .. 2 nprobe of them): their 32 distances
+//      are read (128 B per chunk, coalesced), survivors <= tau are ranked by counting — ascending distance, ties by
+//      centroid id, as every other select here.
+// The row itself is touched for ~nprobe x 128 B instead of nlist x 4 B (64 KB at nlist = 16384).  Rows the bound cannot
+// handle (fewer than nprobe finite group minima, thousands of equal distances) fall back to a bisection over the key
+// space on the full row: slow, rare, exact.
+// ---------------------------------------------------------------------------------------------
+constexpr int CM_THREADS = 128;
+constexpr int CM_CAP = 1024;     // survivors
+constexpr int CM_CHUNKS = 512;   // candidate chunks
+
+__global__ void __launch_bounds__(CM_THREADS) coarse_select_cmin_kernel(const float *__restrict__ dist,
+                                                                        const float *__restrict__ cmin, int cmin_pitch,
+                                                                        int nlist, int nprobe, int *__restrict__ keys,
+                                                                        float *__restrict__ coarse_dis) {
+  __shared__ u64 cand[CM_CAP];
+  __shared__ int chunk_list[CM_CHUNKS];
+  __shared__ float gm_s[CM_THREADS];
+  __shared__ float s_tauf;
+  __shared__ int s_cnt, s_nch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x;
+  const float *row = dist + (size_t)q * nlist;
+  const float *cm = cmin + (size_t)q * cmin_pitch;
+  const float INF = __int_as_float(0x7f800000);
+  // chunks per thread, a multiple of 4 so that a thread's share is whole float4s (cmin_pitch is a multiple of 4)
+  const int E = (((cmin_pitch + CM_THREADS - 1) / CM_THREADS) + 3) & ~3;
+  const int c_lo = tid * E, c_hi = min(c_lo + E, cmin_pitch);
+  float gm = INF;
+  for (int c = c_lo; c < c_hi; c += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(cm + c));
+    gm = fminf(gm, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));  // fminf drops NaN (a chunk of nothing but NaN)
+  }
+  gm = gm < INF ? gm : INF;
+  gm_s[tid] = gm;
+  if (tid == 0) {
+    s_tauf = INF;
+    s_cnt = 0;
+    s_nch = 0;
+  }
+  __syncthreads();
+  {
+    int r = 0;
+    for (int j = 0; j < CM_THREADS; j++) {
+      const float o = gm_s[j];
+      r += (o < gm) || (o == gm && j < tid);
+    }
+    if (r == nprobe - 1 && gm < INF) s_tauf = gm;
+  }
+  __syncthreads();
+  const float tauf = s_tauf;
+  bool slow = !(tauf < INF);
+  if (!slow) {
+    for (int c = c_lo; c < c_hi; c++) {
+      if (cm[c] <= tauf) {
+        const int slot = atomicAdd(&s_nch, 1);
+        if (slot < CM_CHUNKS) chunk_list[slot] = c;
+      }
+    }
+    __syncthreads();
+    const int nch = s_nch;
+    if (nch > CM_CHUNKS) {
+      slow = true;
+    } else {
+      for (int i = warp; i < nch; i += CM_THREADS / 32) {
+        const int c = chunk_list[i] * 32 + lane;
+        const float x = c < nlist ? __ldg(row + c) : INF;
+        const bool pass = x <= tauf;
+        const unsigned m = __ballot_sync(GB_FULL, pass);
+        if (m) {
+          int base = 0;
+          const int leader = __ffs(m) - 1;
+          if (lane == leader) base = atomicAdd(&s_cnt, __popc(m));
+          base = __shfl_sync(GB_FULL, base, leader);
+          const int slot = base + __popc(m & ((1u << lane) - 1u));
+          if (pass && slot < CM_CAP) cand[slot] = ((u64)float_to_ordered(x) << 32) | (uint32_t)c;
+        }
+      }
+      __syncthreads();
+      if (s_cnt > CM_CAP) slow = true;
+    }
+  }
+  int cnt = s_cnt;
+  if (slow) {  // bisection on the key space over the full row
+    u64 lo_b = 0, hi_b = ((u64)float_to_ordered(tauf) << 32) | 0xffffffffu, tau = hi_b;
+    for (int attempt = 0; attempt < 132; attempt++) {
+      __syncthreads();
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int c = tid; c < nlist; c += CM_THREADS) {
+        const u64 key = cw_key(row[c], c);
+        if (key != GB_KEY_MAX && key <= tau) {
+          const int slot = atomicAdd(&s_cnt, 1);
+          if (slot < CM_CAP) cand[slot] = key;
+        }
+      }
+      __syncthreads();
+      cnt = s_cnt;
+      if (cnt <= CM_CAP && (cnt >= nprobe || attempt == 0)) break;  // attempt 0 sees everything at or below tau0
+      if (cnt > CM_CAP) hi_b = tau;
+      else lo_b = tau + 1;
+      tau = lo_b + (hi_b - lo_b) / 2;
+    }
+  }
+  const int c = min(cnt, CM_CAP);
+  for (int i = tid; i < c; i += CM_THREADS) {  // rank by counting; survivors are unique keys
+    const u64 k = cand[i];
+    int r = 0;
+    for (int j = 0; j < c; j++) r += cand[j] < k;
+    if (r < nprobe) {
+      keys[(size_t)q * nprobe + r] = (int)(uint32_t)k;
+      coarse_dis[(size_t)q * nprobe + r] = ordered_to_float((uint32_t)(k >> 32));
+    }
+  }
+  for (int r = c + tid; r < nprobe; r += CM_THREADS) {  // "not enough centroids": key -1
+    keys[(size_t)q * nprobe + r] = -1;
+    coarse_dis[(size_t)q * nprobe + r] = 3.402823466e38f;
+  }
+}
+
+// at least one chunk per group and the bound needs nprobe <= groups
+bool coarse_select_cmin_usable(int nlist, int nprobe) {
+  return nprobe <= CM_THREADS && nprobe >= 1 && (nlist + 31) / 32 >= CM_THREADS && nlist >= nprobe;
+}
+
+cudaError_t launch_coarse_select_cmin(const float *dist, const float *cmin, int cmin_pitch, int n, int nlist, int nprobe,
+                                      int *keys, float *coarse_dis, cudaStream_t st) {
+  if (!coarse_select_cmin_usable(nlist, nprobe) || (cmin_pitch & 3)) return cudaErrorInvalidValue;
+  coarse_select_cmin_kernel<<<n, CM_THREADS, 0, st>>>(dist, cmin, cmin_pitch, nlist, nprobe, keys, coarse_dis);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys, float *coarse_dis,
                                  cudaStream_t st) {
   if (nprobe <= 128 && !getenv("GB200_COARSE_SELECT_CTA")) {

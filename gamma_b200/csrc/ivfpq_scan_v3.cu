@@ -30,39 +30,49 @@ namespace gb {
 // shared-memory carve-up (host mirrors it in scan_v3_smem_bytes).  Everything the hot loop touches sits at a
 // COMPILE-TIME shared-window address (table at GB_SMEM_RESERVED, control words right behind it), so those accesses need
 // no address registers; only the candidate buffer and the item prefix depend on run-time sizes.
-//   [lut 64 KB][misc 96 ints][mbar 16 B][ProbeInfo x nprobe][item prefix x (nprobe + 1), padded to 16][buf u64 cap]
+//   [lut 64 KB][misc 96 ints][mbar 16 B][ring mbarriers 512 B][ProbeInfo x nprobe][item prefix x (nprobe + 1), padded to 16][buf u64 cap]
 //   [posting ring: warps x RING slots x 1280 B]
 // misc: [0..1] tau, [2] cnt, [3] tau_f, [4..67] scratch, [68..70] round flags, [72] q, [73] row
 constexpr int V3_MISC_OFF = 65536;
 constexpr int V3_MBAR_OFF = V3_MISC_OFF + 96 * 4;
-constexpr int V3_PINFO_OFF = V3_MBAR_OFF + 16;
+constexpr int V3_RBAR_OFF = V3_MBAR_OFF + 16;          // ring-slot mbarriers (TMA-fed ring): 16 warps x 4 slots
+constexpr int V3_PINFO_OFF = V3_RBAR_OFF + 16 * 4 * 8;
 constexpr int V3_SLOT_BYTES = 1280;  // one 32-posting block in the ring: codes 1024 B, ids 128 B, t(p) 128 B
 struct V3Smem {
   unsigned char *ring;
   u64 *buf;
   ProbeInfo *pinfo;
   int *item_prefix;
+  uint2 *itab;
   int *misc;
   unsigned long long *mbar;
+  unsigned long long *rbar;  // [warp][RING] one mbarrier per ring slot (TMA-fed ring)
 };
 
-__host__ __device__ inline size_t v3_probe_bytes(int nprobe) {
+// per-query probe block: [ProbeInfo x nprobe][item prefix x (nprobe + 1)], padded to 16 B, then the ITEM TABLE
+// [max_items x {first pool block, blocks << 16 | probe}] (8 B per item, item ids in claim order)
+__host__ __device__ inline size_t v3_itab_off(int nprobe) {
   size_t b = (size_t)nprobe * sizeof(ProbeInfo) + (size_t)(nprobe + 1) * sizeof(int);
   return (b + 15) & ~(size_t)15;
 }
-size_t scan_v3_probe_bytes(int nprobe) { return v3_probe_bytes(nprobe); }
-size_t scan_v3_smem_bytes(int nprobe, int cap, int warps, int ring) {
-  return V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64) + (size_t)warps * ring * V3_SLOT_BYTES;
+__host__ __device__ inline size_t v3_probe_bytes(int nprobe, int max_items) {
+  return v3_itab_off(nprobe) + (((size_t)max_items * 8 + 15) & ~(size_t)15);
+}
+size_t scan_v3_probe_bytes(int nprobe, int max_items) { return v3_probe_bytes(nprobe, max_items); }
+size_t scan_v3_smem_bytes(int nprobe, int max_items, int cap, int warps, int ring) {
+  return V3_PINFO_OFF + v3_probe_bytes(nprobe, max_items) + (size_t)cap * sizeof(u64) + (size_t)warps * ring * V3_SLOT_BYTES;
 }
 
-__device__ __forceinline__ V3Smem v3_carve(unsigned char *smem, int nprobe, int cap) {
+__device__ __forceinline__ V3Smem v3_carve(unsigned char *smem, int nprobe, int max_items, int cap) {
   V3Smem S;
   S.misc = reinterpret_cast<int *>(smem + V3_MISC_OFF);
   S.mbar = reinterpret_cast<unsigned long long *>(smem + V3_MBAR_OFF);
+  S.rbar = reinterpret_cast<unsigned long long *>(smem + V3_RBAR_OFF);
   S.pinfo = reinterpret_cast<ProbeInfo *>(smem + V3_PINFO_OFF);
   S.item_prefix = reinterpret_cast<int *>(smem + V3_PINFO_OFF + (size_t)nprobe * sizeof(ProbeInfo));
-  S.buf = reinterpret_cast<u64 *>(smem + V3_PINFO_OFF + v3_probe_bytes(nprobe));
-  S.ring = smem + V3_PINFO_OFF + v3_probe_bytes(nprobe) + (size_t)cap * sizeof(u64);
+  S.itab = reinterpret_cast<uint2 *>(smem + V3_PINFO_OFF + v3_itab_off(nprobe));
+  S.buf = reinterpret_cast<u64 *>(smem + V3_PINFO_OFF + v3_probe_bytes(nprobe, max_items));
+  S.ring = smem + V3_PINFO_OFF + v3_probe_bytes(nprobe, max_items) + (size_t)cap * sizeof(u64);
   return S;
 }
 
@@ -115,6 +125,29 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- TMA-fed ring: one elected lane issues bulk copies of whole 32-posting blocks, completion on the slot's mbarrier
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAITR_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONER_%=;\n\tbra WAITR_%=;\n\tDONER_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ int ld_volatile_s32(const int *p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -130,9 +163,10 @@ __global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= P.n) return;
   const int np = P.nprobe, ch = P.ch_blocks;
-  unsigned char *dst = P.probe_g + (size_t)q * v3_probe_bytes(np);
+  unsigned char *dst = P.probe_g + (size_t)q * v3_probe_bytes(np, P.v3_max_items);
   ProbeInfo *pinfo = reinterpret_cast<ProbeInfo *>(dst);
   int *prefix = reinterpret_cast<int *>(dst + (size_t)np * sizeof(ProbeInfo));
+  uint2 *itab = reinterpret_cast<uint2 *>(dst + v3_itab_off(np));
   const float *xq = P.xq + (size_t)q * P.d;
   int carry = 0;
   unsigned my_postings = 0;
@@ -163,13 +197,20 @@ __global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
       int v = __shfl_up_sync(GB_FULL, incl, o);
       if (lane >= o) incl += v;
     }
-    if (j < np) prefix[j] = carry + incl - ni;
+    if (j < np) {
+      prefix[j] = carry + incl - ni;
+      // this list's items, in claim order: up to ch consecutive 32-posting blocks each
+      const uint32_t offb = (uint32_t)(pi.off >> 5);
+      int it = carry + incl - ni;
+      for (int b0 = 0; b0 < nb && it < P.v3_max_items; b0 += ch, it++)
+        itab[it] = make_uint2(offb + (uint32_t)b0, ((uint32_t)min(ch, nb - b0) << 16) | (uint32_t)j);
+    }
     carry += __shfl_sync(GB_FULL, incl, 31);
     my_postings += (unsigned)pi.len;
   }
   my_postings = __reduce_add_sync(GB_FULL, my_postings);
   if (lane == 0) {
-    prefix[np] = carry;
+    prefix[np] = carry;  // may exceed the table's capacity (a list grew past the host's bound): those items are located by search
     if (P.scanned) atomicAdd(P.scanned, (unsigned long long)my_postings);
   }
 }
@@ -191,9 +232,9 @@ cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st) {
 // what it copied itself, cp.async.wait_group is per thread).  The copy engine runs ahead of the consumer across item
 // boundaries: the next item is claimed and located while the first block of the current one is scanned.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IP, bool HAS_VALID, int WARPS, int PER, int RING>
+template <bool IP, bool HAS_VALID, int WARPS, int PER, int RING, bool TMA>
 __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Smem &S, BlockTopR &topr, const int q,
-                                                 const int it_first) {
+                                                 const int it_first, uint32_t &ring_epoch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane4 = lane * 4;
   const int np = P.nprobe;
@@ -216,6 +257,9 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   // this lane's bytes of ring slot 0: codes chunk 0 at +0, chunk 1 at +512; id at ring_w + 1024, t(p) at ring_w + 1152
   const uint32_t ring_c = pin_u32(smem_u32(S.ring) + (uint32_t)warp * (RING * V3_SLOT_BYTES) + lane * 16);
   const uint32_t ring_w = pin_u32(smem_u32(S.ring) + (uint32_t)warp * (RING * V3_SLOT_BYTES) + lane * 4);
+  // TMA-fed ring: warp-uniform slot base and this warp's slot barriers
+  const uint32_t ring_b = smem_u32(S.ring) + (uint32_t)warp * (RING * V3_SLOT_BYTES);
+  const uint32_t rbar = smem_u32(S.rbar) + (uint32_t)warp * (4 * 8);
 
   // ---- consumer's item.  bi / bi_stop / bi_end are warp-uniform; bil, seqc differ per lane
   uint32_t bi = 0, bi_end = 0;  // next block to TAKE from the ring / end of the current item
@@ -223,15 +267,19 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   uint32_t bil = 0;             // this lane's posting of block b exists  <=>  b < bil
   uint32_t seqc = 0;            // scan-order word of this lane's posting in block b = seqc + 32 * (b + 1)
   float dis0 = 0.f;
-  // ---- copy engine (producer): runs up to RING blocks ahead, at most into the next located item
-  uint32_t pbi = 0, pbi_end = 0;  // next block to REQUEST / end of the producer's item
-  bool p_ahead = false;           // the producer already works on the located next item
-  uint32_t pn = 0, cn = 0;        // blocks requested / taken so far (slot = count % RING)
+  // ---- copy engine (producer): runs up to RING blocks ahead.  It walks the same items as the consumer, one segment
+  // [pbi, pbi_end) at a time; the item located next waits in [qbi, qbi_end) (empty when qbi == qbi_end) and is popped
+  // when the current segment is fully requested — no hand-shake with the consumer
+  uint32_t pbi = 0, pbi_end = 0;  // next block to REQUEST / end of the producer's segment
+  uint32_t qbi = 0, qbi_end = 0;  // queued segment
+  // blocks requested / taken so far (slot = count % RING).  The counts run on across the queries of this CTA: the
+  // TMA-fed ring's slot barriers keep their phase between queries (slot use u = count / RING waits with parity u & 1)
+  uint32_t pn = ring_epoch, cn = ring_epoch;
   // ---- claims
   int it_next = it_first;       // lane 0: the claim in flight (the first one was issued by the caller)
   bool claim_pending = true;    // a claim has been issued and not consumed yet
   bool nx_valid = false;        // the located item this warp scans next: list nx_j, blocks [nx_bi, nx_bi_end)
-  int nx_j = 0;
+  uint32_t nx_j = 0;
   uint32_t nx_bi = 0, nx_bi_end = 0;
 
   // One claim per item: an atomic add on the query's counter by lane 0.  The result stays in lane 0's register until
@@ -241,24 +289,44 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     if (lane == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_next) : "l"(claim) : "memory");
     claim_pending = true;
   };
-  // request the producer's next block into ring slot pn % RING (all lanes: each copies its own bytes)
+  // request the producer's next block into ring slot pn % RING (all lanes: each copies its own bytes).  Branch-free for
+  // the per-lane cp.async ring: the copies are predicated, a (possibly empty) group is committed either way.
   auto refill_one = [&]() {
-    if (pn - cn >= (uint32_t)RING) return;
-    if (pbi == pbi_end && !p_ahead && nx_valid) {  // current item fully requested: go on with the located next one
-      pbi = nx_bi;
-      pbi_end = nx_bi_end;
-      p_ahead = true;
-    }
-    if (pbi == pbi_end) return;
+    const bool seg_done = pbi == pbi_end;  // pop the queued segment
+    pbi = seg_done ? qbi : pbi;
+    pbi_end = seg_done ? qbi_end : pbi_end;
+    qbi = seg_done ? qbi_end : qbi;
+    const bool go = (pbi != pbi_end) && (pn - cn < (uint32_t)RING);
     const uint32_t so = (pn % RING) * V3_SLOT_BYTES;
-    const unsigned char *cp = wide_at<1024>(codes_lane, pbi);
-    cp_async_16(ring_c + so, cp);
-    cp_async_16(ring_c + so + 512, cp + 512);
-    cp_async_4(ring_w + so + 1024, wide_at<128>(ids_lane, pbi));
-    if (!IP) cp_async_4(ring_w + so + 1152, wide_at<128>(nrm_lane, pbi));
-    cp_async_commit();
-    pn++;
-    pbi++;
+    if (TMA) {
+      // whole block by three bulk copies from one elected lane (no LSU work, no per-lane addresses): the slot's
+      // mbarrier flips when all bytes have landed.  Slot use u = pn / RING waits with parity u & 1.
+      if (go && elect_one()) {
+        const uint32_t bar = rbar + (pn % RING) * 8;
+        mbar_expect_tx_a(bar, IP ? 1152u : 1280u);
+        tma_bulk_g2s_a(ring_b + so, wide_at<1024>(P.codes, pbi), 1024u, bar);
+        tma_bulk_g2s_a(ring_b + so + 1024, wide_at<128>(P.ids, pbi), 128u, bar);
+        if (!IP) tma_bulk_g2s_a(ring_b + so + 1152, wide_at<128>(P.norms, pbi), 128u, bar);
+      }
+    } else {
+      const unsigned char *cp = wide_at<1024>(codes_lane, pbi);
+      const uint32_t g = go ? 1u : 0u;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "@p cp.async.cg.shared.global [%0], [%2], 16;\n\t"
+          "@p cp.async.cg.shared.global [%0+512], [%2+512], 16;\n\t"
+          "@p cp.async.ca.shared.global [%1+1024], [%3], 4;\n\t}" ::"r"(ring_c + so),
+          "r"(ring_w + so), "l"(cp), "l"(wide_at<128>(ids_lane, pbi)), "r"(g)
+          : "memory");
+      if (!IP)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0+1152], [%1], 4;\n\t}" ::"r"(
+                         ring_w + so),
+                     "l"(wide_at<128>(nrm_lane, pbi)), "r"(g)
+                     : "memory");
+      cp_async_commit();
+    }
+    pn += go ? 1u : 0u;
+    pbi += go ? 1u : 0u;
   };
   // Slow path, run when bi == bi_stop (warp-uniform), i.e. after the FIRST block of an item and at its END:
   //  A. a claim is in flight: take its result and locate that item (list j, blocks) so that the copy engine can run
@@ -270,19 +338,28 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
       const int it = __shfl_sync(GB_FULL, it_next, 0);
       nx_valid = it < n_items;
       if (nx_valid) {
-        int j = -1;  // list that holds item `it`: last j with item_prefix[j] <= it
+        if (it < P.v3_max_items) {  // the item table gives list and blocks directly
+          const uint2 e = S.itab[it];
+          nx_j = e.y & 0xffffu;
+          nx_bi = e.x;
+          nx_bi_end = e.x + (e.y >> 16);
+        } else {  // beyond the table (the host sized it from the longest list it knew): last j with item_prefix[j] <= it
+          int j = -1;
 #pragma unroll 1
-        for (int j0 = 0; j0 < np; j0 += 32) {
-          const int v = (j0 + lane < np) ? S.item_prefix[j0 + lane] : 0x7fffffff;
-          j += __popc(__ballot_sync(GB_FULL, v <= it));
+          for (int j0 = 0; j0 < np; j0 += 32) {
+            const int v = (j0 + lane < np) ? S.item_prefix[j0 + lane] : 0x7fffffff;
+            j += __popc(__ballot_sync(GB_FULL, v <= it));
+          }
+          const ProbeInfo pi = S.pinfo[j];
+          const uint32_t offb = (uint32_t)(pi.off >> 5);
+          const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
+          const uint32_t b0 = (uint32_t)(it - S.item_prefix[j]) * (uint32_t)ch;
+          nx_j = (uint32_t)j;
+          nx_bi = offb + b0;
+          nx_bi_end = offb + min(b0 + (uint32_t)ch, nblk);
         }
-        const ProbeInfo pi = S.pinfo[j];
-        const uint32_t offb = (uint32_t)(pi.off >> 5);  // lists start on block boundaries
-        const uint32_t nblk = (uint32_t)(pi.len + 31) >> 5;
-        const uint32_t b0 = (uint32_t)(it - S.item_prefix[j]) * (uint32_t)ch;
-        nx_j = j;
-        nx_bi = offb + b0;
-        nx_bi_end = offb + min(b0 + (uint32_t)ch, nblk);
+        qbi = nx_bi;  // the producer's queue is empty here: it popped the current item before its first block was taken
+        qbi_end = nx_bi_end;
       }
     }
     if (bi == bi_end) {
@@ -295,12 +372,6 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
         bil = offb + ((uint32_t)(pi.len - lane + 31) >> 5);
         seqc = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)lane - (offb << 5) - 32u;
         dis0 = pi.dis0;
-        if (p_ahead) {
-          p_ahead = false;  // the producer is already inside this item
-        } else {
-          pbi = bi;
-          pbi_end = bi_end;
-        }
         claim_issue();
         bi_stop = bi + 1;  // consume that claim after the first block of this item (== bi_end for one-block items)
       }                    // else: the query has no unclaimed item left; bi == bi_end == bi_stop stays
@@ -319,12 +390,20 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     if (bi == bi_stop) slow_path();  // warp-uniform, twice per item
     have_n = bi != bi_end;
     if (have_n) {
-      if (pn == cn) {  // nothing in flight (query start, or the producer could not run ahead): fill the ring now
+      // ring not full although there is something to request (query start, or the next item was located too late for
+      // the producer to run ahead): top it up now
+      if (pn - cn < (uint32_t)RING && (pbi != pbi_end || qbi != qbi_end)) {
 #pragma unroll 1
         for (int k = 0; k < RING; k++) refill_one();
       }
-      if (pn - cn == (uint32_t)RING) cp_async_wait<RING - 1>();  // steady state: RING - 1 younger copies stay in flight
-      else cp_async_wait<0>();
+      if (TMA) {
+        mbar_wait_a(rbar + (cn % RING) * 8, (cn / RING) & 1u);
+      } else {
+        // ring full: the groups of the RING - 1 younger blocks (and possibly empty groups) follow the group of the block
+        // being taken, so "all but the RING - 1 most recent groups" covers it; otherwise wait for everything
+        if (pn - cn == (uint32_t)RING) cp_async_wait<RING - 1>();
+        else cp_async_wait<0>();
+      }
       const uint32_t so = (cn % RING) * V3_SLOT_BYTES;
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(ring_c + so));
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+512];" : "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7) : "r"(ring_c + so));
@@ -398,11 +477,14 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
           vw = (uint32_t)id_n < valid_lim ? __ldg(P.valid + (id_n >> 5)) : 0u;  // latency hidden by the lookups
           asm volatile("shf.l.wrap.b32 %0, 1, 1, %1;" : "=r"(vbit) : "r"(id_n));  // 1 << (id & 31)
         }
-        refill_one();
+        if (!TMA) refill_one();
         s01 = f2_pack(lds_raw<0>(a[0]), lds_raw<1>(a[1]));
         s23 = f2_pack(lds_raw<2>(a[2]), lds_raw<3>(a[3]));
         GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
         GB_ADDR4(c4, 0) GB_ADDR4(c5, 4) GB_ADDR4(c6, 8) GB_ADDR4(c7, 12)
+        // TMA ring: every register the slot fed (codes, id, t(p)) has been read by now, so the async-proxy write
+        // into it cannot pass a pending generic-proxy read
+        if (TMA) refill_one();
         // ---- next block out of the ring, straight into the registers just freed
         take_next();
         GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
@@ -442,6 +524,13 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     if (v & 1) topr.prune_collective<PER>();
     if (!(v & 2)) break;
   }
+  if (TMA) {  // nothing is in flight here (a warp requests only blocks it consumes); drain anyway so the phases stay in step
+    while (cn != pn) {
+      mbar_wait_a(rbar + (cn % RING) * 8, (cn / RING) & 1u);
+      cn++;
+    }
+  }
+  ring_epoch = pn;
 }
 
 // a CTA without a query looks for the running query with the most unclaimed items among the last help_window queries
@@ -449,7 +538,7 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
 template <int THREADS>
 __device__ __forceinline__ bool v3_pick_victim(const ScanParams &P, const V3Smem &S, int &q_out, int &row_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t pbytes = v3_probe_bytes(P.nprobe);
+  const size_t pbytes = v3_probe_bytes(P.nprobe, P.v3_max_items);
   const size_t total_off = (size_t)P.nprobe * sizeof(ProbeInfo) + (size_t)P.nprobe * sizeof(int);
   const int w0 = max(0, P.n - min(P.help_window, 65536));
   for (;;) {
@@ -487,11 +576,11 @@ __device__ __forceinline__ bool v3_pick_victim(const ScanParams &P, const V3Smem
   }
 }
 
-template <bool IP, int THREADS, int MINB, int PER, int RING>
+template <bool IP, int THREADS, int MINB, int PER, int RING, bool TMA>
 __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanParams P) {
   constexpr int WARPS = THREADS / 32;
   const int tid = threadIdx.x;
-  const V3Smem S = v3_carve(gb_scan_smem, P.nprobe, P.cap);
+  const V3Smem S = v3_carve(gb_scan_smem, P.nprobe, P.v3_max_items, P.cap);
   BlockTopR topr;
   topr.buf = S.buf;
   topr.tau = reinterpret_cast<u64 *>(S.misc);
@@ -502,13 +591,16 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
   topr.tau_f = reinterpret_cast<float *>(S.misc + 3);
   topr.is_ip = IP ? 1 : 0;
   if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
-  const uint32_t pbytes = (uint32_t)v3_probe_bytes(P.nprobe);
+  const uint32_t pbytes = (uint32_t)v3_probe_bytes(P.nprobe, P.v3_max_items);
   if (tid == 0) {
     mbar_init(&S.mbar[0], 1);
+    if (TMA)
+      for (int i = 0; i < 16 * 4; i++) mbar_init(&S.rbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   uint32_t parity = 0;
+  uint32_t ring_epoch = 0;
   bool helper = false;
   for (;;) {
     // ---- the next (query, candidate row) of this CTA
@@ -550,8 +642,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
     if ((tid & 31) == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_first) : "l"(claim0) : "memory");
     mbar_wait(&S.mbar[0], parity);
     parity ^= 1u;
-    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING>(P, S, topr, q, it_first);
-    else scan_loop_m32_v3<IP, false, WARPS, PER, RING>(P, S, topr, q, it_first);
+    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch);
+    else scan_loop_m32_v3<IP, false, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch);
     // ---- survivors of this CTA -> cand[q][row][0..R)
     topr.prune_collective<PER>();
     const int n_out = min(*((volatile int *)topr.cnt), P.R);
@@ -563,20 +655,23 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
 
 // cudaFuncSetAttribute is per device and cheap: called on every launch instead of caching per process (an index may live
 // on any device)
+template <bool IP, int T, int MINB, int PER, int RING, bool TMA>
+static cudaError_t launch_v3_one(const ScanParams &P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<IP, T, MINB, PER, RING, TMA>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ivfpq_scan_m32_v3_kernel<IP, T, MINB, PER, RING, TMA><<<grid, T, smem, st>>>(P);
+  return cudaGetLastError();
+}
 template <int T, int MINB, int PER, int RING>
 static cudaError_t launch_v3_shape(const ScanParams &P, int grid, cudaStream_t st) {
-  const size_t smem = scan_v3_smem_bytes(P.nprobe, P.cap, T / 32, RING);
-  cudaError_t e;
-  if (P.is_ip) {
-    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<true, T, MINB, PER, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ivfpq_scan_m32_v3_kernel<true, T, MINB, PER, RING><<<grid, T, smem, st>>>(P);
-  } else {
-    e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<false, T, MINB, PER, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ivfpq_scan_m32_v3_kernel<false, T, MINB, PER, RING><<<grid, T, smem, st>>>(P);
+  const size_t smem = scan_v3_smem_bytes(P.nprobe, P.v3_max_items, P.cap, T / 32, RING);
+  if (P.v3_tma) {
+    return P.is_ip ? launch_v3_one<true, T, MINB, PER, RING, true>(P, grid, smem, st)
+                   : launch_v3_one<false, T, MINB, PER, RING, true>(P, grid, smem, st);
   }
-  return cudaGetLastError();
+  return P.is_ip ? launch_v3_one<true, T, MINB, PER, RING, false>(P, grid, smem, st)
+                 : launch_v3_one<false, T, MINB, PER, RING, false>(P, grid, smem, st);
 }
 
 // CTA shapes (threads, CTAs per SM, ring slots per warp): shared memory per CTA = 64 KB table + candidate buffer + probe
@@ -586,9 +681,9 @@ static cudaError_t launch_v3_shape(const ScanParams &P, int grid, cudaStream_t s
 //   256 x 2, ring 4: 16 warps per SM, 5 blocks in flight per warp
 //   512 x 1, ring 2: recall_num > 512 (candidate buffers of 2048 / 4096 keys, 4 / 8 keys per thread in the select)
 int scan_v3_ctas_per_sm(int threads, int cap) { return (threads >= 512 || cap > 1024) ? 1 : 2; }
-size_t scan_v3_smem_bytes_for(int nprobe, int cap, int threads) {
+size_t scan_v3_smem_bytes_for(int nprobe, int max_items, int cap, int threads) {
   const int ring = threads == 320 ? 3 : threads == 256 ? 4 : 2;
-  return scan_v3_smem_bytes(nprobe, cap, threads / 32, ring);
+  return scan_v3_smem_bytes(nprobe, max_items, cap, threads / 32, ring);
 }
 
 cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st) {
@@ -596,6 +691,8 @@ cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st)
     return cudaErrorInvalidValue;
   switch (P.m32_threads) {
     case 512: return P.cap > 2048 ? launch_v3_shape<512, 1, 8, 2>(P, grid, st) : launch_v3_shape<512, 1, 4, 2>(P, grid, st);
+    case 448: return launch_v3_shape<448, 2, 4, 2>(P, grid, st);
+    case 416: return launch_v3_shape<416, 2, 4, 2>(P, grid, st);
     case 320: return launch_v3_shape<320, 2, 4, 3>(P, grid, st);
     case 256: return launch_v3_shape<256, 2, 4, 4>(P, grid, st);
     default: return launch_v3_shape<384, 2, 4, 2>(P, grid, st);

@@ -52,10 +52,12 @@ struct ScanParams {
   int v3_zero;              // always 0 (keeps the claim address opaque to the compiler, see scan_loop_m32_v3)
   int help_min;             // an idle CTA joins a running query that still has >= help_min unclaimed items ...
   int help_window;          // ... looking at the last help_window queries
+  int v3_max_items;         // capacity of the per-query item table (host bound: nprobe x items of the longest list)
+  int v3_tma;               // posting ring fed by bulk copies (cp.async.bulk, one elected lane) instead of per-lane cp.async
 };
 // v3 launchers (ivfpq_scan_v3.cu)
-size_t scan_v3_probe_bytes(int nprobe);
-size_t scan_v3_smem_bytes_for(int nprobe, int cap, int threads);
+size_t scan_v3_probe_bytes(int nprobe, int max_items);
+size_t scan_v3_smem_bytes_for(int nprobe, int max_items, int cap, int threads);
 int scan_v3_ctas_per_sm(int threads, int cap);
 cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st);

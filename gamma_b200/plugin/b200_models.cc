@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include "common/gamma_common_data.h"
 #include "table/range_query_result.h"
 #include "vector/raw_vector.h"
@@ -72,13 +74,14 @@ B200IVFPQIndex::~B200IVFPQIndex() {
   if (dev_) gb200_destroy(dev_);
 }
 
-int B200IVFPQIndex::Init(const std::string &model_parameters, int indexing_size) {
-  int ret = GammaIVFPQIndex::Init(model_parameters, indexing_size);
-  if (ret) return ret;
-  if (opq_ != nullptr || quantizer_type_ != 0) {
-    LOG(ERROR) << "B200IVFPQ: opq / hnsw coarse quantizer are not supported";
-    return -1;
-  }
+// the validity bitmap is indexed by doc id while postings carry vids: the two coincide only for single-vector fields
+// (VIDMgr::VID2DocID is the identity unless multi_vids_, vector/raw_vector_common.h:44-147)
+static bool MultiVidStore(VectorReader *v) {
+  RawVector *raw = dynamic_cast<RawVector *>(v);
+  return raw && raw->VidMgr() && raw->VidMgr()->MultiVids();
+}
+
+gb200_ivfpq_params B200IVFPQIndex::DeviceParams() const {
   gb200_ivfpq_params p;
   memset(&p, 0, sizeof(p));
   p.device = DeviceOrdinal();
@@ -90,6 +93,21 @@ int B200IVFPQIndex::Init(const std::string &model_parameters, int indexing_size)
   p.metric = metric_type_ == DistanceComputeType::INNER_PRODUCT ? GB200_METRIC_INNER_PRODUCT : GB200_METRIC_L2;
   p.nprobe = (int)this->nprobe;
   p.store_raw = 1;
+  return p;
+}
+
+int B200IVFPQIndex::Init(const std::string &model_parameters, int indexing_size) {
+  int ret = GammaIVFPQIndex::Init(model_parameters, indexing_size);
+  if (ret) return ret;
+  if (opq_ != nullptr || quantizer_type_ != 0) {
+    LOG(ERROR) << "B200IVFPQ: opq / hnsw coarse quantizer are not supported";
+    return -1;
+  }
+  if (MultiVidStore(vector_)) {
+    LOG(ERROR) << "B200IVFPQ: multi-vid vector fields are not supported (filters are applied by vid)";
+    return -1;
+  }
+  gb200_ivfpq_params p = DeviceParams();
   int rc = gb200_ivfpq_create(&p, &dev_);
   if (rc) {
     LOG(ERROR) << "gb200_ivfpq_create failed: " << rc << " " << gb200_last_error();
@@ -110,8 +128,27 @@ int B200IVFPQIndex::PushQuantizers() {
 int B200IVFPQIndex::Indexing() {
   int ret = GammaIVFPQIndex::Indexing();  // faiss::IndexIVFPQ::train on the host (gamma_index_ivfpq.cc:272-354)
   if (ret) return ret;
+  B200RwLock::Shared dl(dev_mu_);
   std::lock_guard<std::mutex> g(mirror_mu_);
   return PushQuantizers() ? -1 : 0;
+}
+
+int B200IVFPQIndex::MirrorList(int l) {
+  long *ids = nullptr;
+  size_t len = 0;
+  uint8_t *cds = nullptr;
+  if (!rt_invert_index_ptr_->GetIvtList(l, ids, len, cds)) len = 0;
+  // idx_array_ words as they are (bit 63 = kDelIdxMask): gb200_ivfpq_replace_list takes the reference layout
+  int rc = gb200_ivfpq_replace_list(dev_, l, (int64_t)len, reinterpret_cast<const int64_t *>(ids), cds);
+  if (rc == 0) mirrored_len_[l] = len;
+  return rc;
+}
+
+int B200IVFPQIndex::SyncDeleted() {
+  RawVector *raw = dynamic_cast<RawVector *>(vector_);
+  bitmap::BitmapManager *bm = raw ? raw->Bitmap() : nullptr;
+  if (!bm) return 0;
+  return gb200_upload_deleted_bitmap(dev_, reinterpret_cast<const uint8_t *>(bm->Bitmap()), bm->BitSize());
 }
 
 int B200IVFPQIndex::MirrorPostings() {
@@ -144,90 +181,108 @@ int B200IVFPQIndex::MirrorRaw() {
 }
 
 int B200IVFPQIndex::ResyncAll() {
-  // rebuild from scratch: simplest correct answer to Load / compaction (rare events)
-  gb200_ivfpq_params p;
-  memset(&p, 0, sizeof(p));
-  p.device = DeviceOrdinal();
-  p.d = this->d;
-  p.raw_d = vector_->MetaInfo()->Dimension();
-  p.nlist = (int)this->nlist;
-  p.nsubvector = (int)this->pq.M;
-  p.nbits = (int)this->pq.nbits;
-  p.metric = metric_type_ == DistanceComputeType::INNER_PRODUCT ? GB200_METRIC_INNER_PRODUCT : GB200_METRIC_L2;
-  p.nprobe = (int)this->nprobe;
-  p.store_raw = 1;
+  // rebuild from scratch after Load.  Caller holds dev_mu_ EXCLUSIVELY (no search is inside the library) and mirror_mu_.
+  gb200_ivfpq_params p = DeviceParams();
   if (dev_) gb200_destroy(dev_);
   dev_ = nullptr;
   if (gb200_ivfpq_create(&p, &dev_)) return -1;
   mirrored_len_.assign(this->nlist, 0);
   raw_mirrored_ = 0;
   if (PushQuantizers()) return -1;
-  // dead postings (kDelIdxMask) must stay dead and keep their slot so positions match
+  // one bulk append of the alive postings (fast path for a big index), then the lists that hold dead slots
+  // (kDelIdxMask: the slot stays so that positions match the host's) are rewritten with the flags in place
   std::vector<int32_t> list_no;
   std::vector<int64_t> vids;
   std::vector<uint8_t> codes;
-  std::vector<std::pair<int64_t, int32_t>> dead;
+  std::vector<int> with_dead;
   for (size_t l = 0; l < this->nlist; l++) {
     long *ids = nullptr;
     size_t len = 0;
     uint8_t *cds = nullptr;
     if (!rt_invert_index_ptr_->GetIvtList(l, ids, len, cds)) continue;
+    bool dead = false;
+    for (size_t j = 0; j < len; j++) dead |= (ids[j] & realtime::kDelIdxMask) != 0;
+    if (dead) {
+      with_dead.push_back((int)l);
+      continue;
+    }
     for (size_t j = 0; j < len; j++) {
       list_no.push_back((int32_t)l);
-      vids.push_back(ids[j] & realtime::kRecoverIdxMask);
+      vids.push_back(ids[j]);
       codes.insert(codes.end(), cds + j * code_size, cds + (j + 1) * code_size);
     }
     mirrored_len_[l] = len;
   }
   if (!list_no.empty() && gb200_ivfpq_append(dev_, (int64_t)list_no.size(), list_no.data(), vids.data(), codes.data()))
     return -1;
-  RawVector *raw = dynamic_cast<RawVector *>(vector_);
-  bitmap::BitmapManager *bm = raw->Bitmap();
-  if (bm && gb200_upload_deleted_bitmap(dev_, reinterpret_cast<const uint8_t *>(bm->Bitmap()), bm->BitSize())) return -1;
+  for (int l : with_dead)
+    if (MirrorList(l)) return -1;
+  if (SyncDeleted()) return -1;
   compacted_seen_ = rt_invert_index_ptr_->cur_ptr_->cur_invert_ptr_->compacted_num_;
   return MirrorRaw();
 }
 
 bool B200IVFPQIndex::Add(int n, const uint8_t *vec) {
   if (!GammaIVFPQIndex::Add(n, vec)) return false;  // assign + residual + pq.compute_codes + AddKeys on the host
+  B200RwLock::Shared dl(dev_mu_);
   std::lock_guard<std::mutex> g(mirror_mu_);
   if (!quantizers_pushed_ && PushQuantizers()) return false;
   return MirrorPostings() == 0;
 }
 
 int B200IVFPQIndex::Update(const std::vector<int64_t> &ids, const std::vector<const uint8_t *> &vecs) {
+  // lists the update may touch, taken BEFORE the host applies it: where every vid lives now
+  std::vector<int> touched;
+  {
+    realtime::RTInvertBucketData *cur = rt_invert_index_ptr_->cur_ptr_->cur_invert_ptr_;
+    for (size_t i = 0; i < ids.size(); i++) {
+      if (ids[i] < 0 || (size_t)ids[i] >= cur->nids_) continue;
+      long loc = cur->vid_bucket_no_pos_[ids[i]];
+      if (loc != -1) touched.push_back((int)(loc >> 32));
+    }
+  }
   int ret = GammaIVFPQIndex::Update(ids, vecs);  // re-assign, re-encode, RealTimeMemData::Update, CompactIfNeed
   if (ret) return ret;
+  B200RwLock::Shared dl(dev_mu_);
   std::lock_guard<std::mutex> g(mirror_mu_);
   realtime::RTInvertBucketData *cur = rt_invert_index_ptr_->cur_ptr_->cur_invert_ptr_;
-  if (cur->compacted_num_ != compacted_seen_) return ResyncAll();  // lists were rewritten
   RawVector *raw = dynamic_cast<RawVector *>(vector_);
-  for (size_t i = 0; i < ids.size(); i++) {
+  for (size_t i = 0; i < ids.size(); i++) {  // ... and where it lives afterwards
     long vid = ids[i];
-    if ((size_t)vid >= cur->nids_) continue;
+    if (vid < 0 || (size_t)vid >= cur->nids_) continue;
     long loc = cur->vid_bucket_no_pos_[vid];
-    if (loc == -1) continue;
-    int list = (int)(loc >> 32), pos = (int)(loc & 0xffffffff);
-    const uint8_t *code = cur->codes_array_[list] + (size_t)pos * code_size;
-    if (gb200_ivfpq_update(dev_, vid, list, code)) return -1;
-    if ((size_t)pos >= mirrored_len_[list]) mirrored_len_[list] = pos + 1;
+    if (loc != -1) touched.push_back((int)(loc >> 32));
     // the raw vector changed too (re-rank reads it)
     ScopeVector sv;
     raw->GetVector(vid, sv);
     if (sv.Get() && gb200_upload_raw(dev_, vid, 1, reinterpret_cast<const float *>(sv.Get()))) return -1;
   }
+  if (cur->compacted_num_ != compacted_seen_) {  // CompactBucket rewrote some lists: the ones that got shorter
+    if (SyncDeleted()) return -1;
+    for (size_t l = 0; l < this->nlist; l++)
+      if ((size_t)cur->retrieve_idx_pos_[l] < mirrored_len_[l]) touched.push_back((int)l);
+    compacted_seen_ = cur->compacted_num_;
+  }
+  std::sort(touched.begin(), touched.end());
+  touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+  // every touched list is replaced by the host's copy (dead flags included): searches keep running, the swap is a
+  // publication of the new extent
+  for (int l : touched)
+    if (MirrorList(l)) return -1;
   return 0;
 }
 
 int B200IVFPQIndex::Delete(const std::vector<int64_t> &ids) {
   GammaIVFPQIndex::Delete(ids);
   // liveness is the deleted-docs bitmap (set by the engine before this call); mirror the bits
+  B200RwLock::Shared dl(dev_mu_);
   return gb200_set_deleted(dev_, ids.data(), (int64_t)ids.size(), 1) ? -1 : 0;
 }
 
 int B200IVFPQIndex::Load(const std::string &index_dir) {
   int ret = GammaIVFPQIndex::Load(index_dir);
   if (ret < 0) return ret;
+  B200RwLock::Exclusive dl(dev_mu_);  // the device index is replaced: no search may be inside it
   std::lock_guard<std::mutex> g(mirror_mu_);
   if (this->is_trained && ResyncAll()) return -1;
   return ret;
@@ -254,9 +309,13 @@ int B200IVFPQIndex::Search(RetrievalContext *retrieval_context, int n, const uin
     FillEmpty(n, k, sp.metric == GB200_METRIC_INNER_PRODUCT, distances, labels);
     return 0;
   }
+  B200RwLock::Shared dl(dev_mu_);  // held for the whole device search
   {
     std::lock_guard<std::mutex> g(mirror_mu_);
     if (MirrorRaw()) return -1;  // the store grows ahead of the index (AddToStore, gamma_engine.cc:651)
+    // the reference tests docids_bitmap_ live, and some engine paths set bits without calling Delete()
+    // (DelDocByQuery, search/gamma_engine.cc:866): bring the device bitmap in line (a memcmp when nothing changed)
+    if (SyncDeleted()) return -1;
   }
   std::vector<gb200_range_filter> filters;
   CollectFilters(cond, &filters);
@@ -288,12 +347,23 @@ B200FLATIndex::~B200FLATIndex() {
 int B200FLATIndex::Init(const std::string &model_parameters, int indexing_size) {
   int ret = GammaFLATIndex::Init(model_parameters, indexing_size);
   if (ret) return ret;
+  if (MultiVidStore(vector_)) {
+    LOG(ERROR) << "B200FLAT: multi-vid vector fields are not supported (filters are applied by vid)";
+    return -1;
+  }
   int metric = metric_type_ == DistanceComputeType::INNER_PRODUCT ? GB200_METRIC_INNER_PRODUCT : GB200_METRIC_L2;
   if (gb200_flat_create(DeviceOrdinal(), vector_->MetaInfo()->Dimension(), metric, &dev_)) {
     LOG(ERROR) << "gb200_flat_create failed: " << gb200_last_error();
     return -1;
   }
   return 0;
+}
+
+int B200FLATIndex::SyncDeleted() {
+  RawVector *raw = dynamic_cast<RawVector *>(vector_);
+  bitmap::BitmapManager *bm = raw ? raw->Bitmap() : nullptr;
+  if (!bm) return 0;
+  return gb200_upload_deleted_bitmap(dev_, reinterpret_cast<const uint8_t *>(bm->Bitmap()), bm->BitSize());
 }
 
 int B200FLATIndex::MirrorRaw() {
@@ -340,6 +410,7 @@ int B200FLATIndex::Search(RetrievalContext *retrieval_context, int n, const uint
   {
     std::lock_guard<std::mutex> g(mirror_mu_);
     if (MirrorRaw()) return -1;
+    if (SyncDeleted()) return -1;
   }
   std::vector<gb200_range_filter> filters;
   CollectFilters(cond, &filters);

@@ -11,6 +11,8 @@
 //
 // Compiles against the unmodified reference headers (-I<reference root>); nothing else is needed.
 #pragma once
+#include <pthread.h>
+
 #include <mutex>
 #include <vector>
 
@@ -19,6 +21,26 @@
 #include "index/impl/gamma_index_ivfpq.h"
 
 namespace tig_gamma {
+
+// reader/writer lock that compiles as C++11 (the reference builds with -std=c++11: no std::shared_mutex)
+class B200RwLock {
+ public:
+  B200RwLock() { pthread_rwlock_init(&l_, nullptr); }
+  ~B200RwLock() { pthread_rwlock_destroy(&l_); }
+  struct Shared {
+    explicit Shared(B200RwLock &m) : m_(m) { pthread_rwlock_rdlock(&m_.l_); }
+    ~Shared() { pthread_rwlock_unlock(&m_.l_); }
+    B200RwLock &m_;
+  };
+  struct Exclusive {
+    explicit Exclusive(B200RwLock &m) : m_(m) { pthread_rwlock_wrlock(&m_.l_); }
+    ~Exclusive() { pthread_rwlock_unlock(&m_.l_); }
+    B200RwLock &m_;
+  };
+
+ private:
+  pthread_rwlock_t l_;
+};
 
 class B200IVFPQIndex : public GammaIVFPQIndex {
  public:
@@ -39,9 +61,15 @@ class B200IVFPQIndex : public GammaIVFPQIndex {
   int PushQuantizers();
   int MirrorPostings();   // append whatever the CPU lists gained since the last call
   int MirrorRaw();        // upload raw vectors added to the store since the last call
-  int ResyncAll();        // after Load / compaction: rebuild the device lists from the CPU lists
+  int MirrorList(int l);  // device copy of list l := the CPU list (after Update / CompactBucket touched it)
+  int SyncDeleted();      // device live-docs bitmap := docids_bitmap_ (only changed words travel)
+  int ResyncAll();        // after Load: rebuild the device index from the CPU lists (replaces dev_)
+  gb200_ivfpq_params DeviceParams() const;
 
+  // dev_mu_ (always taken before mirror_mu_): shared by every call that uses dev_, exclusive while ResyncAll replaces it —
+  // the engine serves searches concurrently with Add / Update / Load.  mirror_mu_ guards the mirror bookkeeping.
   gb200_index *dev_ = nullptr;
+  B200RwLock dev_mu_;
   std::mutex mirror_mu_;
   std::vector<size_t> mirrored_len_;
   long raw_mirrored_ = 0;
@@ -63,6 +91,7 @@ class B200FLATIndex : public GammaFLATIndex {
 
  private:
   int MirrorRaw();
+  int SyncDeleted();
   gb200_index *dev_ = nullptr;
   std::mutex mirror_mu_;
   long raw_mirrored_ = 0;

@@ -217,6 +217,129 @@ int main(int argc, char **argv) {
   search(cpu_flat, fj, true, nullptr, lo, hi, D0, I0);
   search(gpu_flat, fj, true, nullptr, lo, hi, D1, I1);
   report("flat_score_window", 1.0, 0.0);
+  // ---- docs deleted through the bitmap alone (DelDocByQuery sets bits without calling RetrievalModel::Delete,
+  // search/gamma_engine.cc:866): the reference tests the bitmap live, the plugin re-syncs it before every search
+  search(cpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+  {
+    int hidden = 0;
+    for (int q = 0; q < nq && hidden < 40; q += 3)
+      if (I0[(size_t)q * k] >= 0 && !bm->Test((uint32_t)I0[(size_t)q * k])) {
+        bm->Set((uint32_t)I0[(size_t)q * k]);
+        hidden++;
+      }
+  }
+  search(cpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, true, nullptr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_bitmap_only_delete", 0.995, 1e-6);
+  search(cpu_flat, fj, true, nullptr, -FMAX, FMAX, D0, I0);
+  search(gpu_flat, fj, true, nullptr, -FMAX, FMAX, D1, I1);
+  report("flat_bitmap_only_delete", 1.0, 0.0);
+
+  // ---- Update + CompactBucket on the host (RealTimeMemData::CompactIfNeed, realtime_mem_data.cc:354-424): delete 40 % of
+  // the largest bucket, then update 24 docs; the plugin replaces the touched / compacted lists on the device
+  {
+    GammaIVFPQIndex *c = dynamic_cast<GammaIVFPQIndex *>(cpu);
+    size_t best = 0, best_len = 0;
+    for (size_t l = 0; l < c->nlist; l++) {
+      long *ids = nullptr;
+      size_t len = 0;
+      uint8_t *cds = nullptr;
+      if (c->rt_invert_index_ptr_->GetIvtList(l, ids, len, cds) && len > best_len) best = l, best_len = len;
+    }
+    long *ids = nullptr;
+    size_t len = 0;
+    uint8_t *cds = nullptr;
+    c->rt_invert_index_ptr_->GetIvtList(best, ids, len, cds);
+    std::vector<int64_t> dele2;
+    for (size_t j = 0; j < len && dele2.size() < len * 2 / 5; j++)
+      if (!(ids[j] & realtime::kDelIdxMask) && !bm->Test((uint32_t)ids[j])) dele2.push_back(ids[j]);
+    for (int64_t v : dele2) bm->Set((uint32_t)v);
+    for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat}) m->Delete(dele2);
+    const long compacted_before = c->rt_invert_index_ptr_->cur_ptr_->cur_invert_ptr_->compacted_num_;
+    std::vector<int64_t> uids;
+    std::vector<const uint8_t *> uvecs;
+    for (int t = 0; t < 24; t++) {
+      int64_t id = 5000 + 311 * t;
+      if (bm->Test((uint32_t)id)) continue;
+      const float *nv = &xb[(size_t)((id * 7 + 13) % N) * d];
+      raw->UpdateToStore((int)id, (uint8_t *)nv, d * sizeof(float));
+      uids.push_back(id);
+      uvecs.push_back((const uint8_t *)nv);
+    }
+    for (RetrievalModel *m : {cpu, gpu, cpu_flat, gpu_flat})
+      if (m->Update(uids, uvecs)) {
+        printf("{\"error\":\"Update failed: %s\"}\n", gb200_last_error());
+        return 7;
+      }
+    const long compacted = c->rt_invert_index_ptr_->cur_ptr_->cur_invert_ptr_->compacted_num_ - compacted_before;
+    printf("{\"host_compacted_postings\":%ld,\"updated\":%zu}\n", compacted, uids.size());
+    if (compacted <= 0) fails++;  // the case must exercise CompactBucket
+  }
+  search(cpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, true, nullptr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_rerank_after_update_and_compaction", 0.995, 1e-6);
+  search(cpu, rj, false, &mr, -FMAX, FMAX, D0, I0);
+  search(gpu, rj, false, &mr, -FMAX, FMAX, D1, I1);
+  report("ivfpq_adc_filter_after_compaction", 0.98, 1e-4);
+
+  // ---- Dump / Load in the reference's own file format (gamma_index_ivfpq.cc:958-1048, index/gamma_index_io.cc:140-196):
+  // a dump written by the reference IVFPQ model is loaded by a fresh B200IVFPQ, and the other way round
+  {
+    utils::make_dir("/tmp/b200_plugin_parity/dump_cpu");
+    utils::make_dir("/tmp/b200_plugin_parity/dump_b200");
+    if (cpu->Dump("/tmp/b200_plugin_parity/dump_cpu") || gpu->Dump("/tmp/b200_plugin_parity/dump_b200")) {
+      printf("{\"error\":\"Dump failed\"}\n");
+      return 8;
+    }
+    RetrievalModel *gpu2 = reflector().GetNewModel("B200IVFPQ");
+    RetrievalModel *cpu2 = reflector().GetNewModel("IVFPQ");
+    gpu2->vector_ = raw;
+    cpu2->vector_ = raw;
+    if (gpu2->Init(json, first) || cpu2->Init(json, first)) {
+      printf("{\"error\":\"Init of the loading models failed: %s\"}\n", gb200_last_error());
+      return 8;
+    }
+    int n_loaded = gpu2->Load("/tmp/b200_plugin_parity/dump_cpu");
+    int n_loaded_cpu = cpu2->Load("/tmp/b200_plugin_parity/dump_b200");
+    printf("{\"loaded_into_b200\":%d,\"loaded_into_reference\":%d}\n", n_loaded, n_loaded_cpu);
+    if (n_loaded <= 0 || n_loaded_cpu <= 0) fails++;
+    search(cpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+    search(gpu2, rj, true, nullptr, -FMAX, FMAX, D1, I1);
+    report("b200_loads_reference_dump", 0.995, 1e-6);
+    search(cpu2, rj, false, nullptr, -FMAX, FMAX, D0, I0);
+    search(gpu, rj, false, nullptr, -FMAX, FMAX, D1, I1);
+    report("reference_loads_b200_dump", 0.98, 1e-4);
+    search(gpu, rj, false, nullptr, -FMAX, FMAX, D0, I0);
+    search(gpu2, rj, false, nullptr, -FMAX, FMAX, D1, I1);
+    report("loaded_b200_equals_live_b200", 1.0, 0.0);
+    delete gpu2;
+    delete cpu2;
+  }
+
+  // ---- concurrent Search (the engine's normal mode, tests/test.h:1033-1062): 8 threads, results equal the serial ones
+  {
+    search(gpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);
+    int bad = 0;
+#pragma omp parallel for num_threads(8) reduction(+ : bad)
+    for (int t = 0; t < 32; t++) {
+      std::vector<float> Dt;
+      std::vector<int64_t> It;
+      PerfTool pt;
+      GammaSearchCondition cond(&pt);
+      cond.topn = k;
+      cond.has_rank = true;
+      cond.range_query_result = nullptr;
+      cond.Init(-FMAX, FMAX, bm, raw);
+      cond.retrieval_params_ = gpu->Parse(rj);
+      Dt.assign((size_t)nq * k, 0.f);
+      It.assign((size_t)nq * k, -1);
+      int rc = gpu->Search(&cond, nq, (const uint8_t *)xq.data(), k, Dt.data(), It.data());
+      if (rc || memcmp(It.data(), I0.data(), It.size() * sizeof(int64_t)) || memcmp(Dt.data(), D0.data(), Dt.size() * sizeof(float)))
+        bad++;
+    }
+    printf("{\"case\":\"concurrent_search_8_threads\",\"mismatching_calls\":%d,\"ok\":%s}\n", bad, bad ? "false" : "true");
+    if (bad) fails++;
+  }
   printf("{\"plugin_parity\":\"%s\",\"gpu_mem_bytes\":%ld}\n", fails ? "FAIL" : "PASS", gpu->GetTotalMemBytes());
   return fails ? 1 : 0;
 }

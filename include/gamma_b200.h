@@ -115,6 +115,12 @@ int gb200_ivfpq_get_list(gb200_index *ix, int32_t list_no, int64_t *ids, uint8_t
  * running; list_no == -1: every list, into a new tightly packed pool (also returns the regions abandoned by list
  * growth; searches are drained for the swap).  *dropped (may be NULL) = postings removed.                          */
 int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped);
+/* Replace the whole content of one list by n postings given in the REFERENCE layout (ids[i] as in idx_array_: vid,
+ * bit 63 = kDelIdxMask for a posting that was moved away and only keeps its slot; AoS codes).  This is how a host that
+ * owns the lists (the RetrievalModel plugin: RTInvertBucketData after Update / CompactBucket,
+ * realtime/realtime_mem_data.cc:119-147, 264-327) brings the device copy of a list in line with its own, whatever
+ * happened to it: the new content goes into a fresh region and is swapped in by publication, searches keep running. */
+int gb200_ivfpq_replace_list(gb200_index *ix, int32_t list_no, int64_t n, const int64_t *ids, const uint8_t *codes);
 
 /* ---- raw vectors: the read side of VectorReader::Gets / RawVector::GetVectorHeader
  * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are

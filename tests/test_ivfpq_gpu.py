@@ -291,6 +291,28 @@ def test_coarse_select_nprobe_sweep(nprobe):
     assert np.all(np.diff(cd, axis=1) >= 0)
 
 
+@pytest.mark.parametrize("nprobe", [1, 16, 33, 64, 128])
+def test_coarse_select_from_chunk_minima(nprobe, monkeypatch):
+    """nlist >= 4096: the select starts from the chunk minima the tensor-core GEMM emits (coarse_select_cmin_kernel).
+    Parity with the reference's quantizer->search, and bit-identical to the full-row select of the same distances."""
+    from gamma_b200 import synth
+    f = fx_l2_nlist4096()
+    ix = f.mirror(raw=False)
+    xq = synth.mixture(300, f.d, synth.SEED_QUERY + 33, n_clusters=512)
+    xq[7] = 0.0  # all-zero query
+    cd_ref, k_ref = f.ref.coarse(xq, nprobe)
+    cd, k = ix.coarse(xq, nprobe)
+    r = compare_topk(cd_ref, k_ref, cd, k, rtol=1e-4, atol=1e-4)
+    assert r["n_id_mismatch_unexplained"] == 0 and r["max_rel_err"] <= 1e-4, r
+    assert np.all(np.diff(cd, axis=1) >= 0)
+    xq[8] = f.centroids[5]  # a query that IS a centroid: |q|^2 + |c|^2 - 2 q.c cancels to ~0 (clamped), both paths agree
+    cd, k = ix.coarse(xq, nprobe)
+    monkeypatch.setenv("GB200_COARSE_FULL_SELECT", "1")
+    ix.reload_tuning()
+    cd2, k2 = ix.coarse(xq, nprobe)
+    assert np.array_equal(k, k2) and np.array_equal(cd, cd2)
+
+
 @pytest.mark.parametrize("metric", ["L2", "InnerProduct"])
 def test_m64_default_kernel_parity(metric):
     """M = 64 is the reference's default nsubvector (gamma_index_ivfpq.h:693) and BASELINE config 3: the conflict-free

@@ -24,3 +24,11 @@ def test_plugin_matches_reference_models_through_the_reflector():
     cases = {l["case"]: l for l in lines if "case" in l}
     assert cases["flat_filter_delete_update"]["ids_identical"] == 1.0
     assert cases["ivfpq_rerank"]["ids_identical"] >= 0.995
+    # docs deleted through the bitmap alone, host-side Update + CompactBucket mirrored list by list, Dump / Load in the
+    # reference's file format in both directions, 8 concurrent searches
+    for name in ("ivfpq_bitmap_only_delete", "flat_bitmap_only_delete", "ivfpq_rerank_after_update_and_compaction",
+                 "ivfpq_adc_filter_after_compaction", "b200_loads_reference_dump", "reference_loads_b200_dump",
+                 "loaded_b200_equals_live_b200", "concurrent_search_8_threads"):
+        assert cases[name]["ok"], cases[name]
+    assert cases["loaded_b200_equals_live_b200"]["ids_identical"] == 1.0
+    assert any(l.get("host_compacted_postings", 0) > 0 for l in lines)
