@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
         L.gb200_reload_tuning.argtypes = [C.c_void_p]
         L.gb200_ivfpq_compact.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.gb200_ivfpq_replace_list.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+        L.gb200_ivfpq_encode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gb200_ivfpq_add_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
@@ -266,6 +268,24 @@ class B200IVFPQ(_Base):
     def update(self, vid, new_list, code):
         c = np.ascontiguousarray(code, dtype=np.uint8)
         return lib().gb200_ivfpq_update(self.h, int(vid), int(new_list), c.ctypes.data)
+
+    def encode(self, x):
+        """stage 1 of GammaIVFPQIndex::Add on the device: (list_no [n] i32, codes [n, M] u8)"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        ln = np.empty(n, np.int32)
+        cd = np.empty((n, self.M), np.uint8)
+        _check(lib().gb200_ivfpq_encode(self.h, n, x.ctypes.data, x.shape[1], ln.ctypes.data, cd.ctypes.data), "encode")
+        return ln, cd
+
+    def add_raw(self, x, first_vid):
+        """the whole Add: raw upload + device encode + append; returns (list_no, codes) as appended"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        ln = np.empty(n, np.int32)
+        cd = np.empty((n, self.M), np.uint8)
+        _check(lib().gb200_ivfpq_add_raw(self.h, int(first_vid), n, x.ctypes.data, ln.ctypes.data, cd.ctypes.data), "add_raw")
+        return ln, cd
 
     def replace_list(self, list_no, ids, codes):
         """device copy of one list := the given reference-layout content (ids with kDelIdxMask in bit 63, AoS codes)"""

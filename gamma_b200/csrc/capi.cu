@@ -1230,13 +1230,13 @@ static int coarse_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, i
     return GB200_EUNSUPPORTED;
   }
   CKI(c.ws_xn.ensure((size_t)n * sizeof(float)));
-  CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
   // distance producer: tcgen05 3xTF32 GEMM (default) or the CUDA-core fp32 kernel (GB200_COARSE=simt)
   const bool use_tc = !ix->tune.coarse_simt && (d % 4 == 0) && (nlist % 4 == 0);
   if (use_tc) {
     CKI(c.ws_xs.ensure((size_t)n * d * sizeof(float)));
-    CK(launch_tf32_residual(d_xq, c.ws_xs.as<float>(), (size_t)n * d, c.stream));
-    c.launches++;
+    CK(launch_rows_prep(d_xq, n, d, c.ws_xn.as<float>(), c.ws_xs.as<float>(), c.stream));
+  } else {
+    CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
   }
   // bound the distance matrix scratch to ~1 GiB by chunking the queries
   long long rows = std::max<long long>(1, (1LL << 28) / nlist);
@@ -1694,6 +1694,86 @@ int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, floa
   return GB200_OK;
 }
 
+// ---- encode (stage 1 of Add) ---------------------------------------------------------------------------
+// rows already on the device (x_stride floats per row, x_stride <= d); outputs to host
+static int encode_dev(gb200_index *ix, SearchCtx &c, int64_t n, const float *d_x, int x_stride, int32_t *list_no,
+                      uint8_t *codes) {
+  const int d = ix->p.d, M = ix->p.nsubvector;
+  const int64_t CH = 1 << 17;
+  for (int64_t s0 = 0; s0 < n; s0 += CH) {
+    const int m = (int)std::min<int64_t>(CH, n - s0);
+    const float *rows = d_x + (size_t)s0 * x_stride;
+    if (x_stride != d) {  // ConvertVectorDim: zero-pad to d for the distance producer
+      CKI(c.ws_xq.ensure((size_t)m * d * sizeof(float)));
+      CK(cudaMemsetAsync(c.ws_xq.p, 0, (size_t)m * d * sizeof(float), c.stream));
+      CK(cudaMemcpy2DAsync(c.ws_xq.p, (size_t)d * sizeof(float), rows, (size_t)x_stride * sizeof(float),
+                           (size_t)x_stride * sizeof(float), m, cudaMemcpyDeviceToDevice, c.stream));
+      rows = c.ws_xq.as<float>();
+    }
+    const int stride = x_stride != d ? d : x_stride;
+    CKI(c.ws_keys.ensure((size_t)m * sizeof(int)));
+    CKI(c.ws_cdis.ensure((size_t)m * sizeof(float)));
+    CKI(coarse_dev(ix, c, m, rows, 1, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
+    CKI(c.ws_cand.ensure((size_t)m * M));
+    CK(launch_pq_encode(rows, stride, c.ws_keys.as<int>(), ix->d_cent, ix->d_pq, m, d, M, ix->dsub, 1,
+                        c.ws_cand.as<uint8_t>(), c.stream));
+    c.launches++;
+    CK(cudaMemcpyAsync(list_no + s0, c.ws_keys.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(codes + (size_t)s0 * M, c.ws_cand.p, (size_t)m * M, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+  }
+  ix->launches += c.launches;
+  c.launches = 0;
+  return GB200_OK;
+}
+
+int gb200_ivfpq_encode(gb200_index *ix, int64_t n, const float *x, int x_dim, int32_t *list_no, uint8_t *codes) {
+  if (!ix || ix->kind != 0 || n < 0 || x_dim <= 0 || x_dim > ix->p.d || (n > 0 && (!x || !list_no || !codes)))
+    return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n == 0) return GB200_OK;
+  CKI(use_device(ix));
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  SearchCtx &c = *s.c;
+  const int64_t CH = 1 << 17;
+  for (int64_t s0 = 0; s0 < n; s0 += CH) {
+    const int64_t m = std::min<int64_t>(CH, n - s0);
+    CKI(c.ws_flat.ensure((size_t)m * x_dim * sizeof(float)));
+    CK(cudaMemcpyAsync(c.ws_flat.p, x + (size_t)s0 * x_dim, (size_t)m * x_dim * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    CKI(encode_dev(ix, c, m, c.ws_flat.as<float>(), x_dim, list_no + s0, codes + (size_t)s0 * ix->p.nsubvector));
+  }
+  return GB200_OK;
+}
+
+int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no, uint8_t *codes) {
+  if (!ix || ix->kind != 0 || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n == 0) return GB200_OK;
+  const int M = ix->p.nsubvector, rd = ix->p.raw_d;
+  // the raw rows first (re-rank and flat read them; the encode below reads them from the device store)
+  CKI(gb200_upload_raw(ix, first_vid, n, x));
+  std::vector<int32_t> ln_own;
+  std::vector<uint8_t> cd_own;
+  if (!list_no) {
+    ln_own.resize((size_t)n);
+    list_no = ln_own.data();
+  }
+  if (!codes) {
+    cd_own.resize((size_t)n * M);
+    codes = cd_own.data();
+  }
+  {
+    CKI(use_device(ix));
+    SearchScope s(ix);  // shared hold: the raw store cannot be replaced while the rows are read
+    if (!s.c) return GB200_ECUDA;
+    CKI(encode_dev(ix, *s.c, n, ix->d_raw + (size_t)first_vid * rd, rd, list_no, codes));
+  }
+  std::vector<int64_t> vids((size_t)n);
+  for (int64_t i = 0; i < n; i++) vids[i] = first_vid + i;
+  return gb200_ivfpq_append(ix, n, list_no, vids.data(), codes);
+}
+
 // ---- flat ----------------------------------------------------------------------------------------
 // x - tf32(x) and |x|^2 of the raw rows [aux_n, rows), kept next to the raw store once a batched flat search needs them.
 // Index-level state shared by all searches: built under aux_mu on the caller's stream, which is then drained so that
@@ -1743,9 +1823,8 @@ static int flat_tc_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, 
   CKI(ensure_raw_aux(ix, c, N));
   CKI(c.ws_xs.ensure((size_t)n * d * sizeof(float)));
   CKI(c.ws_xn.ensure((size_t)n * sizeof(float)));
-  CK(launch_tf32_residual(d_xq, c.ws_xs.as<float>(), (size_t)n * d, c.stream));
-  CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
-  c.launches += 2;
+  CK(launch_rows_prep(d_xq, n, d, c.ws_xn.as<float>(), c.ws_xs.as<float>(), c.stream));
+  c.launches += 1;
   long long nc_max = ((1LL << 26) / n) & ~127LL;  // distance tile <= 256 MB
   if (nc_max < 1024) nc_max = 1024;
   if (ix->tune.flat_chunk_rows > 0) nc_max = std::max(1024LL, ix->tune.flat_chunk_rows & ~127LL);  // tests: force many chunks

@@ -119,6 +119,8 @@ cudaError_t launch_compact_lists(const CompactParams &P, int n_lists, cudaStream
 
 // K1 — coarse quantiser: dist[n][nlist] = |q|^2 + |c|^2 - 2 q.c (clamped at 0), then top-nprobe
 cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st);
+// |x|^2 and x - tf32(x) of every row in one pass (the query side of the tensor-core distance producer)
+cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st);
 cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,
                                const float *cent_norm, int n, int nlist, int d, float *dist,
                                cudaStream_t st);
@@ -135,6 +137,11 @@ cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe
 bool coarse_select_cmin_usable(int nlist, int nprobe);
 cudaError_t launch_coarse_select_cmin(const float *dist, const float *cmin, int cmin_pitch, int n, int nlist, int nprobe,
                                       int *keys, float *coarse_dis, cudaStream_t st);
+
+// K5 — encode half of Add (encode.cu): residual against the assigned centroid + PQ argmin per sub-quantiser, in faiss'
+// own arithmetic.  x rows are x_stride floats wide (columns beyond it read as zero), keys from the coarse stage.
+cudaError_t launch_pq_encode(const float *x, int x_stride, const int *keys, const float *centroids, const float *pq,
+                             long long n, int d, int M, int dsub, int by_residual, uint8_t *codes, cudaStream_t st);
 
 // K3 — merge the per-split survivors, optional exact re-rank, score window, top-k
 struct RerankParams {

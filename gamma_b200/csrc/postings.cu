@@ -241,6 +241,29 @@ __global__ void row_norms_kernel(const float *x, int rows, int d, float *out) {
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(GB_FULL, s, o);
   if (lane == 0) out[r] = s;
 }
+// |x|^2 (same summation order as row_norms_kernel) and x - tf32(x) of every row in ONE pass: the two operands the
+// tensor-core distance producer needs next to the rows themselves (one launch instead of two on the search path)
+__global__ void rows_prep_kernel(const float *x, int rows, int d, float *norms, float *small) {
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  int lane = threadIdx.x & 31;
+  const float *p = x + (size_t)r * d;
+  float *q = small + (size_t)r * d;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = p[i];
+    s = fmaf(v, v, s);
+    q[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(GB_FULL, s, o);
+  if (lane == 0) norms[r] = s;
+}
+cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  rows_prep_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, d, norms, small);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   row_norms_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, d, out);

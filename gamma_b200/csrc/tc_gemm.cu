@@ -31,6 +31,8 @@ constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_big, A_small, B_big, 
 constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, 64 columns each
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;    // TMA warp + MMA warp + epilogue warps
 constexpr int TC_TMEM_COLS = 128;                     // fp32 accumulator: 128 lanes x 128 columns
+constexpr int TC_TR_PITCH = 20;                       // epilogue transpose strip: 16 columns + 4 pad (16-byte rows)
+constexpr int TC_TR_FLOATS = 32 * TC_TR_PITCH + 64;   // per epilogue warp: the strip + |y|^2 of its 64 columns
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t *bar, int count) {
@@ -109,7 +111,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
   uint64_t *tmem_full = empty + TC_STAGES;   // [2]
   uint64_t *tmem_empty = tmem_full + 2;      // [2]
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-  float *tr_all = reinterpret_cast<float *>(tmem_ptr + 4);  // TC_EPI_WARPS x 32 x 33 floats
+  float *tr_all = reinterpret_cast<float *>(tmem_ptr + 4);  // TC_EPI_WARPS x TC_TR_FLOATS, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (P.M + TC_BM - 1) / TC_BM, tiles_n = (P.N + TC_BN - 1) / TC_BN;
@@ -187,76 +189,91 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_big, const __gri
     }
   } else {
     // ===== epilogue warps 2..9: TMEM lanes (warp % 4) * 32 .. + 31 (the hardware ties a warp to that lane quarter);
-    // two warps share a quarter and take 64 of the tile's 128 columns each — with K = 128 (coarse quantiser) the
-    // tile's 48 MMAs take ~3.2k cycles and four epilogue warps (one per scheduler) could not drain 64 KB in that time
+    // two warps share a quarter and take 64 of the tile's 128 columns each.  Everything arithmetic happens in the
+    // accumulator's own layout (lane = row, 16 columns per tcgen05.ld): |q|^2 is lane-local, the 16 |y|^2 come as four
+    // broadcast LDS.128 from a per-warp strip, and the minimum over the row's 32-column chunk is a lane-local running
+    // min — ~4 instructions per element.  The tile then goes through a padded shared-memory transpose with 128-bit
+    // accesses both ways so that global stores are whole 64-byte row segments (profiles/r02f: the previous epilogue
+    // — scalar transpose, a shuffle, a REDUX and 64-bit address arithmetic per element, ~34 instructions per element on
+    // two warps per scheduler — took ~10 k cycles per tile against ~4 k for the tile's MMAs).
     const int quarter = warp & 3;
     const int col_half = (warp - 2) >> 2;  // 0: columns 0..63, 1: columns 64..127
+    float *tr = tr_all + (warp - 2) * TC_TR_FLOATS;  // [32 rows][TC_TR_PITCH] transpose strip, then 64 floats of |y|^2
+    float *bn_w = tr + 32 * TC_TR_PITCH;
+    const float INF = __int_as_float(0x7f800000);
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, i++) {
       const int tile_m = t % tiles_m, tile_n = t / tiles_m;
       const int as = i & 1, ause = i >> 1;
+      const int row0 = tile_m * TC_BM + quarter * 32;  // this warp's 32 rows; lane l holds row row0 + l
+      const int colw = tile_n * TC_BN + col_half * (TC_BN / 2);  // this warp's 64 columns
+      const float an_mine = (P.l2 && P.a_norm && row0 + lane < P.M) ? P.a_norm[row0 + lane] : 0.f;
+      if (P.l2) {  // |y|^2 of the warp's columns; +inf beyond N keeps those columns out of the chunk minima
+        __syncwarp();
+        bn_w[lane] = (P.b_norm && colw + lane < P.N) ? __ldg(P.b_norm + colw + lane) : (colw + lane < P.N ? 0.f : INF);
+        bn_w[32 + lane] =
+            (P.b_norm && colw + 32 + lane < P.N) ? __ldg(P.b_norm + colw + 32 + lane) : (colw + 32 + lane < P.N ? 0.f : INF);
+        __syncwarp();
+      }
       tc_mbar_wait(&tmem_full[as], ause & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row0 = tile_m * TC_BM + quarter * 32;          // this warp's 32 rows; lane l holds row row0 + l
-      const float an_mine = (P.l2 && P.a_norm && row0 + lane < P.M) ? P.a_norm[row0 + lane] : 0.f;
-      float *tr = tr_all + (warp - 2) * (32 * 33);              // per-warp 32 x 32 transpose tile (+1 pad)
+      float cmin_run = INF;
 #pragma unroll 1
-      for (int c0 = col_half * (TC_BN / 2); c0 < (col_half + 1) * (TC_BN / 2); c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_TMEM_COLS + c0);
+      for (int c0 = 0; c0 < TC_BN / 2; c0 += 16) {
+        uint32_t v[16];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TC_TMEM_COLS + col_half * (TC_BN / 2) + c0);
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= (col_half + 1) * (TC_BN / 2)) {  // this warp's share of the accumulator is in registers: hand it back
+        if (c0 + 16 >= TC_BN / 2) {  // this warp's share of the accumulator is in registers: hand it back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
         }
-        // transpose through shared memory so that a warp stores 32 consecutive columns of ONE row (128 B)
-        // per instruction instead of 16 B of 32 different rows; conflict-free both ways thanks to the pad
+        float r[16];
+        if (P.l2) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) tr[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int col = tile_n * TC_BN + c0 + lane;
-        const float bn = (P.l2 && P.b_norm && col < P.N) ? __ldg(P.b_norm + col) : 0.f;
-        float *dst = P.out + (size_t)row0 * P.ldo + col;
-        if (P.cmin) {
-          // same stores, plus the minimum of the 32 columns of every row: L2 distances are clamped at 0, so their bit
-          // patterns order like unsigned integers (NaN sorts above +inf and loses) and one REDUX per row does it
-          uint32_t mine = 0x7f800000u;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; rr++) {
-            const float acc = tr[rr * 33 + lane];
-            const float an = __shfl_sync(0xffffffffu, an_mine, rr);
-            float r = an + bn - 2.f * acc;
-            r = r < 0.f ? 0.f : r;
-            const bool ok = col < P.N;
-            if (row0 + rr < P.M && ok) dst[(size_t)rr * P.ldo] = r;
-            const uint32_t m = __reduce_min_sync(0xffffffffu, ok ? __float_as_uint(r) : 0x7f800000u);
-            if (lane == rr) mine = m;
-          }
-          if (row0 + lane < P.M)
-            P.cmin[(size_t)(row0 + lane) * P.cmin_pitch + ((tile_n * TC_BN + c0) >> 5)] = __uint_as_float(mine);
-        } else {
-#pragma unroll 8
-          for (int rr = 0; rr < 32; rr++) {
-            const float acc = tr[rr * 33 + lane];
-            const float an = __shfl_sync(0xffffffffu, an_mine, rr);
-            float r = acc;
-            if (P.l2) {
-              r = an + bn - 2.f * acc;
-              r = r < 0.f ? 0.f : r;
+          for (int j4 = 0; j4 < 4; j4++) {
+            const float4 bn = *reinterpret_cast<const float4 *>(bn_w + c0 + j4 * 4);  // broadcast
+            const float b[4] = {bn.x, bn.y, bn.z, bn.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              // (|q|^2 + |y|^2) - 2 <q, y>, one rounding each, as faiss computes it; negative -> 0, NaN stays NaN
+              float x = fmaf(-2.f, __uint_as_float(v[j4 * 4 + j]), an_mine + b[j]);
+              asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(x));
+              r[j4 * 4 + j] = x;
+              cmin_run = fminf(cmin_run, x);  // drops NaN
             }
-            if (row0 + rr < P.M && col < P.N) dst[(size_t)rr * P.ldo] = r;
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) r[j] = __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++)
+          *reinterpret_cast<float4 *>(tr + lane * TC_TR_PITCH + j4 * 4) = make_float4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
+        __syncwarp();
+        // 4 lanes per row, 8 rows per instruction: every store is a 64-byte row segment
+        const int pr = lane >> 2, pc = (lane & 3) * 4;
+        const int col = colw + c0 + pc;
+        float *dst = P.out + (size_t)(row0 + pr) * P.ldo + col;
+        const size_t step = (size_t)8 * P.ldo;
+        const bool col_ok = col < P.N;  // N % 4 == 0: a 4-column piece is inside or outside as a whole
+#pragma unroll
+        for (int tq = 0; tq < 4; tq++) {
+          const float4 o = *reinterpret_cast<const float4 *>(tr + (tq * 8 + pr) * TC_TR_PITCH + pc);
+          if (col_ok && row0 + tq * 8 + pr < P.M) *reinterpret_cast<float4 *>(dst) = o;
+          dst += step;
         }
         __syncwarp();
+        if (P.cmin && (c0 & 16)) {  // a 32-column chunk is complete
+          if (row0 + lane < P.M) P.cmin[(size_t)(row0 + lane) * P.cmin_pitch + ((colw + c0 - 16) >> 5)] = cmin_run;
+          cmin_run = INF;
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -326,12 +343,14 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
   if (M <= 0 || N <= 0) return cudaSuccess;
   if ((K & 3) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)a_small & 15) || ((uintptr_t)b_small & 15))
     return cudaErrorInvalidValue;
+  // the epilogue stores 16-byte pieces: rows of out start on 16-byte boundaries and hold N rounded up to 4 columns
+  if ((ldo & 3) || ((uintptr_t)out & 15) || ldo < ((N + 3) & ~3)) return cudaErrorInvalidValue;
   CUtensorMap ma, mas, mb, mbs;
   if (!make_map(&ma, a, M, K) || !make_map(&mas, a_small, M, K) || !make_map(&mb, b, N, K) ||
       !make_map(&mbs, b_small, N, K))
     return cudaErrorNotSupported;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * sizeof(uint64_t) + 16 +
-                      TC_EPI_WARPS * 32 * 33 * sizeof(float) + 1024;
+                      TC_EPI_WARPS * TC_TR_FLOATS * sizeof(float) + 1024;
   {  // per device and cheap: set on every launch (an index may live on any device)
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

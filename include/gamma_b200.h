@@ -122,6 +122,17 @@ int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped);
  * happened to it: the new content goes into a fresh region and is swapped in by publication, searches keep running. */
 int gb200_ivfpq_replace_list(gb200_index *ix, int32_t list_no, int64_t n, const int64_t *ids, const uint8_t *codes);
 
+/* ---- encode on the device: stage 1 of GammaIVFPQIndex::Add (index/impl/gamma_index_ivfpq.cc:424-476) —
+ * quantizer->assign (the tensor-core coarse stage with nprobe = 1), compute_residuals, pq.compute_codes with faiss'
+ * own sub-distance arithmetic (codes are bit-identical to the CPU engine's for nsubvector slices narrower than 16
+ * floats; an assignment can differ only where two centroids are at rounding distance).
+ * x: n rows of x_dim floats, x_dim <= d (columns beyond x_dim are zero: ConvertVectorDim).  list_no n, codes n x M. */
+int gb200_ivfpq_encode(gb200_index *ix, int64_t n, const float *x, int x_dim, int32_t *list_no, uint8_t *codes);
+/* the whole Add for vids first_vid .. first_vid + n - 1: upload the raw rows (n x raw_d), encode them on the device,
+ * append the postings (AddKeys semantics as gb200_ivfpq_append).  list_no / codes (may be NULL) return what was
+ * appended, for a host that keeps its own copy of the lists (Dump).                                                  */
+int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no, uint8_t *codes);
+
 /* ---- raw vectors: the read side of VectorReader::Gets / RawVector::GetVectorHeader
  * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are
  * implicit = first_vid .. first_vid+n-1; re-upload of an existing range = UpdateToStore. */
