@@ -41,9 +41,41 @@ WORKLOADS = {
                desc="IVFPQ d=128 nlist=16384 PQ64x8 10M vecs nprobe=32 batch=1024 + range-filter bitmap (30% pass) + 1% deleted"),
     "c2": dict(N=1_000_000, d=128, nlist=4096, M=32, nprobe=16, batch=256, filt=False,
                desc="IVFPQ d=128 nlist=4096 PQ32x8 1M vecs nprobe=16 batch=256"),
+    # BASELINE.json configs[4]: built ON the device (seeded torch mixture generated chunk by chunk, trained with the setup
+    # tooling, encoded + appended by gb200_ivfpq_add_stored) — 51 GB of raw vectors never touch the host
+    "c5": dict(N=100_000_000, d=128, nlist=65536, M=32, nprobe=64, batch=4096, filt=False, device_build=True,
+               cpu_N=10_000_000,
+               desc="IVFPQ d=128 nlist=65536 PQ32x8 100M vecs nprobe=64 batch=4096 recall_num=100 rerank k=10 L2"),
+    # BASELINE.json configs[3]: the tensor-core flat path
+    "c4": dict(kind="flat", N=5_000_000, d=768, batch=512, metric="InnerProduct",
+               desc="FLAT InnerProduct d=768 5M vecs batch=512 k=10 (tcgen05 3xTF32 candidates, exact fp32 re-score)"),
 }
 K_TOP, RECALL_NUM = 10, 100
 METRIC = "QPS @ recall@10 (d=128, 10M vecs, nprobe=32, batch=1024)"
+
+
+class DeviceData:
+    """Seeded mixture of Gaussians generated ON the device, chunk by chunk; chunk [s, e) always comes out the same (its
+    generator is seeded from s), so the rows can be regenerated for the ground truth and for the CPU engine's subset."""
+    CHUNK = 1_000_000
+
+    def __init__(self, d, dev, normalize=False, n_clusters=4096, seed=20240601, spread=0.3):
+        import torch
+        self.d, self.dev, self.normalize, self.seed, self.spread = d, dev, normalize, seed, spread
+        g = torch.Generator(device=dev).manual_seed(seed + 7919)
+        self.centres = torch.randn(n_clusters, d, device=dev, generator=g)
+
+    def rows(self, s, e, salt=0):
+        import torch
+        g = torch.Generator(device=self.dev).manual_seed(self.seed + 1000003 * salt + s)
+        a = torch.randint(0, self.centres.shape[0], (e - s,), device=self.dev, generator=g)
+        x = self.centres[a] + self.spread * torch.randn(e - s, self.d, device=self.dev, generator=g)
+        if self.normalize:
+            x = torch.nn.functional.normalize(x, dim=1)
+        return x.contiguous()
+
+    def queries(self, n, rank):
+        return self.rows(0, n, salt=17 + rank)
 
 
 def log(*a):
@@ -309,6 +341,318 @@ def time_reference(r, w, xq, filters, n_queries, reps, warm=1):
     return n_queries / float(np.median(times)), cores, times, I
 
 
+def build_on_device(w, local, rank, with_lib, scale=1.0):
+    """Workloads too large to stage on the host (c5): rows are generated on the device chunk by chunk (DeviceData),
+    the quantizers are trained with the setup tooling on the first rows, and — with_lib — every chunk goes
+    gb200_upload_raw_dev -> gb200_ivfpq_add_stored (device encode + append).  Returns the index (or None), the
+    trained state, and host copies of the first cpu_N rows with their list numbers / codes for the CPU engine."""
+    import torch
+    from gamma_b200 import builder
+    dev = torch.device("cuda:%d" % local)
+    N, d, nlist, M, cpu_N = w["N"], w["d"], w["nlist"], w["M"], w["cpu_N"]
+    if scale != 1.0:  # dev only
+        N, nlist = max(int(N * scale), 200_000), max(256, int(nlist * scale))
+        cpu_N = min(cpu_N, N)
+    data = DeviceData(d, dev)
+    t = time.time()
+    train_n = min(N, 39 * nlist)
+    xt = torch.cat([data.rows(s, min(s + DeviceData.CHUNK, train_n)) for s in range(0, train_n, DeviceData.CHUNK)])
+    coarse_t = builder.kmeans(xt, nlist, 10, 1234)
+    a = builder._assign(xt, coarse_t, (coarse_t * coarse_t).sum(1))
+    sub = slice(0, min(train_n, 400_000))  # 256 points per PQ centroid are plenty (faiss caps the training set likewise)
+    pq_t = builder.train_pq((xt[sub] - coarse_t[a[sub]]).contiguous(), M, 25, 1235)
+    del xt, a
+    torch.cuda.empty_cache()
+    coarse, pq = coarse_t.cpu().numpy(), pq_t.cpu().numpy()
+    log("trained %d coarse centroids + PQ%dx8 on %d rows in %.1fs" % (nlist, M, train_n, time.time() - t))
+    ix = None
+    if with_lib:
+        from gamma_b200 import api
+        ix = api.B200IVFPQ(local)
+        model_json = json.dumps({"ncentroids": nlist, "nsubvector": M, "metric_type": "L2", "nprobe": w["nprobe"]})
+        if ix.Init(model_json, d) != 0:
+            raise SystemExit("gb200 create failed: %s" % api.lib().gb200_last_error().decode())
+        ix.set_quantizers(coarse, pq)
+    want_cpu = rank == 0
+    xb_cpu = np.empty((cpu_N, d), np.float32) if want_cpu else None
+    ln_cpu = np.empty(cpu_N, np.int32) if want_cpu else None
+    cd_cpu = np.empty((cpu_N, M), np.uint8) if want_cpu else None
+    t = time.time()
+    for s in range(0, N, DeviceData.CHUNK):
+        e = min(N, s + DeviceData.CHUNK)
+        if not with_lib and s >= cpu_N:
+            break
+        x = data.rows(s, e)
+        torch.cuda.synchronize()  # the library copies on its own stream: the rows must exist first
+        keep = want_cpu and s < cpu_N
+        if with_lib:
+            ix.upload_raw_dev(x.data_ptr(), e - s, first_vid=s)
+            got = ix.add_stored(s, e - s, want_codes=keep)
+        else:
+            ln_t, cd_t = builder.encode(x, coarse_t, pq_t)
+            got = (ln_t.cpu().numpy(), cd_t.cpu().numpy())
+        if keep:
+            m = min(e, cpu_N) - s
+            xb_cpu[s:s + m] = x[:m].cpu().numpy()
+            ln_cpu[s:s + m] = got[0][:m]
+            cd_cpu[s:s + m] = got[1][:m]
+        del x
+    log("%s %d rows in %.1fs" % ("uploaded + device-encoded + appended" if with_lib else "encoded the CPU subset of", N, time.time() - t))
+    return dict(ix=ix, data=data, coarse=coarse, pq=pq, xb_cpu=xb_cpu, ln_cpu=ln_cpu, cd_cpu=cd_cpu, N=N, nlist=nlist, cpu_N=cpu_N)
+
+
+def ground_truth_regenerated(data, N, xq_t, k):
+    """exact top-k over rows regenerated chunk by chunk (the database exists only inside the library)"""
+    import torch
+    n = xq_t.shape[0]
+    best_d = torch.full((n, k), float("inf"), device=xq_t.device)
+    best_i = torch.full((n, k), -1, dtype=torch.int64, device=xq_t.device)
+    qn = (xq_t * xq_t).sum(1, keepdim=True)
+    for s in range(0, N, DeviceData.CHUNK):
+        xs = data.rows(s, min(N, s + DeviceData.CHUNK))
+        dist = qn + (xs * xs).sum(1)[None, :] - 2.0 * (xq_t @ xs.t())
+        d_, i_ = dist.topk(k, dim=1, largest=False)
+        cat_d, cat_i = torch.cat([best_d, d_], 1), torch.cat([best_i, i_ + s], 1)
+        sel = cat_d.topk(k, dim=1, largest=False)
+        best_d, best_i = sel.values, torch.gather(cat_i, 1, sel.indices)
+    return best_i
+
+
+def main_flat(args, w, rank, world, local, device):
+    """--workload c4: FLAT InnerProduct d=768, 5M vectors, batch 512, k=10 — the tensor-core flat path (tcgen05 3xTF32
+    chunked GEMM -> running candidate select -> exact fp32 re-score).  Database generated on the device and replicated
+    per rank; queries sharded by rank (weak scaling), one NCCL all-gather of the packed top-k for N > 1.
+    roofline: bound "tensor" for the GEMM kernel, achieved = ALGORITHMIC flops 2 n N d over the CUDA-event
+    time of the search; peak = TF32 dense = measured bf16 / 2."""
+    import torch
+    N, d, n, metric = w["N"], w["d"], w["batch"], w["metric"]
+    if args.scale != 1.0:
+        N = max(int(N * args.scale), 20000)
+    ip = metric != "L2"
+    k = K_TOP
+    fj = json.dumps({"metric_type": metric, "parallel_on_queries": 0})
+    flat_metric = "QPS (FLAT %s d=%d, %d vecs, batch=%d, k=%d)" % (metric, d, N, n, k)
+    # ------------------------------------------------------------------ reference arm: GammaFLATIndex on the host cores
+    if args.impl == "reference":
+        from oracle import ref
+        data = DeviceData(d, torch.device(device), normalize=ip) if torch.cuda.is_available() else None
+        if data is None:
+            raise SystemExit("bench.py --workload c4 generates its rows on the device: needs a GPU")
+        t = time.time()
+        r = ref.RefIndex(d, "FLAT", json.dumps({"metric_type": metric}), indexing_size=N, bitmap_bits=max(2 * N, 1024))
+        for s in range(0, N, DeviceData.CHUNK):
+            r.add_raw(data.rows(s, min(N, s + DeviceData.CHUNK)).cpu().numpy())
+        xq = data.queries(n, 0).cpu().numpy()
+        log("reference FLAT engine loaded with %d rows in %.1fs" % (N, time.time() - t))
+        ref.set_threads(host_cores())
+        nq = min(args.cpu_queries, 16, n)
+        ts = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            r.search(xq[:nq], k, fj)
+            if it >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(ts))
+        val = nq / (ms / 1e3)
+        out = dict(metric=flat_metric, value=val, unit="queries/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                   impl="reference", config=dict(workload=w["desc"], N=N, queries_per_step=nq),
+                   cpu_baseline=dict(value=val, unit="queries/s", cores=ref.max_threads(), kind="reference",
+                                     sample="%d of the %d-query batch per step, %d steps, parallel_on_queries=0 "
+                                            "(OpenMP over the database, gamma_index_flat.cc:250-291)" % (nq, n, args.steps)),
+                   e2e=dict(value=val, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(out), flush=True)
+        return 0
+    # ------------------------------------------------------------------ our arm
+    from gamma_b200 import api
+    from gamma_b200 import dist as gdist
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device(device)
+    data = DeviceData(d, dev, normalize=ip)
+    ix = api.B200FLAT(local)
+    if ix.Init(json.dumps({"metric_type": metric}), d) != 0:
+        raise SystemExit("gb200 flat create failed: %s" % api.lib().gb200_last_error().decode())
+    t = time.time()
+    for s in range(0, N, DeviceData.CHUNK):
+        x = data.rows(s, min(N, s + DeviceData.CHUNK))
+        torch.cuda.synchronize()
+        ix.upload_raw_dev(x.data_ptr(), x.shape[0], first_vid=s)
+    xq_d = data.queries(n, rank)
+    torch.cuda.synchronize()
+    log("database %d x %d on the device in %.1fs, %.2f GB" % (N, d, time.time() - t, ix.GetTotalMemBytes() / 1e9))
+    out_d, D_d, I_d = gdist.packed_topk_buffer(n, k, dev)
+    out_bytes = out_d.numel()
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        import torch.distributed as dist
+        out_all = torch.empty(world * out_bytes, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        rc_ = ix.search_dev(xq_d.data_ptr(), n, k, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream, metric=metric)
+        assert rc_ == 0, api.lib().gb200_last_error()
+        if world > 1:
+            dist.all_gather_into_tensor(out_all, out_d)
+
+    step_dev()
+    torch.cuda.synchronize()
+    I_ours, D_ours = I_d.cpu().numpy().copy(), D_d.cpu().numpy().copy()
+    # exact check against an fp32 brute force over regenerated rows (first 32 queries)
+    nc = min(32, n)
+    best_d = torch.full((nc, k), -float("inf") if ip else float("inf"), device=dev)
+    best_i = torch.full((nc, k), -1, dtype=torch.int64, device=dev)
+    for s in range(0, N, DeviceData.CHUNK):
+        xs = data.rows(s, min(N, s + DeviceData.CHUNK))
+        sc = xq_d[:nc] @ xs.t()
+        if not ip:
+            sc = (xq_d[:nc] * xq_d[:nc]).sum(1, keepdim=True) + (xs * xs).sum(1)[None, :] - 2.0 * sc
+        d_, i_ = sc.topk(k, dim=1, largest=ip)
+        cd, ci = torch.cat([best_d, d_], 1), torch.cat([best_i, i_ + s], 1)
+        sel = cd.topk(k, dim=1, largest=ip)
+        best_d, best_i = sel.values, torch.gather(ci, 1, sel.indices)
+    ids_ok = float((best_i.cpu().numpy() == I_ours[:nc]).mean())
+    rel = float(((best_d - D_d[:nc]).abs() / best_d.abs().clamp(min=1e-6)).max())
+    log("vs exact fp32 brute force on %d queries: ids identical %.4f, max rel distance error %.2e" % (nc, ids_ok, rel))
+    torch.cuda.empty_cache()
+
+    ix.set_profiling(True)
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)
+    sampler.start()
+    for _ in range(3):
+        step_dev()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ix.launch_count()
+    mark0 = sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()  # the database (15 GB, twice with its TF32 companion) is far larger than L2: no flush needed
+    e1.record(stream)
+    torch.cuda.synchronize()
+    mark1 = sampler.mark()
+    launches = ix.launch_count() - launches0 + (args.steps if world > 1 else 0)
+    if world > 1:
+        dist.barrier()
+    for _ in range(3):
+        step_dev()
+    torch.cuda.synchronize()
+    clocks = sampler.stop(mark0, mark1)
+    tm = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item()) / args.steps
+    value = world * n / (ms / 1e3)
+
+    # ---- e2e through the host C-ABI call (pinned host buffers, H2D + D2H inside); N > 1: + exchange + D2H of the gather
+    xq_pin = xq_d.cpu().pin_memory()
+    D_pin = torch.empty(n, k, dtype=torch.float32).pin_memory()
+    I_pin = torch.empty(n, k, dtype=torch.int64).pin_memory()
+    sp = api._Base._sp(metric, -1, 0, 0, -api.FLT_MAX, api.FLT_MAX)
+    if world > 1:
+        out_all_pin = torch.empty(world * out_bytes, dtype=torch.uint8).pin_memory()
+        xq_stage = torch.empty_like(xq_d)
+
+    def step_host():
+        if world == 1:
+            rc_ = api.lib().gb200_flat_search(ix.h, n, xq_pin.data_ptr(), k, ctypes.byref(sp), None, 0, D_pin.data_ptr(),
+                                              I_pin.data_ptr())
+            assert rc_ == 0, api.lib().gb200_last_error()
+            return
+        xq_stage.copy_(xq_pin, non_blocking=True)
+        rc_ = ix.search_dev(xq_stage.data_ptr(), n, k, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream, metric=metric)
+        assert rc_ == 0, api.lib().gb200_last_error()
+        dist.all_gather_into_tensor(out_all, out_d)
+        out_all_pin.copy_(out_all, non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(2):
+        step_host()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = world * n * args.steps / float(te.item())
+    if world == 1:
+        assert np.array_equal(I_pin.numpy(), I_ours), "host-API result differs from device-API result"
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+    hbm_peak, _ = measured_peaks()
+    flop_alg = 2.0 * n * N * d
+    roofline = dict(bound="tensor", achieved=flop_alg / (ms / 1e3) / 1e12, peak=tf32_peak, unit="TFLOP/s",
+                    frac=flop_alg / (ms / 1e3) / 1e12 / tf32_peak, traffic=None,
+                    kernel="tc_gemm_tf32x3_kernel (one launch per database chunk; time = CUDA events around the whole search)",
+                    algorithmic_flop_per_step=flop_alg, executed_tensor_flop_per_step=3.0 * flop_alg,
+                    hbm_algorithmic_bytes=float(N) * d * 4, hbm_achieved_gbs=float(N) * d * 4 / (ms / 1e3) / 1e9, hbm_peak=hbm_peak,
+                    peak_source="TF32 dense = measured bf16 / 2 (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)")
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle import ref
+            t = time.time()
+            r = ref.RefIndex(d, "FLAT", json.dumps({"metric_type": metric}), indexing_size=N, bitmap_bits=max(2 * N, 1024))
+            for s in range(0, N, DeviceData.CHUNK):
+                r.add_raw(data.rows(s, min(N, s + DeviceData.CHUNK)).cpu().numpy())
+            log("reference FLAT engine loaded with the same %d rows in %.1fs" % (N, time.time() - t))
+            ref.set_threads(host_cores())
+            nq = min(args.cpu_queries, 16, n)
+            xq_h = xq_d.cpu().numpy()
+            ts = []
+            I_cpu = None
+            for it in range(3):
+                t0 = time.perf_counter()
+                D_cpu, I_cpu = r.search(xq_h[:nq], k, fj)
+                if it >= 1:
+                    ts.append(time.perf_counter() - t0)
+            cpu = dict(value=nq / float(np.median(ts)), unit="queries/s", cores=ref.max_threads(), kind="reference",
+                       sample="first %d queries of the batch over all %d rows, median of 2 runs after 1 warm-up, "
+                              "parallel_on_queries=0" % (nq, N),
+                       ids_identical_frac=float((I_cpu == I_ours[:nq]).mean()),
+                       distances_identical_frac=float((D_cpu == D_ours[:nq]).mean()))
+            r.close()
+        except Exception as e:
+            cpu = dict(value=None, unit="queries/s", cores=None, kind="reference", sample="failed: %r" % (e,))
+    out = dict(metric=flat_metric, value=value, unit="queries/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f32 (3xTF32 tensor-core candidates, exact fp32 re-score)", data="synthetic (device-generated mixture)",
+               config=dict(workload=w["desc"], N=N, d=d, batch_per_gpu=n, global_batch=world * n, k=k,
+                           parallelism="query-sharded x%d, database replicated, NCCL all-gather of top-k" % world,
+                           l2="database (2 x %.1f GB with its TF32 companion) >> L2: no flush" % (N * d * 4 / 1e9),
+                           scaled_down=args.scale != 1.0),
+               roofline=roofline, cpu_baseline=cpu,
+               e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * d * 4),
+                        d2h_bytes_per_step=int(n * k * 12 * (world if world > 1 else 1))),
+               gpu_launches=int(launches), clocks=clocks,
+               check=dict(queries=nc, ids_identical_frac=ids_ok, max_rel_distance_err=rel))
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,17 +686,33 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(device))
 
-    N, nlist, xb, xq_all = build_dataset(w, args.scale)
-    dist_ctx = (rank, world) if args.impl == "ours" else (0, 1)
-    coarse, pq, list_no, codes = build_index_state(w, N, nlist, xb, device, dist_ctx)
-    filters, dele = make_filter(w, N)
+    if w.get("kind") == "flat":
+        return main_flat(args, w, rank, world, local, device)
+    devb = None
     n = w["batch"]
-    # every rank gets its own batch of fresh queries (weak scaling); rank r uses slice r
-    xq = np.ascontiguousarray(xq_all[(rank % 8) * n:(rank % 8 + 1) * n])
+    if w.get("device_build"):
+        if not have_gpu:
+            raise SystemExit("bench.py --workload %s builds its index on the device: needs a GPU" % args.workload)
+        devb = build_on_device(w, local, rank, with_lib=args.impl == "ours", scale=args.scale)
+        N, nlist = devb["N"], devb["nlist"]
+        coarse, pq = devb["coarse"], devb["pq"]
+        # the CPU engine gets the first cpu_N rows (stated in the JSON line); ours searches all N
+        xb, list_no, codes = devb["xb_cpu"], devb["ln_cpu"], devb["cd_cpu"]
+        filters, dele = [], None
+        xq = devb["data"].queries(n, rank).cpu().numpy()
+    else:
+        N, nlist, xb, xq_all = build_dataset(w, args.scale)
+        dist_ctx = (rank, world) if args.impl == "ours" else (0, 1)
+        coarse, pq, list_no, codes = build_index_state(w, N, nlist, xb, device, dist_ctx)
+        filters, dele = make_filter(w, N)
+        # every rank gets its own batch of fresh queries (weak scaling); rank r uses slice r
+        xq = np.ascontiguousarray(xq_all[(rank % 8) * n:(rank % 8 + 1) * n])
+    N_cpu = devb["cpu_N"] if devb else N
+    cpu_note = (" on the first %d of the %d vectors (same quantizers, lists %.0fx shorter)" % (N_cpu, N, N / N_cpu)) if devb else ""
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
-        r = build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele)
+        r = build_reference(w, N_cpu, nlist, xb, coarse, pq, list_no, codes, dele)
         nq = min(args.cpu_queries, n)
         qps_list = []
         from oracle import ref
@@ -372,9 +732,10 @@ def main():
         out = dict(metric=METRIC, value=val, unit="queries/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                    data="synthetic", impl="reference",
-                   config=dict(workload=w["desc"], N=N, nlist=nlist, queries_per_step=nq, scaled_down=args.scale != 1.0),
+                   config=dict(workload=w["desc"], N=N, nlist=nlist, queries_per_step=nq, scaled_down=args.scale != 1.0 or bool(devb),
+                               cpu_N=N_cpu),
                    cpu_baseline=dict(value=val, unit="queries/s", cores=cores, kind="reference",
-                                     sample="%d of the %d-query batch per step, %d steps, OpenMP over queries" % (nq, n, args.steps)),
+                                     sample="%d of the %d-query batch per step, %d steps, OpenMP over queries%s" % (nq, n, args.steps, cpu_note)),
                    e2e=dict(value=val, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out), flush=True)
         return 0
@@ -382,20 +743,23 @@ def main():
     # ------------------------------------------------------------------ our arm
     from gamma_b200 import api
     t = time.time()
-    model_json = json.dumps({"ncentroids": nlist, "nsubvector": w["M"], "metric_type": "L2", "nprobe": w["nprobe"]})
-    ix = api.B200IVFPQ(local)
-    rc = ix.Init(model_json, w["d"])
-    if rc != 0:
-        raise SystemExit("gb200 create failed: %s" % api.lib().gb200_last_error().decode())
-    ix.set_quantizers(coarse, pq)
-    rc = ix.append(list_no, np.arange(N, dtype=np.int64), codes)
-    assert rc == 0, api.lib().gb200_last_error()
-    for s in range(0, N, 1 << 21):
-        ix.upload_raw(xb[s:s + (1 << 21)], first_vid=s)
-    if dele is not None:
-        ix.set_deleted(dele, True)
-    if filters:
-        ix.set_filters(filters)
+    if devb:
+        ix = devb["ix"]
+    else:
+        model_json = json.dumps({"ncentroids": nlist, "nsubvector": w["M"], "metric_type": "L2", "nprobe": w["nprobe"]})
+        ix = api.B200IVFPQ(local)
+        rc = ix.Init(model_json, w["d"])
+        if rc != 0:
+            raise SystemExit("gb200 create failed: %s" % api.lib().gb200_last_error().decode())
+        ix.set_quantizers(coarse, pq)
+        rc = ix.append(list_no, np.arange(N, dtype=np.int64), codes)
+        assert rc == 0, api.lib().gb200_last_error()
+        for s in range(0, N, 1 << 21):
+            ix.upload_raw(xb[s:s + (1 << 21)], first_vid=s)
+        if dele is not None:
+            ix.set_deleted(dele, True)
+        if filters:
+            ix.set_filters(filters)
     log("device mirror built in %.1fs, %.2f GB" % (time.time() - t, ix.GetTotalMemBytes() / 1e9))
 
     dev = torch.device(device)
@@ -427,12 +791,18 @@ def main():
         vm = filters[0][3].astype(bool).copy()
         vm[dele] = False
         valid_mask = torch.from_numpy(vm).to(dev)
-    xb_t = torch.from_numpy(xb[: min(N, 10_000_000)]).to(dev) if N <= 12_000_000 else None
+    xb_t = torch.from_numpy(xb[: min(N, 10_000_000)]).to(dev) if (N <= 12_000_000 and not devb) else None
     rec_ours = None
+    gt = None
     if xb_t is not None:
         gt = ground_truth(xb_t, xq_d, K_TOP, valid_mask).cpu().numpy()
         rec_ours = recall_at_k(I_ours, gt)
         del xb_t
+        torch.cuda.empty_cache()
+    elif devb:  # exact ground truth for the first 256 queries over regenerated rows
+        nq_gt = min(256, n)
+        gt = ground_truth_regenerated(devb["data"], N, xq_d[:nq_gt], K_TOP).cpu().numpy()
+        rec_ours = recall_at_k(I_ours[:nq_gt], gt)
         torch.cuda.empty_cache()
     log("recall@10 (ours) = %s" % rec_ours)
 
@@ -590,7 +960,7 @@ def main():
     scan_avg_ms = float(np.mean(scan_ms))
     achieved = alg_bytes / (scan_avg_ms / 1e3) / 1e9
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                    kernel=("ivfpq_scan_m32_v%s_kernel" % os.environ.get("GB200_SCAN_VARIANT", "3") if w["M"] == 32 else
+                    kernel=("ivfpq_scan_m32_v3_kernel" if w["M"] == 32 else
                             "ivfpq_scan_m64_kernel" if w["M"] == 64 else
                             "ivfpq_scan_generic_kernel") + " (CUDA events around that one launch on the search stream)",
                     algorithmic_bytes_per_launch=alg_bytes,
@@ -607,15 +977,15 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = build_reference(w, N, nlist, xb, coarse, pq, list_no, codes, dele)
+            r = build_reference(w, N_cpu, nlist, xb, coarse, pq, list_no, codes, dele)
             nq = min(args.cpu_queries, n)
             qps, cores, times, I_cpu = time_reference(r, w, xq, filters, nq, reps=3)
-            agree = float((I_cpu == I_ours[:nq]).mean())
             cpu = dict(value=qps, unit="queries/s", cores=cores, kind="reference",
-                       sample="first %d queries of the batch, median of 3 runs after 1 warm-up, parallel_on_queries=1" % nq,
-                       ids_identical_frac=agree)
-            if rec_ours is not None:
-                cpu["recall_at_10"] = recall_at_k(I_cpu, gt[:nq])
+                       sample="first %d queries of the batch, median of 3 runs after 1 warm-up, parallel_on_queries=1%s" % (nq, cpu_note))
+            if not devb:  # same index on both sides: the ids must be the same
+                cpu["ids_identical_frac"] = float((I_cpu == I_ours[:nq]).mean())
+                if rec_ours is not None:
+                    cpu["recall_at_10"] = recall_at_k(I_cpu, gt[:nq])
             r.close()
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = dict(value=None, unit="queries/s", cores=None, kind="reference", sample="failed: %r" % (e,))

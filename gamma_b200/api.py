@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
         L.gb200_ivfpq_replace_list.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_encode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_add_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_ivfpq_add_stored.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
         L.gb200_sync.argtypes = [C.c_void_p]
@@ -285,6 +286,16 @@ class B200IVFPQ(_Base):
         ln = np.empty(n, np.int32)
         cd = np.empty((n, self.M), np.uint8)
         _check(lib().gb200_ivfpq_add_raw(self.h, int(first_vid), n, x.ctypes.data, ln.ctypes.data, cd.ctypes.data), "add_raw")
+        return ln, cd
+
+    def add_stored(self, first_vid, n, want_codes=False):
+        """encode + append rows [first_vid, first_vid + n) of the device raw store"""
+        if not want_codes:
+            _check(lib().gb200_ivfpq_add_stored(self.h, int(first_vid), int(n), None, None), "add_stored")
+            return None
+        ln = np.empty(n, np.int32)
+        cd = np.empty((n, self.M), np.uint8)
+        _check(lib().gb200_ivfpq_add_stored(self.h, int(first_vid), int(n), ln.ctypes.data, cd.ctypes.data), "add_stored")
         return ln, cd
 
     def replace_list(self, list_no, ids, codes):

@@ -15,6 +15,7 @@ import torch
 def _assign(x, c, c_norm, chunk=65536):
     """argmin_j |x_i - c_j|^2 for rows of x (n,d) against c (k,d)."""
     out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    chunk = max(1024, min(chunk, (1 << 29) // max(1, c.shape[0])))  # keep the distance block around 2 GB
     for s in range(0, x.shape[0], chunk):
         xs = x[s:s + chunk]
         d = c_norm[None, :] - 2.0 * (xs @ c.t())

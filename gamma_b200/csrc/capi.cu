@@ -90,18 +90,15 @@ inline long long roundup32(long long v) { return (v + 31) & ~31LL; }
 // Tuning knobs: environment variables read ONCE at index creation (gb200_reload_tuning re-reads them, for A/B runs);
 // defaults are the measured best.
 struct Tuning {
-  int scan_variant = 3;   // GB200_SCAN_VARIANT: M = 32 scan: 3 = persistent kernel with dynamic items (default), 2 = one CTA per (query, split)
-  int scan_threads = 0;   // GB200_SCAN_THREADS: v3: 384 (default) / 320 / 256 (2 CTAs / SM, ring 2 / 3 / 4), 512; v2: 256 (default) / 384 / 512
-  int pf_blocks = 4;      // GB200_SCAN_PF: v2 / M = 64: L2 prefetch distance in 32-posting blocks
+  int scan_threads = 0;   // GB200_SCAN_THREADS: M = 32 kernel: 384 (default) / 320 / 256 (2 CTAs / SM, ring 2 / 3 / 4), 512
+  int pf_blocks = 4;      // GB200_SCAN_PF: M = 64 kernel: L2 prefetch distance in 32-posting blocks
   int ch_blocks = 8;      // GB200_SCAN_CH: blocks per item (v3)
   int help_min = 8;       // GB200_SCAN_HELP_MIN: idle CTAs join a query that has >= this many unclaimed items (v3)
   int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
   int v3_tma = 0;         // GB200_SCAN_TMA: v3 posting ring fed by bulk copies (1) or per-lane cp.async (0)
-  int splits = 0;         // GB200_SCAN_SPLITS: v2 / M = 64 / generic: CTAs per query, 0 = automatic
-  int tail = 0;           // GB200_SCAN_TAIL: v2 plan: splits of the last partial wave, 0 = automatic
-  int no_plan = 0;        // GB200_SCAN_NOPLAN: v2 without the positional work plan
-  int steal = 0;          // GB200_SCAN_STEAL: v2, 256 threads: intra-CTA work stealing
-  int scan_timing = 0;    // GB200_SCAN_TIMING: per-phase cycle counters of the v2 kernel on stderr
+  int splits = 0;         // GB200_SCAN_SPLITS: M = 64 / generic: CTAs per query, 0 = automatic
+  int tail = 0;           // GB200_SCAN_TAIL: M = 64 plan: splits of the last partial wave, 0 = automatic
+  int no_plan = 0;        // GB200_SCAN_NOPLAN: M = 64 without the positional work plan
   int coarse_simt = 0;    // GB200_COARSE=simt: CUDA-core fp32 coarse distances instead of the tcgen05 GEMM
   int coarse_full_select = 0;  // GB200_COARSE_FULL_SELECT=1: select over whole rows instead of starting from chunk minima
   int lut_inline = 0;     // GB200_LUT_INLINE: build the tables on the main stream
@@ -111,7 +108,6 @@ struct Tuning {
   void read() {
     *this = Tuning();
     auto geti = [](const char *k, int d) { const char *e = getenv(k); return e && *e ? atoi(e) : d; };
-    scan_variant = geti("GB200_SCAN_VARIANT", scan_variant);
     scan_threads = geti("GB200_SCAN_THREADS", scan_threads);
     if (scan_threads != 256 && scan_threads != 320 && scan_threads != 384 && scan_threads != 416 && scan_threads != 448 &&
         scan_threads != 512)
@@ -124,8 +120,6 @@ struct Tuning {
     splits = std::max(0, geti("GB200_SCAN_SPLITS", 0));
     tail = std::max(0, geti("GB200_SCAN_TAIL", 0));
     no_plan = geti("GB200_SCAN_NOPLAN", 0);
-    steal = geti("GB200_SCAN_STEAL", 0);
-    scan_timing = geti("GB200_SCAN_TIMING", 0);
     lut_inline = geti("GB200_LUT_INLINE", 0);
     coarse_full_select = geti("GB200_COARSE_FULL_SELECT", 0);
     max_contexts = std::max(1, std::min(64, geti("GB200_MAX_CONTEXTS", max_contexts)));
@@ -146,7 +140,6 @@ struct SearchCtx {
       ws_ctl, ws_cmin;
   DevBuf valid_filt, filt_bytes, filt_desc;  // per-call range filters -> validity bitmap
   unsigned long long *d_scanned = nullptr;
-  unsigned long long *d_timing = nullptr;
   int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
   long long launches = 0;
   bool timed = false;  // the events of the last call were recorded
@@ -168,7 +161,6 @@ struct SearchCtx {
                       &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc, &ws_cmin};
     for (DevBuf *b : bufs) b->release();
     if (d_scanned) cudaFree(d_scanned);
-    if (d_timing) cudaFree(d_timing);
     for (int i = 0; i < 6; i++)
       if (ev[i]) cudaEventDestroy(ev[i]);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -1317,26 +1309,18 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     return GB200_EINVAL;
   }
   // ---- kernel, CTA shape, candidate buffer.
-  //  mode 1 (M = 32): v3 persistent kernel (default) or v2 (one CTA per (query, split), GB200_SCAN_VARIANT=2, R <= 512);
-  //  mode 2 (M = 64): 384 threads, 2 CTAs per SM, v2-style work plan;  mode 0: generic kernel.
-  int variant = ix->mode == 1 ? T.scan_variant : ix->mode == 2 ? 2 : 0;
+  //  mode 1 (M = 32): persistent kernel with dynamic items (variant 3, ivfpq_scan_v3.cu);
+  //  mode 2 (M = 64): one CTA per (query, split), 384 threads, 2 CTAs per SM, positional work plan (variant 2);
+  //  mode 0: generic kernel (any M % 4 == 0).
+  const int variant = ix->mode == 1 ? 3 : ix->mode == 2 ? 2 : 0;
   int threads = T.scan_threads;
   int cap = scan_buffer_cap(R);  // power of two >= R + 512, >= 1024
   int ctas_per_sm = 3;
   if (ix->mode == 1) {
-    if (variant != 2 && variant != 3) variant = 3;
-    if (variant == 2) {
-      if (threads != 256 && threads != 384 && threads != 512) threads = 256;
-      if (cap > 2048 || (cap > 1024 && threads != 512)) variant = 3;  // v2 keeps 4 keys per thread in its select
-      else if (threads == 512 && cap < 2048) cap = 2048;
-      ctas_per_sm = threads >= 384 ? 2 : 3;
-    }
-    if (variant == 3) {
-      if (threads == 0) threads = 384;
-      if (cap > 1024) threads = 512;                 // R > 512: 2048 / 4096 keys (4 / 8 per thread in the select)
-      if (threads == 512 && cap < 2048) cap = 2048;  // room for one block of each of the 16 warps
-      ctas_per_sm = scan_v3_ctas_per_sm(threads, cap);
-    }
+    if (threads == 0) threads = 384;
+    if (cap > 1024) threads = 512;                 // R > 512: 2048 / 4096 keys (4 / 8 per thread in the select)
+    if (threads == 512 && cap < 2048) cap = 2048;  // room for one block of each of the 16 warps
+    ctas_per_sm = scan_v3_ctas_per_sm(threads, cap);
   } else if (ix->mode == 2) {
     threads = 384;
     if (cap < R + 384) cap *= 2;  // room for one block of every warp above the survivors
@@ -1372,7 +1356,6 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   P.m32_threads = threads;
   P.variant = variant;
   P.pf_blocks = T.pf_blocks;
-  P.steal = T.steal;
   P.s_tail = 1;
 
   // ---- how the batch is cut into CTAs
@@ -1422,11 +1405,6 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   P.S = S;
   CKI(c.ws_cand.ensure((size_t)n * S * R * sizeof(u64)));
   P.cand = c.ws_cand.as<u64>();
-  if (T.scan_timing && variant == 2 && ix->mode == 1) {
-    if (!c.d_timing) CK(cudaMalloc(&c.d_timing, 8 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c.d_timing, 0, 8 * sizeof(unsigned long long), c.stream));
-    P.timing = c.d_timing;
-  }
   const size_t smem_need = variant == 3 ? scan_v3_smem_bytes_for(nprobe, P.v3_max_items, cap, threads) : scan_smem_bytes(P, ix->mode);
   if (smem_need > 227 * 1024) {
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d nprobe=%d): not implemented", smem_need, M, R, nprobe);
@@ -1511,18 +1489,8 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
 // wait for the context's stream and publish its counters as the index's "last call" statistics
 static int finish_profile(gb200_index *ix, SearchCtx &c) {
   unsigned long long sc = 0;
-  unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool timing = c.d_timing && ix->tune.scan_timing;
-  if (timing) CK(cudaMemcpyAsync(t, c.d_timing, sizeof(t), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaMemcpyAsync(&sc, c.d_scanned, sizeof(sc), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaStreamSynchronize(c.stream));
-  if (timing) {
-    double n = t[7] ? (double)t[7] : 1.0;
-    fprintf(stderr,
-            "[gb200 scan timing] ctas %llu | per-CTA cycles: table %.0f setup %.0f loop %.0f (in-loop prunes %.0f, %0.2f prunes, "
-            "%.1f sync points) final %.0f\n",
-            t[7], t[0] / n, t[1] / n, t[2] / n, t[4] / n, t[5] / n, t[6] / n, t[3] / n);
-  }
   std::lock_guard<std::mutex> g(ix->stats_mu);
   ix->last_scanned = (long long)sc;
   ix->launches += c.launches;
@@ -1746,13 +1714,16 @@ int gb200_ivfpq_encode(gb200_index *ix, int64_t n, const float *x, int x_dim, in
   return GB200_OK;
 }
 
-int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no, uint8_t *codes) {
-  if (!ix || ix->kind != 0 || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
+int gb200_ivfpq_add_stored(gb200_index *ix, int64_t first_vid, int64_t n, int32_t *list_no, uint8_t *codes) {
+  if (!ix || ix->kind != 0 || first_vid < 0 || n < 0) return GB200_EINVAL;
   if (!ix->trained) return GB200_ENOTTRAINED;
   if (n == 0) return GB200_OK;
+  if (first_vid + n > ix->raw_n.load()) {
+    set_err("add_stored: rows %lld .. %lld are not in the raw store (%lld rows)", (long long)first_vid,
+            (long long)(first_vid + n - 1), (long long)ix->raw_n.load());
+    return GB200_EINVAL;
+  }
   const int M = ix->p.nsubvector, rd = ix->p.raw_d;
-  // the raw rows first (re-rank and flat read them; the encode below reads them from the device store)
-  CKI(gb200_upload_raw(ix, first_vid, n, x));
   std::vector<int32_t> ln_own;
   std::vector<uint8_t> cd_own;
   if (!list_no) {
@@ -1772,6 +1743,15 @@ int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const flo
   std::vector<int64_t> vids((size_t)n);
   for (int64_t i = 0; i < n; i++) vids[i] = first_vid + i;
   return gb200_ivfpq_append(ix, n, list_no, vids.data(), codes);
+}
+
+int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no, uint8_t *codes) {
+  if (!ix || ix->kind != 0 || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n == 0) return GB200_OK;
+  // the raw rows first (re-rank and flat read them; the encode reads them from the device store)
+  CKI(gb200_upload_raw(ix, first_vid, n, x));
+  return gb200_ivfpq_add_stored(ix, first_vid, n, list_no, codes);
 }
 
 // ---- flat ----------------------------------------------------------------------------------------

@@ -253,378 +253,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) ivfpq_scan_generic_kernel(ScanPa
   write_survivors<PER>(topr, P, q, split);
 }
 
-#define GB_TICK(slot)                                                   \
-  if (P.timing && threadIdx.x == 0) {                                   \
-    long long t_now = clock64();                                        \
-    atomicAdd(P.timing + (slot), (unsigned long long)(t_now - t_last)); \
-    t_last = t_now;                                                     \
-  }
-
-// =============================================================================================
-// M = 32 kernel, v2.  Same data structures and selection as above; what changed and why (profiles/r01a):
-//  * v1 issued 212 instructions per 32-posting block for 96 useful ones (PRMT + LDS + FADD per lookup): the
-//    prefetched block was copied register-to-register every iteration.  Here the 32 table addresses are formed
-//    first, which kills the code registers, and the NEXT block is loaded straight into those registers —
-//    no copies, still one block in flight per warp during the 32 lookups;
-//  * no periodic CTA barrier: warps meet only when the candidate buffer needs a prune (all of them see
-//    cnt > soft_limit within one block) and at the end — v1 spent 20 % of its issue stalls at barriers;
-//  * the probe table of the (query, split) — list extents, dis0, block prefix — is precomputed by
-//    probe_setup_kernel and arrives with the lookup table through the same mbarrier (one more bulk copy)
-//    instead of three dependent global round trips per CTA;
-//  * the posting stream is pulled towards L2 `pf` blocks ahead with prefetch.global.L2 (one
-//    instruction per block, one 128 B line per lane), so the register prefetch only has to cover L2 latency.
-// =============================================================================================
-// STEAL (opt-in, GB200_SCAN_STEAL=1, not yet validated on hardware): intra-CTA work stealing.  Every warp still owns a
-// contiguous share of the CTA's blocks and walks it front to back, but claims it STEAL_CH blocks at a time from a
-// shared (front, back) word; a warp whose share is empty takes chunks from the BACK of the share with the most
-// blocks left (one 64-bit CAS, re-opening the list there).  profiles/r01c: 17 % of all warp time is spent at the
-// CTA's final barrier waiting for the slowest warp of the static split; taking fixed chunks from a single shared
-// counter was measured and lost more to re-opening lists than it gained — here only the thieves re-open.
-constexpr int STEAL_CH = 4;
-
-template <bool IP, bool HAS_VALID, int WARPS, int PER, bool STEAL = false>
-__device__ __forceinline__ void scan_loop_m32_v2(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
-                                                 const int total_blocks, const int np_s) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lane4 = lane * 4;
-  const int per_warp = (total_blocks + WARPS - 1) / WARPS;
-  const int w0 = min(total_blocks, warp * per_warp);
-  int left = min(total_blocks, w0 + per_warp) - w0;  // blocks this warp still has to LOAD
-  // STEAL: shares live in shared memory as (front | back << 32), block indices in the CTA's block sequence
-  u64 *rng = reinterpret_cast<u64 *>(S.misc + 4);  // [WARPS <= 16], the unused warp_part scratch
-  int ahead = 0;                                    // STEAL: blocks of my own share not yet claimed (for the prefetch)
-  bool own_done = false;
-  if constexpr (STEAL) {
-    if (lane == 0) rng[warp] = (u64)(uint32_t)w0 | ((u64)(uint32_t)(w0 + left) << 32);
-    ahead = left;
-    left = 0;
-    __syncthreads();  // every share is published before anyone may look for a victim
-  }
-  const int soft_limit = P.cap - WARPS * 32;
-  volatile int *flags = S.misc + 68;  // 3 rotating slots: bit0 = prune wanted, bit1 = work left
-  const int pf = P.pf_blocks;
-  // ids at or beyond the bitmap's size (appended after this search began) and negative ids (dead / padding) fail
-  const uint32_t valid_lim = (uint32_t)(P.valid_bits < 0x7fffffffLL ? P.valid_bits : 0x7fffffffLL);
-
-  int pj = 0;
-  if (left > 0)
-    while (S.blk_prefix[pj + 1] <= w0) pj++;
-  int bl = 0, len = 0;  // blocks left in this list, postings left for this lane
-  uint32_t seq0 = 0;
-  float dis0 = 0.f;
-  const uint8_t *cptr = nullptr;
-  const int *iptr = nullptr;
-  const float *nptr = nullptr;
-  // L2 prefetch streams, one 128 B line per lane and block: lanes 0..7 the 1 KB of codes, lane 8 the ids,
-  // lane 9 the t(p) words (L2 metric only)
-  const char *pfp = nullptr;
-  const uint32_t pf_stride = lane < 8 ? 1024u : 128u;
-  const bool pf_lane = pf > 0 && lane < (IP ? 9 : 10);
-  auto stream_base = [&](const ProbeInfo &pi, int b_start) -> const char * {
-    const long long first = pi.off + (long long)b_start * 32;
-    return lane < 8 ? reinterpret_cast<const char *>(P.codes + (size_t)first * 32) + lane * 128
-                    : lane == 8 ? reinterpret_cast<const char *>(P.ids + first)
-                                : reinterpret_cast<const char *>(P.norms + first);
-  };
-  auto open_list = [&](int j, int b_start) {
-    const ProbeInfo pi = S.pinfo[j];
-    bl = ((pi.len + 31) >> 5) - b_start;
-    dis0 = pi.dis0;
-    seq0 = ((uint32_t)pi.rank << GB_SEQ_POS_BITS) + (uint32_t)(b_start * 32 + lane);
-    len = pi.len - (b_start * 32 + lane);  // > 0 <=> this lane's posting exists
-    const long long first = pi.off + (long long)b_start * 32;
-    cptr = P.codes + (size_t)first * 32 + lane * 16;
-    iptr = P.ids + first + lane;
-    nptr = P.norms + first + lane;
-    if (pf_lane) {
-      pfp = stream_base(pi, b_start) + (size_t)pf * pf_stride;  // steady state: block (current + pf)
-      // head of the NEXT list this warp will walk (its first blocks have no steady-state prefetch)
-      if (left + (STEAL ? ahead : 0) > bl && j + 1 < np_s) {
-        const ProbeInfo pn = S.pinfo[j + 1];
-        const int nb = min(min((pn.len + 31) >> 5, pf), left + (STEAL ? ahead : 0) - bl);
-        const char *h = stream_base(pn, 0);
-#pragma unroll 1
-  #pragma unroll 1
-      for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
-      }
-    }
-  };
-  if (left > 0) {
-    if (pf_lane) {  // head of this warp's first list
-      const ProbeInfo pi = S.pinfo[pj];
-      const int b0 = w0 - S.blk_prefix[pj];
-      const int nb = min(min(((pi.len + 31) >> 5) - b0, pf), left);
-      const char *h = stream_base(pi, b0);
-#pragma unroll 1
-      for (int b = 0; b < nb; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
-    }
-    open_list(pj, w0 - S.blk_prefix[pj]);
-  }
-  // STEAL: claim the next chunk — from the front of my own share (contiguous with what I walked, no re-open), else
-  // from the back of the fullest share (re-open there).  Warp-uniform; returns false when the CTA has no blocks left.
-  bool first_claim = true;
-  auto claim = [&]() -> bool {
-    int b0 = 0, nb = 0;
-    bool stolen = false;
-    if (!own_done) {
-      if (lane == 0) {
-        u64 old = *((volatile u64 *)&rng[warp]);
-        for (;;) {
-          const uint32_t f = (uint32_t)old, b = (uint32_t)(old >> 32);
-          if (f >= b) break;
-          const uint32_t c = min((uint32_t)STEAL_CH, b - f);
-          const u64 seen = atomicCAS(reinterpret_cast<unsigned long long *>(&rng[warp]), old,
-                                     (u64)(f + c) | ((u64)b << 32));
-          if (seen == old) {
-            b0 = (int)f, nb = (int)c;
-            ahead = (int)(b - f - c);
-            break;
-          }
-          old = seen;
-        }
-      }
-      nb = __shfl_sync(GB_FULL, nb, 0);
-      b0 = __shfl_sync(GB_FULL, b0, 0);
-      ahead = __shfl_sync(GB_FULL, ahead, 0);
-      if (nb == 0) {
-        own_done = true;
-        ahead = 0;
-      }
-    }
-    if (nb == 0) {  // look for a victim: the share with the most unclaimed blocks
-      for (;;) {
-        u64 w = lane < WARPS ? *((volatile u64 *)&rng[lane]) : 0ull;
-        int rem = (int)(uint32_t)(w >> 32) - (int)(uint32_t)w;
-        rem = rem > 0 ? rem : 0;
-        const int best = __reduce_max_sync(GB_FULL, rem);
-        if (best == 0) return false;  // nothing left anywhere
-        const int victim = __ffs(__ballot_sync(GB_FULL, rem == best)) - 1;
-        if (lane == 0) {
-          u64 old = *((volatile u64 *)&rng[victim]);
-          const uint32_t f = (uint32_t)old, b = (uint32_t)(old >> 32);
-          if (f < b) {
-            const uint32_t c = min((uint32_t)STEAL_CH, b - f);
-            const u64 seen = atomicCAS(reinterpret_cast<unsigned long long *>(&rng[victim]), old,
-                                       (u64)f | ((u64)(b - c) << 32));
-            if (seen == old) b0 = (int)(b - c), nb = (int)c;
-          }
-        }
-        nb = __shfl_sync(GB_FULL, nb, 0);
-        b0 = __shfl_sync(GB_FULL, b0, 0);
-        if (nb > 0) break;  // else: lost the race, look again
-      }
-      stolen = true;
-    }
-    left = nb;
-    if (stolen || first_claim) {  // position the list walk at block b0 (own chunks after the first continue in place)
-      pj = 0;
-      while (S.blk_prefix[pj + 1] <= b0) pj++;
-      if (pf_lane) {
-        const ProbeInfo pi = S.pinfo[pj];
-        const int bs = b0 - S.blk_prefix[pj];
-        const int nh = min(min(((pi.len + 31) >> 5) - bs, pf), left);
-        const char *h = stream_base(pi, bs);
-#pragma unroll 1
-        for (int b = 0; b < nh; b++) l2_prefetch_line(h + (size_t)b * pf_stride);
-      }
-      open_list(pj, b0 - S.blk_prefix[pj]);
-      first_claim = false;
-    }
-    return true;
-  };
-
-  // the block in flight (per lane): 32 pre-rotated code bytes, vid, t(p), list dis0, scan-order word
-  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
-  int id_n = -1;
-  float nrm_n = 0.f, base_n = 0.f;
-  uint32_t seq_n = 0xffffffffu;
-  auto issue_loads = [&]() {
-    if constexpr (STEAL) {
-      if (left == 0) claim();
-    }
-    if (left > 0) {  // warp-uniform
-      while (bl == 0) open_list(++pj, 0);
-      const uint4 v0 = ldg_nc_v4(cptr);
-      const uint4 v1 = ldg_nc_v4(cptr + 512);
-      c0 = v0.x, c1 = v0.y, c2 = v0.z, c3 = v0.w, c4 = v1.x, c5 = v1.y, c6 = v1.z, c7 = v1.w;
-      seq_n = seq0;
-      base_n = dis0;
-      id_n = -1;
-      nrm_n = 0.f;
-      if (len > 0) {
-        id_n = ldg_nc_s32(iptr);
-        if (!IP) nrm_n = ldg_nc_f32(nptr);
-      }
-      if (pf_lane) {
-        if (bl > pf) l2_prefetch_line(pfp);
-        pfp += pf_stride;
-      }
-      cptr += 1024;
-      iptr += 32;
-      nptr += 32;
-      seq0 += 32;
-      len -= 32;
-      bl--;
-      left--;
-    } else {
-      seq_n = 0xffffffffu;
-    }
-  };
-
-  u64 skey = 0;
-  bool spend = false;
-  auto try_append = [&](bool pass, u64 key) -> bool {
-    const unsigned m = __ballot_sync(GB_FULL, pass);
-    if (m == 0) return false;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(topr.cnt, __popc(m));
-    base = __shfl_sync(GB_FULL, base, leader);
-    const int slot = base + __popc(m & ((1u << lane) - 1u));
-    bool pending = pass;
-    if (pass && slot < topr.cap) {
-      topr.buf[slot] = key;
-      pending = false;
-    }
-    spend = pending;
-    skey = key;
-    return __any_sync(GB_FULL, pending);
-  };
-
-  bool stalled = false;
-  issue_loads();
-  int round = 0;
-  for (;;) {
-    if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
-    bool over = false;
-    while (!stalled && !over && seq_n != 0xffffffffu) {  // warp-uniform
-      // ---- A/C: table addresses (code << 8 | lane * 4) 16 at a time (keeps the kernel at 64 registers so that
-      // 32 warps fit on an SM), 32 conflict-free lookups on four accumulation chains.  The second half's
-      // addresses kill the code registers, which are then refilled with the NEXT block (B).
-      uint32_t a[16];
-      float s0, s1, s2, s3;
-#define GB_ADDR4(W, I)                     \
-  a[I + 0] = prmt_v(W, lane4, 0x5504);     \
-  a[I + 1] = prmt_v(W, lane4, 0x5514);     \
-  a[I + 2] = prmt_v(W, lane4, 0x5524);     \
-  a[I + 3] = prmt_v(W, lane4, 0x5534);
-#define GB_LOOK4(I, O)               \
-  s0 += lds_raw<O + 0>(a[I + 0]);    \
-  s1 += lds_raw<O + 1>(a[I + 1]);    \
-  s2 += lds_raw<O + 2>(a[I + 2]);    \
-  s3 += lds_raw<O + 3>(a[I + 3]);
-      GB_ADDR4(c0, 0) GB_ADDR4(c1, 4) GB_ADDR4(c2, 8) GB_ADDR4(c3, 12)
-      s0 = lds_raw<0>(a[0]), s1 = lds_raw<1>(a[1]), s2 = lds_raw<2>(a[2]), s3 = lds_raw<3>(a[3]);
-      GB_LOOK4(4, 4) GB_LOOK4(8, 8) GB_LOOK4(12, 12)
-      GB_ADDR4(c4, 0) GB_ADDR4(c5, 4) GB_ADDR4(c6, 8) GB_ADDR4(c7, 12)
-      const int id = id_n;
-      const uint32_t seq = seq_n;
-      const float nb = base_n + nrm_n;
-      uint32_t vw = 0xffffffffu;
-      if (HAS_VALID) vw = (uint32_t)id < valid_lim ? __ldg(P.valid + (id >> 5)) : 0u;  // latency hidden by the lookups
-      // ---- B: next block straight into the registers just freed
-      issue_loads();
-      GB_LOOK4(0, 16) GB_LOOK4(4, 20) GB_LOOK4(8, 24) GB_LOOK4(12, 28)
-#undef GB_ADDR4
-#undef GB_LOOK4
-      // ---- D: filter, key, admission
-      // every warp reads the counter once per block so that all of them notice a wanted prune within one block, whether
-      // or not they append anything themselves.  Two 32-bit loads on purpose: fetching {tau, cnt} with one
-      // ld.volatile.shared.v4 hung this kernel on B200.
-      const uint32_t tau_hi = *((volatile uint32_t *)topr.tau + 1);
-      over = *((volatile int *)topr.cnt) > soft_limit;
-      const float dis = nb + ((s0 + s1) + (s2 + s3));
-      bool ok = id >= 0;
-      if (HAS_VALID) ok = ok && ((vw >> (id & 31)) & 1u);
-      const uint32_t k32 = dist_to_key32<IP>(dis);
-      const bool pass = ok && (dis == dis) && k32 <= tau_hi;  // cheap pre-test on the distance word
-      if (__any_sync(GB_FULL, pass)) {
-        const u64 key = ((u64)k32 << 32) | seq;
-        stalled = try_append(pass && key < topr.threshold(), key);
-        // appenders re-read the counter after their own atomicAdd: a warp starts a block only while
-        // cnt <= cap - 32 * WARPS, so the buffer cannot overflow between sync points
-        over = over || *((volatile int *)topr.cnt) > soft_limit;
-      }
-    }
-    const bool more = stalled || seq_n != 0xffffffffu;
-    over = over || stalled;
-    const int slot = round % 3;
-    if (lane == 0 && (more || over)) atomicOr((int *)&flags[slot], (over ? 1 : 0) | (more ? 2 : 0));
-    __syncthreads();
-    const int v = flags[slot];
-    if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
-    round++;
-    if (v & 1) {
-      long long tp0 = clock64();
-      topr.prune_collective<PER>();
-      if (P.timing && threadIdx.x == 0) {
-        atomicAdd(P.timing + 4, (unsigned long long)(clock64() - tp0));
-        atomicAdd(P.timing + 5, 1ull);
-      }
-    }
-    if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 6, 1ull);  // sync points
-    if (!(v & 2)) break;
-  }
-}
-
-template <bool IP, int THREADS, int MINB, int PER, bool STEAL = false>
-__global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v2_kernel(ScanParams P) {
-  constexpr int WARPS = THREADS / 32;
-  long long t_last = clock64();
-  // work item = (query, split, number of splits of that query): either the plan of plan_items_kernel (heaviest
-  // queries first and unsplit, the queries of the last partial wave split so that it fills the machine) or the
-  // plain (split, query) grid
-  int q, split, nsp;
-  size_t item;
-  if (P.n_items > 0) {
-    item = blockIdx.x;
-    if ((int)blockIdx.x < P.n_full) {
-      q = blockIdx.x, split = 0, nsp = 1;
-    } else {
-      const int t = blockIdx.x - P.n_full;
-      q = P.n_full + t / P.s_tail, split = t % P.s_tail, nsp = P.s_tail;
-    }
-  } else {
-    q = blockIdx.y;
-    split = blockIdx.x, nsp = P.S;
-    item = (size_t)q * P.S + split;
-  }
-  const int tid = threadIdx.x;
-  ScanSmem S = carve(gb_scan_smem, P, 1);
-  BlockTopR topr = make_topr(S, P);
-  if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
-  const int np_s = (P.nprobe - split + nsp - 1) / nsp;
-  if (tid == 0) {
-    *topr.cnt = 0;
-    *topr.tau = GB_KEY_MAX;
-    S.misc[68] = S.misc[69] = S.misc[70] = 0;
-    mbar_init(&S.mbar[0], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // the query's table [256][64] (lut_build_m32_kernel, L2 resident) and this (query, split)'s probe table
-    // (probe_setup_kernel) land in shared memory through one mbarrier
-    const uint32_t pbytes = (uint32_t)scan_probe_bytes(P.max_np_s);
-    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
-    mbar_expect_tx(&S.mbar[0], 65536u + pbytes);
-    tma_bulk_g2s(S.pinfo, P.probe_g + item * pbytes, pbytes, &S.mbar[0]);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      tma_bulk_g2s(reinterpret_cast<char *>(S.lut) + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
-  }
-  __syncthreads();  // mbarrier initialised before anyone polls it
-  mbar_wait(&S.mbar[0], 0);
-  GB_TICK(0);  // wait for the tables
-  const int total_blocks = S.blk_prefix[np_s];
-  if (P.valid) scan_loop_m32_v2<IP, true, WARPS, PER, STEAL>(P, S, topr, total_blocks, np_s);
-  else scan_loop_m32_v2<IP, false, WARPS, PER, STEAL>(P, S, topr, total_blocks, np_s);
-  GB_TICK(2);  // scan loop incl. in-loop prunes
-  write_survivors<PER>(topr, P, q, split);
-  if (split == 0)  // an unsplit (or less split) query leaves the other slots of its [S][R] candidate row empty
-    for (int i = nsp * P.R + tid; i < P.S * P.R; i += THREADS) P.cand[(size_t)q * P.S * P.R + i] = GB_KEY_MAX;
-  GB_TICK(3);  // final prune + write
-  if (P.timing && threadIdx.x == 0) atomicAdd(P.timing + 7, 1ull);
-}
-
-// K2b — probe tables for the v2 kernel: one warp per (query, split) writes, in the kernel's shared-memory
+// K2b — probe tables for the M = 64 kernel: one warp per (query, split) writes, in the kernel's shared-memory
 // layout, [ProbeInfo x max_np_s][exclusive prefix of 32-posting block counts x (max_np_s + 1)]:
 // scan_one_list's list lookup (gamma_index_ivfpq.cc:597-640) and dis0 of precompute_list_tables
 // (gamma_index_ivfpq.h:216-230, 236-299) hoisted out of the scan.
@@ -750,10 +379,10 @@ template <typename K>
 static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int threads, size_t *configured,
                                  cudaStream_t st) {
   size_t smem = scan_smem_bytes(P, mode);
-  if (smem > *configured) {
+  {  // the attribute is per device and setting it is cheap: no process-wide cache (an index may live on any device)
+    (void)configured;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    *configured = smem;
   }
   dim3 grid(P.S, P.n);
   if (P.n_items > 0) grid = dim3(P.n_items, 1);
@@ -761,26 +390,10 @@ static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int th
   return cudaGetLastError();
 }
 
-template <int T, int MINB>
-static cudaError_t launch_m32_v2(const ScanParams &P, cudaStream_t st) {
-  static size_t conf[2] = {0, 0};
-  return P.is_ip ? launch_kernel(ivfpq_scan_m32_v2_kernel<true, T, MINB, 4>, P, 1, T, &conf[0], st)
-                 : launch_kernel(ivfpq_scan_m32_v2_kernel<false, T, MINB, 4>, P, 1, T, &conf[1], st);
-}
-static cudaError_t launch_m32_v2_steal(const ScanParams &P, cudaStream_t st) {  // opt-in, 256 threads x 3 CTAs only
-  static size_t conf[2] = {0, 0};
-  return P.is_ip ? launch_kernel(ivfpq_scan_m32_v2_kernel<true, 256, 3, 4, true>, P, 1, 256, &conf[0], st)
-                 : launch_kernel(ivfpq_scan_m32_v2_kernel<false, 256, 3, 4, true>, P, 1, 256, &conf[1], st);
-}
-
-// v2 needs: cap <= 1024 (4 keys per thread in the select), the probe tables, and dynamic shared memory at
-// shared-window offset GB_SMEM_RESERVED (checked by the host with cudaDevAttrReservedSharedMemoryPerBlock)
-bool scan_m32_v2_usable(const ScanParams &P) { return P.cap <= 4 * P.m32_threads && P.probe_g != nullptr; }
-int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads >= 384 ? 2 : 3; }
-
 // =============================================================================================
-// M = 64 kernel (opt-in: GB200_SCAN_M64=1 at index creation; BASELINE config C3 = PQ64x8).
-// Same structure as the M = 32 v2 kernel.  Differences:
+// M = 64 kernel (the reference's default nsubvector; BASELINE config C3 = PQ64x8): one CTA per (query, split), probe
+// table + lookup table by TMA bulk copies on one mbarrier, static per-warp split, next block loaded into the code
+// registers the address formation just freed, L2 prefetch pf blocks ahead.  Against the M = 32 kernel:
 //  * table [256 codes][96 words] = 96 KB: words 64..95 duplicate 0..31, lane l reads word (l + s) of row `code` at step
 //    s = 0..63 — bank (l + s) mod 32, conflict free; the mirror pre-rotates the 64 code bytes of posting i by i
 //    (LAYOUT_M64_ROT) so that step s uses stored byte s;
@@ -789,8 +402,8 @@ int scan_m32_v2_ctas_per_sm(const ScanParams &P) { return P.m32_threads >= 384 ?
 //  * a block of 32 postings is 2 KB of codes (4 chunks of 16 B per posting): 16 code registers, refilled in two
 //    halves as soon as the addresses of that half have been formed;
 //  * 384 threads, 2 CTAs per SM (2 x 108 KB of shared memory), candidate buffer of 1024 keys.
-// NOT yet validated on hardware (written after the round's GPU budget was spent): tests/test_ivfpq_gpu.py holds the
-// parity test, skipped unless GB200_TEST_M64=1.
+// Validated on hardware in round 2 (tests/test_ivfpq_gpu.py::test_m64_default_kernel_parity); 0.59 of the measured HBM
+// peak on config C3.
 // =============================================================================================
 template <bool IP, bool HAS_VALID, int WARPS, int PER>
 __device__ __forceinline__ void scan_loop_m64(const ScanParams &P, const ScanSmem &S, BlockTopR &topr,
@@ -1079,12 +692,7 @@ static cudaError_t launch_m64(const ScanParams &P, cudaStream_t st) {
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st) {
   static size_t conf[4] = {0, 0, 0, 0};
   if (mode == 2) return P.cap <= 4 * 384 ? launch_m64<4>(P, st) : launch_m64<16>(P, st);
-  if (mode == 1) {  // M = 32, v2 (the default v3 kernel is launched through launch_ivfpq_scan_v3)
-    if (!scan_m32_v2_usable(P)) return cudaErrorInvalidValue;
-    if (P.steal && P.m32_threads == 256) return launch_m32_v2_steal(P, st);
-    return P.m32_threads == 512 ? launch_m32_v2<512, 2>(P, st)
-           : P.m32_threads == 384 ? launch_m32_v2<384, 2>(P, st) : launch_m32_v2<256, 3>(P, st);
-  }
+  if (mode == 1) return cudaErrorInvalidValue;  // M = 32 runs the persistent kernel (launch_ivfpq_scan_v3)
   if (P.cap > 4 * SCAN_THREADS)
     return P.is_ip ? launch_kernel(ivfpq_scan_generic_kernel<true, 16>, P, 0, SCAN_THREADS, &conf[0], st)
                    : launch_kernel(ivfpq_scan_generic_kernel<false, 16>, P, 0, SCAN_THREADS, &conf[1], st);

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
   uint2 *itab = reinterpret_cast<uint2 *>(dst + v3_itab_off(np));
   const float *xq = P.xq + (size_t)q * P.d;
   int carry = 0;
-  unsigned my_postings = 0;
+  unsigned my_postings = 0, n_full = 0;
   for (int j0 = 0; j0 < np; j0 += 32) {
     const int j = j0 + lane;
     ProbeInfo pi;
@@ -197,16 +197,45 @@ __global__ void __launch_bounds__(256) probe_setup_v3_kernel(ScanParams P) {
       int v = __shfl_up_sync(GB_FULL, incl, o);
       if (lane >= o) incl += v;
     }
+    if (j < np) prefix[j] = carry + incl - ni;
+    carry += __shfl_sync(GB_FULL, incl, 31);
+    n_full += __reduce_add_sync(GB_FULL, (unsigned)(nb / ch));
+    my_postings += (unsigned)pi.len;
+  }
+  // ---- item table.  Claim order = table order: all FULL items (ch blocks) of every list first, the lists' shorter
+  // remainders last, so that the warps of a CTA run out of work within a short item of each other (the scan-order key
+  // of a posting does not depend on who scans it when).  If the table cannot hold every item (a list outgrew the host's
+  // bound) the order is list-major, the one the scan's search fallback assumes for the items beyond the table.
+  const bool reorder = carry <= P.v3_max_items;
+  int c_full = 0, c_rem = 0, c_all = 0;
+  for (int j0 = 0; j0 < np; j0 += 32) {
+    const int j = j0 + lane;
+    int nb = 0;
+    uint32_t offb = 0;
     if (j < np) {
-      prefix[j] = carry + incl - ni;
-      // this list's items, in claim order: up to ch consecutive 32-posting blocks each
-      const uint32_t offb = (uint32_t)(pi.off >> 5);
-      int it = carry + incl - ni;
+      nb = (pinfo[j].len + 31) >> 5;  // written by this very lane above
+      offb = (uint32_t)(pinfo[j].off >> 5);
+    }
+    const int nf = nb / ch, rem = nb - nf * ch, ni = nf + (rem ? 1 : 0);
+    int i_full = nf, i_rem = rem ? 1 : 0, i_all = ni;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(GB_FULL, i_full, o), b = __shfl_up_sync(GB_FULL, i_rem, o),
+                c = __shfl_up_sync(GB_FULL, i_all, o);
+      if (lane >= o) i_full += a, i_rem += b, i_all += c;
+    }
+    if (reorder) {
+      int it = c_full + i_full - nf;
+      for (int k = 0; k < nf; k++, it++) itab[it] = make_uint2(offb + (uint32_t)(k * ch), ((uint32_t)ch << 16) | (uint32_t)j);
+      if (rem) itab[(int)n_full + c_rem + i_rem - 1] = make_uint2(offb + (uint32_t)(nf * ch), ((uint32_t)rem << 16) | (uint32_t)j);
+    } else {
+      int it = c_all + i_all - ni;
       for (int b0 = 0; b0 < nb && it < P.v3_max_items; b0 += ch, it++)
         itab[it] = make_uint2(offb + (uint32_t)b0, ((uint32_t)min(ch, nb - b0) << 16) | (uint32_t)j);
     }
-    carry += __shfl_sync(GB_FULL, incl, 31);
-    my_postings += (unsigned)pi.len;
+    c_full += __shfl_sync(GB_FULL, i_full, 31);
+    c_rem += __shfl_sync(GB_FULL, i_rem, 31);
+    c_all += __shfl_sync(GB_FULL, i_all, 31);
   }
   my_postings = __reduce_add_sync(GB_FULL, my_postings);
   if (lane == 0) {
@@ -234,7 +263,7 @@ cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 template <bool IP, bool HAS_VALID, int WARPS, int PER, int RING, bool TMA>
 __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Smem &S, BlockTopR &topr, const int q,
-                                                 const int it_first, uint32_t &ring_epoch) {
+                                                 const int it_first, uint32_t &ring_epoch, const uint32_t lut_parity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lane4 = lane * 4;
   const int np = P.nprobe;
@@ -440,7 +469,8 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
   };
 
   bool stalled = false;
-  take_next();  // the first claim of this query was issued before the table wait (claim_pending == true)
+  take_next();  // the first claim of this query was issued before the probe block arrived (claim_pending == true)
+  mbar_wait(&S.mbar[1], lut_parity);  // the lookup table, while this warp's first blocks travel
   int round = 0;
   for (;;) {
     if (stalled) stalled = try_append(spend && skey < topr.threshold(), skey);  // after a prune
@@ -593,7 +623,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
   if (smem_u32(gb_scan_smem) != GB_SMEM_RESERVED) __trap();  // the LDS immediates assume it (host checks the attribute)
   const uint32_t pbytes = (uint32_t)v3_probe_bytes(P.nprobe, P.v3_max_items);
   if (tid == 0) {
-    mbar_init(&S.mbar[0], 1);
+    mbar_init(&S.mbar[0], 1);  // probe block (extents, item table)
+    mbar_init(&S.mbar[1], 1);  // the query's lookup table
     if (TMA)
       for (int i = 0; i < 16 * 4; i++) mbar_init(&S.rbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -630,20 +661,23 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
       *topr.tau_f = IP ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);  // everything finite is admitted
       S.misc[68] = S.misc[69] = S.misc[70] = 0;
       const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
-      mbar_expect_tx(&S.mbar[0], 65536u + pbytes);
+      mbar_expect_tx(&S.mbar[0], pbytes);
       tma_bulk_g2s(S.pinfo, P.probe_g + (size_t)q * pbytes, pbytes, &S.mbar[0]);
+      mbar_expect_tx(&S.mbar[1], 65536u);
 #pragma unroll
-      for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[0]);
+      for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[1]);
     }
     __syncthreads();
     // every warp's first claim travels to L2 and back while the tables arrive
     int it_first = 0;
     int *const claim0 = P.v3_claim + q + (tid & 31) * P.v3_zero;  // address formed outside the branch (see scan_loop_m32_v3)
     if ((tid & 31) == 0) asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(it_first) : "l"(claim0) : "memory");
+    // the small probe block is enough to claim, locate and request the first postings: the 64 KB table is awaited
+    // inside the loop, after the first blocks are in flight
     mbar_wait(&S.mbar[0], parity);
+    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
+    else scan_loop_m32_v3<IP, false, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
     parity ^= 1u;
-    if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch);
-    else scan_loop_m32_v3<IP, false, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch);
     // ---- survivors of this CTA -> cand[q][row][0..R)
     topr.prune_collective<PER>();
     const int n_out = min(*((volatile int *)topr.cnt), P.R);

@@ -35,12 +35,10 @@ struct ScanParams {
   long long valid_bits;     // docs the bitmap covers; ids beyond it (appended after the search began) are skipped
   u64 *cand;                // [n][S][R] surviving keys (unsorted), GB_KEY_MAX padded
   unsigned long long *scanned;  // += postings walked (may be nullptr)
-  unsigned long long *timing;   // optional [8] phase cycle counters (GB200_SCAN_TIMING=1), else nullptr
   int n, d, M, dsub, nlist, nprobe, S, R, cap, chunk, max_np_s, is_ip;
   int m32_threads;          // tuning: CTA size of the M = 32 kernel (256 / 320 / 384)
-  int variant;              // M = 32: 3 = persistent kernel (ivfpq_scan_v3.cu), 2 = one CTA per (query, split)
-  int pf_blocks;            // v2 loop: L2 prefetch distance in 32-posting blocks (0 = off)
-  int steal;                // v2 loop, 256-thread shape: intra-CTA work stealing (opt-in, GB200_SCAN_STEAL=1)
+  int variant;              // 3 = persistent M = 32 kernel (ivfpq_scan_v3.cu), 2 = M = 64 kernel, 0 = generic
+  int pf_blocks;            // M = 64 loop: L2 prefetch distance in 32-posting blocks (0 = off)
   unsigned char *probe_g;   // v2: [items][scan_probe_bytes(max_np_s)] from launch_probe_setup
   int n_items;              // v2: > 0: grid = n_items work items; S is then the row count of cand per query.  The plan is
   int n_full, s_tail;       //     positional: query q < n_full is one item, the others s_tail items each
@@ -63,8 +61,6 @@ cudaError_t launch_probe_setup_v3(const ScanParams &P, cudaStream_t st);
 cudaError_t launch_ivfpq_scan_v3(const ScanParams &P, int grid, cudaStream_t st);
 size_t scan_probe_bytes_host(int max_np_s);
 cudaError_t launch_probe_setup(const ScanParams &P, cudaStream_t st);
-bool scan_m32_v2_usable(const ScanParams &P);
-int scan_m32_v2_ctas_per_sm(const ScanParams &P);
 size_t scan_smem_bytes(const ScanParams &P, int mode);
 int scan_buffer_cap(int R);
 cudaError_t launch_ivfpq_scan(const ScanParams &P, int mode, cudaStream_t st);

@@ -132,6 +132,10 @@ int gb200_ivfpq_encode(gb200_index *ix, int64_t n, const float *x, int x_dim, in
  * append the postings (AddKeys semantics as gb200_ivfpq_append).  list_no / codes (may be NULL) return what was
  * appended, for a host that keeps its own copy of the lists (Dump).                                                  */
 int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no, uint8_t *codes);
+/* same for rows that are already in the device raw store (gb200_upload_raw / gb200_upload_raw_dev): encode + append
+ * vids first_vid .. first_vid + n - 1 — the engine's AddRTVecsToIndex loop, which indexes what AddToStore stored
+ * earlier (vector/vector_manager.cc:280-382).  list_no / codes may be NULL.                                            */
+int gb200_ivfpq_add_stored(gb200_index *ix, int64_t first_vid, int64_t n, int32_t *list_no, uint8_t *codes);
 
 /* ---- raw vectors: the read side of VectorReader::Gets / RawVector::GetVectorHeader
  * (index/retrieval_model.h:192-215, vector/memory_raw_vector.cc:110-142); vids are

@@ -91,8 +91,8 @@ def test_full_search_with_rerank(fx, metric):
 def test_large_batch_work_plan_parity(monkeypatch):
     """More queries than resident CTA slots (SMs x 3): the persistent scan hands queries to CTAs from a queue and lets
     idle CTAs join running queries (several candidate rows per query, merged by the re-rank) — it must still
-    reproduce the CPU engine, and every other way of cutting the batch (one row per query, tiny items, the 512-thread
-    shape, the v2 kernel with and without its positional plan) must return bit-identical results."""
+    reproduce the CPU engine, and every other way of cutting the batch (one row per query, tiny items, other CTA shapes,
+    the bulk-copy fed posting ring) must return bit-identical results."""
     from gamma_b200 import synth
     f = fx_l2_m32()
     ix = f.mirror()
@@ -102,9 +102,8 @@ def test_large_batch_work_plan_parity(monkeypatch):
     assert rc == 0
     assert assert_rerank_parity(f, ix, xq, k, nprobe, R, "L2", D, I) > 0.995
     for env in ({"GB200_SCAN_ROWS": "1"}, {"GB200_SCAN_CH": "1", "GB200_SCAN_HELP_MIN": "1", "GB200_SCAN_ROWS": "8"},
-                {"GB200_SCAN_THREADS": "512"}, {"GB200_SCAN_THREADS": "384", "GB200_SCAN_PF": "0"},
-                {"GB200_SCAN_VARIANT": "2"}, {"GB200_SCAN_VARIANT": "2", "GB200_SCAN_NOPLAN": "1"},
-                {"GB200_SCAN_VARIANT": "2", "GB200_SCAN_THREADS": "512"}):
+                {"GB200_SCAN_THREADS": "512"}, {"GB200_SCAN_THREADS": "320"}, {"GB200_SCAN_THREADS": "256", "GB200_SCAN_CH": "3"},
+                {"GB200_SCAN_TMA": "1"}, {"GB200_SCAN_TMA": "1", "GB200_SCAN_THREADS": "256", "GB200_SCAN_CH": "2"}):
         for kk, vv in env.items():
             monkeypatch.setenv(kk, vv)
         ix.reload_tuning()
