@@ -38,13 +38,15 @@ WORKLOADS = {
     "headline": dict(N=10_000_000, d=128, nlist=16384, M=32, nprobe=32, batch=1024, filt=False,
                      desc="IVFPQ d=128 nlist=16384 PQ32x8 10M vecs nprobe=32 batch=1024 recall_num=100 rerank k=10 L2"),
     "c3": dict(N=10_000_000, d=128, nlist=16384, M=64, nprobe=32, batch=1024, filt=True,
+               metric="QPS @ recall@10 (d=128, 10M vecs, PQ64x8, nprobe=32, batch=1024, range filter + deletions)",
                desc="IVFPQ d=128 nlist=16384 PQ64x8 10M vecs nprobe=32 batch=1024 + range-filter bitmap (30% pass) + 1% deleted"),
     "c2": dict(N=1_000_000, d=128, nlist=4096, M=32, nprobe=16, batch=256, filt=False,
+               metric="QPS @ recall@10 (d=128, 1M vecs, nlist=4096, nprobe=16, batch=256)",
                desc="IVFPQ d=128 nlist=4096 PQ32x8 1M vecs nprobe=16 batch=256"),
     # BASELINE.json configs[4]: built ON the device (seeded torch mixture generated chunk by chunk, trained with the setup
     # tooling, encoded + appended by gb200_ivfpq_add_stored) — 51 GB of raw vectors never touch the host
     "c5": dict(N=100_000_000, d=128, nlist=65536, M=32, nprobe=64, batch=4096, filt=False, device_build=True,
-               cpu_N=10_000_000,
+               cpu_N=10_000_000, metric="QPS @ recall@10 (d=128, 100M vecs, nlist=65536, nprobe=64, batch=4096)",
                desc="IVFPQ d=128 nlist=65536 PQ32x8 100M vecs nprobe=64 batch=4096 recall_num=100 rerank k=10 L2"),
     # BASELINE.json configs[3]: the tensor-core flat path
     "c4": dict(kind="flat", N=5_000_000, d=768, batch=512, metric="InnerProduct",
@@ -729,7 +731,7 @@ def main():
                 qps_list.append(dt)
         ms = 1e3 * float(np.mean(qps_list))
         val = nq / (ms / 1e3)
-        out = dict(metric=METRIC, value=val, unit="queries/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        out = dict(metric=w.get("metric", METRIC), value=val, unit="queries/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                    data="synthetic", impl="reference",
                    config=dict(workload=w["desc"], N=N, nlist=nlist, queries_per_step=nq, scaled_down=args.scale != 1.0 or bool(devb),
@@ -990,7 +992,7 @@ def main():
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = dict(value=None, unit="queries/s", cores=None, kind="reference", sample="failed: %r" % (e,))
 
-    out = dict(metric=METRIC, value=value, unit="queries/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+    out = dict(metric=w.get("metric", METRIC), value=value, unit="queries/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                data="synthetic",
                config=dict(workload=w["desc"], N=N, nlist=nlist, M=w["M"], nprobe=w["nprobe"], batch_per_gpu=n,

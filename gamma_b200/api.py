@@ -45,7 +45,8 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status",
+    "gb200_comm_buffers", "gb200_comm_exchange", "gb200_ivfpq_search_sharded",
 ]
 
 
@@ -97,6 +98,17 @@ def lib():
         L.gb200_ivfpq_replace_list.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_encode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_add_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.gb200_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+        L.gb200_comm_destroy.argtypes = [C.c_void_p]
+        L.gb200_comm_slot_bytes.argtypes = [C.c_void_p]
+        L.gb200_comm_slot_bytes.restype = C.c_int64
+        L.gb200_comm_status.argtypes = [C.c_void_p]
+        L.gb200_comm_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_comm_exchange.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.gb200_ivfpq_search_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_ivfpq_set_opq.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_add_stored.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
         L.gb200_last_scan_kernel_ms.restype = C.c_float
@@ -270,6 +282,13 @@ class B200IVFPQ(_Base):
         c = np.ascontiguousarray(code, dtype=np.uint8)
         return lib().gb200_ivfpq_update(self.h, int(vid), int(new_list), c.ctypes.data)
 
+    def set_opq(self, A, b=None):
+        """OPQ pre-transform y = A x + b of the model (faiss::OPQMatrix), A [d, d]"""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        _check(lib().gb200_ivfpq_set_opq(self.h, A.shape[1], A.shape[0], A.ctypes.data,
+                                         None if bb is None else bb.ctypes.data), "set_opq")
+
     def encode(self, x):
         """stage 1 of GammaIVFPQIndex::Add on the device: (list_no [n] i32, codes [n, M] u8)"""
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -403,3 +422,51 @@ class B200FLAT(_Base):
     def search_dev(self, xq_ptr, n, k, D_ptr, I_ptr, stream_ptr, metric=None, min_score=-FLT_MAX, max_score=FLT_MAX):
         sp = self._sp(self.metric if metric is None else metric, -1, 0, 0, min_score, max_score)
         return lib().gb200_flat_search_dev(self.h, n, xq_ptr, k, C.byref(sp), D_ptr, I_ptr, stream_ptr)
+
+
+COMM_HANDLE_BYTES = 128
+
+
+class Comm:
+    """One rank's endpoint of the multi-GPU result exchange (gb200_comm): peer stores over NVLink, no collective."""
+
+    def __init__(self, device, rank, world, slot_bytes):
+        self.rank, self.world = rank, world
+        self.h = C.c_void_p()
+        self.handle = (C.c_uint8 * COMM_HANDLE_BYTES)()
+        _check(lib().gb200_comm_create(device, rank, world, int(slot_bytes), C.byref(self.h), self.handle), "comm_create")
+        self.slot_bytes = int(lib().gb200_comm_slot_bytes(self.h))
+
+    def handle_bytes(self):
+        return bytes(self.handle)
+
+    def connect(self, all_handles):
+        """all_handles: world entries of COMM_HANDLE_BYTES bytes, rank-major"""
+        blob = b"".join(all_handles)
+        assert len(blob) == self.world * COMM_HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib().gb200_comm_connect(self.h, buf), "comm_connect")
+
+    def buffers(self):
+        mine, allp = C.c_void_p(), C.c_void_p()
+        _check(lib().gb200_comm_buffers(self.h, C.byref(mine), C.byref(allp)), "comm_buffers")
+        return mine.value, allp.value
+
+    def exchange(self, nbytes, stream_ptr):
+        _check(lib().gb200_comm_exchange(self.h, int(nbytes), stream_ptr), "comm_exchange")
+
+    def search_sharded(self, ix, xq_ptr, n, k, stream_ptr, nprobe=-1, recall_num=100, metric=None, has_rank=True):
+        """returns the device address of the gathered window: rank r's block ([n*k] f32, [n*k] i64) at + r * slot_bytes"""
+        sp = ix._sp(ix.metric if metric is None else metric, nprobe, recall_num, has_rank, -FLT_MAX, FLT_MAX)
+        D_all = C.c_void_p()
+        _check(lib().gb200_ivfpq_search_sharded(ix.h, self.h, n, xq_ptr, k, C.byref(sp), C.byref(D_all), None, stream_ptr),
+               "search_sharded")
+        return D_all.value
+
+    def status(self):
+        return int(lib().gb200_comm_status(self.h))
+
+    def close(self):
+        if self.h:
+            lib().gb200_comm_destroy(self.h)
+            self.h = None

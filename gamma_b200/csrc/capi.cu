@@ -137,7 +137,7 @@ struct SearchCtx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_user = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4, 5 bracket the scan kernel alone
   DevBuf ws_xq, ws_xn, ws_dist, ws_keys, ws_cdis, ws_cand, ws_out_d, ws_out_i, ws_flat, ws_lut, ws_xs, ws_fstate, ws_probe,
-      ws_ctl, ws_cmin;
+      ws_ctl, ws_cmin, ws_xt;
   DevBuf valid_filt, filt_bytes, filt_desc;  // per-call range filters -> validity bitmap
   unsigned long long *d_scanned = nullptr;
   int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
@@ -158,7 +158,7 @@ struct SearchCtx {
   void destroy() {
     if (stream) cudaStreamSynchronize(stream);
     DevBuf *bufs[] = {&ws_xq,  &ws_xn, &ws_dist,   &ws_keys,  &ws_cdis, &ws_cand,    &ws_out_d,   &ws_out_i, &ws_flat,
-                      &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc, &ws_cmin};
+                      &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc, &ws_cmin, &ws_xt};
     for (DevBuf *b : bufs) b->release();
     if (d_scanned) cudaFree(d_scanned);
     for (int i = 0; i < 6; i++)
@@ -198,6 +198,8 @@ struct gb200_index {
   std::atomic<bool> trained{false};
   float *d_cent = nullptr, *d_cent_norm = nullptr, *d_pq = nullptr, *d_pq_t = nullptr;
   float *d_cent_small = nullptr;  // centroid - tf32(centroid): second operand of the 3xTF32 tensor-core GEMM
+  // OPQ pre-transform (gb200_ivfpq_set_opq): A transposed [d][d] and the bias, or nullptr
+  float *d_opq_At = nullptr, *d_opq_b = nullptr;
 
   // posting pools: bump allocation, lists grow by allocate-copy-swap at the tail (host tables are writer-only)
   long long pool_cap = 0, pool_used = 0, pool_live_cap = 0;
@@ -340,7 +342,8 @@ static void free_index(gb200_index *ix) {
     delete c;
   }
   void *ptrs[] = {ix->d_raw_small, ix->d_raw_norm, ix->d_cent_small, ix->d_cent, ix->d_cent_norm, ix->d_pq,   ix->d_pq_t, ix->d_codes,
-                  ix->d_ids,       ix->d_norms,    ix->d_off,        ix->d_len,  ix->d_woff,      ix->d_raw,  ix->d_live};
+                  ix->d_ids,       ix->d_norms,    ix->d_off,        ix->d_len,  ix->d_woff,      ix->d_raw,  ix->d_live,
+                  ix->d_opq_At,    ix->d_opq_b};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&ix->w_stage, &ix->w_pub, &ix->inst.valid, &ix->inst.filt_bytes, &ix->inst.filt_desc};
@@ -459,6 +462,32 @@ int gb200_ivfpq_set_quantizers(gb200_index *ix, const float *coarse, const float
   ix->launches += 2;
   CK(cudaStreamSynchronize(ix->wstream));
   ix->trained = true;
+  return GB200_OK;
+}
+
+int gb200_ivfpq_set_opq(gb200_index *ix, int d_in, int d_out, const float *A, const float *b) {
+  if (!ix || ix->kind != 0 || !A) return GB200_EINVAL;
+  if (d_in != ix->p.d || d_out != ix->p.d) {
+    set_err("opq %d -> %d on an index of dimension %d: only d_in == d_out == d is implemented", d_in, d_out, ix->p.d);
+    return GB200_EUNSUPPORTED;
+  }
+  std::lock_guard<std::mutex> w(ix->writer_mu);
+  CKI(use_device(ix));
+  ExclusiveScope x(ix);
+  const int d = ix->p.d;
+  std::vector<float> At((size_t)d * d);
+  for (int o = 0; o < d; o++)
+    for (int k = 0; k < d; k++) At[(size_t)k * d + o] = A[(size_t)o * d + k];
+  if (!ix->d_opq_At) CK(cudaMalloc(&ix->d_opq_At, (size_t)d * d * sizeof(float)));
+  CK(cudaMemcpyAsync(ix->d_opq_At, At.data(), (size_t)d * d * sizeof(float), cudaMemcpyHostToDevice, ix->wstream));
+  if (b) {
+    if (!ix->d_opq_b) CK(cudaMalloc(&ix->d_opq_b, (size_t)d * sizeof(float)));
+    CK(cudaMemcpyAsync(ix->d_opq_b, b, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, ix->wstream));
+  } else if (ix->d_opq_b) {
+    cudaFree(ix->d_opq_b);
+    ix->d_opq_b = nullptr;
+  }
+  CK(cudaStreamSynchronize(ix->wstream));
   return GB200_OK;
 }
 
@@ -1292,9 +1321,10 @@ int gb200_debug_plan(int n, int slots, int nprobe, int recall_num, int s_uniform
 }
 
 // scan + rerank with probes already on the device
-static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, int k, const gb200_search_params *sp,
-                           int nprobe, const int *d_keys, const float *d_cdis, const uint32_t *d_valid,
-                           long long valid_bits, float *d_out_d, long long *d_out_i) {
+// d_xq: the queries the quantizers see (OPQ applied if the model has one); d_xq_raw: as given, for the exact re-rank
+static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, const float *d_xq_raw, int k,
+                           const gb200_search_params *sp, int nprobe, const int *d_keys, const float *d_cdis,
+                           const uint32_t *d_valid, long long valid_bits, float *d_out_d, long long *d_out_i) {
   const int M = ix->p.nsubvector;
   const Tuning &T = ix->tune;
   int R = sp->recall_num < k ? k : sp->recall_num;  // gamma_index_ivfpq.cc:762-765
@@ -1462,7 +1492,7 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   Q.keys = d_keys;
   Q.list_off = ix->d_off;
   Q.ids = ix->d_ids;
-  Q.xq = d_xq;
+  Q.xq = d_xq_raw;
   Q.raw = ix->d_raw;
   Q.nraw = ix->raw_n.load();
   Q.out_dist = d_out_d;
@@ -1535,6 +1565,13 @@ static int ivfpq_search_impl(gb200_index *ix, SearchCtx &c, int n, const float *
     CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     d_xq = c.ws_xq.as<float>();
   }
+  const float *d_xq_raw = d_xq;  // the exact re-rank compares the query as given with the raw vectors
+  if (ix->d_opq_At) {            // opq_->apply(n, xq) (gamma_index_ivfpq.cc:547-555)
+    CKI(c.ws_xt.ensure((size_t)n * d * sizeof(float)));
+    CK(launch_linear_apply(d_xq, d, n, d, ix->d_opq_At, ix->d_opq_b, d, c.ws_xt.as<float>(), c.stream));
+    c.launches++;
+    d_xq = c.ws_xt.as<float>();
+  }
   const uint32_t *d_valid = nullptr;
   long long valid_bits = 0;
   if (use_installed_filter && ix->inst.active) {
@@ -1579,7 +1616,7 @@ static int ivfpq_search_impl(gb200_index *ix, SearchCtx &c, int n, const float *
     d_D = c.ws_out_d.as<float>();
     d_I = c.ws_out_i.as<long long>();
   }
-  CKI(scan_rerank_dev(ix, c, n, d_xq, k, sp, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>(), d_valid, valid_bits, d_D,
+  CKI(scan_rerank_dev(ix, c, n, d_xq, d_xq_raw, k, sp, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>(), d_valid, valid_bits, d_D,
                       d_I));
   if (!out_on_dev) {
     CK(cudaMemcpyAsync(D, d_D, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -1649,9 +1686,15 @@ int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, floa
   const int d = ix->p.d;
   CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
   CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  const float *d_q = c.ws_xq.as<float>();
+  if (ix->d_opq_At) {
+    CKI(c.ws_xt.ensure((size_t)n * d * sizeof(float)));
+    CK(launch_linear_apply(d_q, d, n, d, ix->d_opq_At, ix->d_opq_b, d, c.ws_xt.as<float>(), c.stream));
+    d_q = c.ws_xt.as<float>();
+  }
   CKI(c.ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
   CKI(c.ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
-  CKI(coarse_dev(ix, c, n, c.ws_xq.as<float>(), nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
+  CKI(coarse_dev(ix, c, n, d_q, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
   std::vector<int> k32((size_t)n * nprobe);
   CK(cudaMemcpyAsync(k32.data(), c.ws_keys.p, k32.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaMemcpyAsync(coarse_dis, c.ws_cdis.p, (size_t)n * nprobe * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -1671,14 +1714,19 @@ static int encode_dev(gb200_index *ix, SearchCtx &c, int64_t n, const float *d_x
   for (int64_t s0 = 0; s0 < n; s0 += CH) {
     const int m = (int)std::min<int64_t>(CH, n - s0);
     const float *rows = d_x + (size_t)s0 * x_stride;
-    if (x_stride != d) {  // ConvertVectorDim: zero-pad to d for the distance producer
+    if (ix->d_opq_At) {  // opq_->apply (gamma_index_ivfpq.cc:448-450); reads x_stride columns, zero beyond
+      CKI(c.ws_xt.ensure((size_t)m * d * sizeof(float)));
+      CK(launch_linear_apply(rows, x_stride, m, d, ix->d_opq_At, ix->d_opq_b, d, c.ws_xt.as<float>(), c.stream));
+      c.launches++;
+      rows = c.ws_xt.as<float>();
+    } else if (x_stride != d) {  // ConvertVectorDim: zero-pad to d for the distance producer
       CKI(c.ws_xq.ensure((size_t)m * d * sizeof(float)));
       CK(cudaMemsetAsync(c.ws_xq.p, 0, (size_t)m * d * sizeof(float), c.stream));
       CK(cudaMemcpy2DAsync(c.ws_xq.p, (size_t)d * sizeof(float), rows, (size_t)x_stride * sizeof(float),
                            (size_t)x_stride * sizeof(float), m, cudaMemcpyDeviceToDevice, c.stream));
       rows = c.ws_xq.as<float>();
     }
-    const int stride = x_stride != d ? d : x_stride;
+    const int stride = (ix->d_opq_At || x_stride != d) ? d : x_stride;
     CKI(c.ws_keys.ensure((size_t)m * sizeof(int)));
     CKI(c.ws_cdis.ensure((size_t)m * sizeof(float)));
     CKI(coarse_dev(ix, c, m, rows, 1, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));

@@ -115,6 +115,9 @@ cudaError_t launch_compact_lists(const CompactParams &P, int n_lists, cudaStream
 
 // K1 — coarse quantiser: dist[n][nlist] = |q|^2 + |c|^2 - 2 q.c (clamped at 0), then top-nprobe
 cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st);
+// OPQ pre-transform: y = A x + b for every row (At = A transposed, [d_in][d_out]; x rows x_stride wide, zero beyond)
+cudaError_t launch_linear_apply(const float *x, int x_stride, int rows, int d_in, const float *At, const float *b,
+                                int d_out, float *y, cudaStream_t st);
 // |x|^2 and x - tf32(x) of every row in one pass (the query side of the tensor-core distance producer)
 cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st);
 cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,

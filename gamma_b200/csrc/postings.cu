@@ -264,6 +264,28 @@ cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, floa
   return cudaGetLastError();
 }
 
+// y[r][o] = b[o] + sum_k x[r][k] * At[k][o]   (At = A transposed: [d_in][d_out]; OPQMatrix::apply, fp32 FMA chain over k)
+__global__ void __launch_bounds__(256) linear_apply_kernel(const float *__restrict__ x, int x_stride, int d_in,
+                                                           const float *__restrict__ At, const float *__restrict__ b,
+                                                           int d_out, float *__restrict__ y) {
+  extern __shared__ float xs[];
+  const int r = blockIdx.x;
+  for (int k = threadIdx.x; k < d_in; k += blockDim.x) xs[k] = k < x_stride ? x[(size_t)r * x_stride + k] : 0.f;
+  __syncthreads();
+  for (int o = threadIdx.x; o < d_out; o += blockDim.x) {
+    float s = b ? b[o] : 0.f;
+    for (int k = 0; k < d_in; k++) s = fmaf(xs[k], __ldg(At + (size_t)k * d_out + o), s);
+    y[(size_t)r * d_out + o] = s;
+  }
+}
+cudaError_t launch_linear_apply(const float *x, int x_stride, int rows, int d_in, const float *At, const float *b,
+                                int d_out, float *y, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int threads = d_out >= 256 ? 256 : ((d_out + 31) & ~31);
+  linear_apply_kernel<<<rows, threads, (size_t)d_in * sizeof(float), st>>>(x, x_stride, d_in, At, b, d_out, y);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   row_norms_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, d, out);

@@ -5,6 +5,8 @@
 
 #include <algorithm>
 
+#include <faiss/VectorTransform.h>
+
 #include "common/gamma_common_data.h"
 #include "table/range_query_result.h"
 #include "vector/raw_vector.h"
@@ -99,8 +101,8 @@ gb200_ivfpq_params B200IVFPQIndex::DeviceParams() const {
 int B200IVFPQIndex::Init(const std::string &model_parameters, int indexing_size) {
   int ret = GammaIVFPQIndex::Init(model_parameters, indexing_size);
   if (ret) return ret;
-  if (opq_ != nullptr || quantizer_type_ != 0) {
-    LOG(ERROR) << "B200IVFPQ: opq / hnsw coarse quantizer are not supported";
+  if (quantizer_type_ != 0) {
+    LOG(ERROR) << "B200IVFPQ: the hnsw coarse quantizer is not supported";
     return -1;
   }
   if (MultiVidStore(vector_)) {
@@ -121,6 +123,11 @@ int B200IVFPQIndex::PushQuantizers() {
   faiss::IndexFlat *flat = dynamic_cast<faiss::IndexFlat *>(this->quantizer);
   if (!flat || !this->is_trained) return -1;
   int rc = gb200_ivfpq_set_quantizers(dev_, flat->xb.data(), this->pq.centroids.data());
+  if (rc == 0 && opq_ != nullptr) {  // model parameter "opq": the trained OPQMatrix travels with the quantizers
+    faiss::LinearTransform *lt = dynamic_cast<faiss::LinearTransform *>(opq_);
+    if (!lt) return -1;
+    rc = gb200_ivfpq_set_opq(dev_, lt->d_in, lt->d_out, lt->A.data(), lt->have_bias ? lt->b.data() : nullptr);
+  }
   if (rc == 0) quantizers_pushed_ = true;
   return rc;
 }

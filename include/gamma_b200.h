@@ -122,6 +122,13 @@ int gb200_ivfpq_compact(gb200_index *ix, int32_t list_no, int64_t *dropped);
  * happened to it: the new content goes into a fresh region and is swapped in by publication, searches keep running. */
 int gb200_ivfpq_replace_list(gb200_index *ix, int32_t list_no, int64_t n, const int64_t *ids, const uint8_t *codes);
 
+/* OPQ pre-transform of the model (model parameter "opq", faiss::OPQMatrix: y = A x + b; index/impl/gamma_index_ivfpq.cc:
+ * 158-165 creates it, :338-341 trains it, :448-450 / :547-555 apply it to added vectors and to queries).  Once set,
+ * queries are transformed on the device before the coarse quantiser and the table build, added vectors before
+ * assign / encode; re-rank keeps using the raw query against the raw vectors (:706).  A: d_out x d_in row-major with
+ * d_in == d_out == d; b: d_out floats or NULL.                                                                       */
+int gb200_ivfpq_set_opq(gb200_index *ix, int d_in, int d_out, const float *A, const float *b);
+
 /* ---- encode on the device: stage 1 of GammaIVFPQIndex::Add (index/impl/gamma_index_ivfpq.cc:424-476) —
  * quantizer->assign (the tensor-core coarse stage with nprobe = 1), compute_residuals, pq.compute_codes with faiss'
  * own sub-distance arithmetic (codes are bit-identical to the CPU engine's for nsubvector slices narrower than 16
@@ -212,6 +219,32 @@ int gb200_sync(gb200_index *ix);
 /* Tuning knobs (GB200_* environment variables) are read once when an index is created; this re-reads
  * them for an existing index (A/B runs in bench.py and the tests).                           */
 int gb200_reload_tuning(gb200_index *ix);
+
+/* ---- multi-GPU: one process per GPU, index replicated, batch sharded by query.  Replaces the host-side
+ * merge of faiss IndexReplicas / IndexShards the reference's GPU model relies on (index/impl/gpu/gamma_gpu_cloner.cpp:
+ * 209-212).  Every rank owns a result window in device memory; after its search it stores its [n][k] block into every
+ * peer's window over NVLink (peer memory mapped through CUDA IPC) and waits for theirs — one kernel, no collective
+ * library on the data path.  The opaque handles travel between the processes by whatever channel the host has
+ * (MPI, torch.distributed, a file).                                                                                  */
+typedef struct gb200_comm gb200_comm;
+#define GB200_COMM_HANDLE_BYTES 128
+/* slot_bytes >= n * k * 12 of the largest per-rank batch; handle: GB200_COMM_HANDLE_BYTES bytes to hand to the peers */
+int gb200_comm_create(int device, int rank, int world, int64_t slot_bytes, gb200_comm **out, uint8_t *handle);
+/* handles: world x GB200_COMM_HANDLE_BYTES, rank-major (this rank's own entry is ignored) */
+int gb200_comm_connect(gb200_comm *c, const uint8_t *handles);
+int gb200_comm_destroy(gb200_comm *c);
+int64_t gb200_comm_slot_bytes(gb200_comm *c);
+/* 0 = every exchange so far saw all peers; 1 + p = peer p did not arrive within ~4 s (synchronises the device)       */
+int gb200_comm_status(gb200_comm *c);
+/* device pointers for the NEXT exchange: where this rank's result goes ([n*k] f32 then [n*k] i64) and the start of the
+ * gathered window (rank r's block at all_slots + r * slot_bytes)                                                       */
+int gb200_comm_buffers(gb200_comm *c, void **my_slot, void **all_slots);
+/* push the block written into my_slot to every peer and wait for theirs, all on `stream`                              */
+int gb200_comm_exchange(gb200_comm *c, int64_t bytes, void *stream);
+/* search this rank's n queries (device pointers) and exchange: afterwards (in stream order) rank r's distances are at
+ * *D_all + r * slot_bytes / 4 ... — see gb200_comm_buffers for the layout                                             */
+int gb200_ivfpq_search_sharded(gb200_index *ix, gb200_comm *c, int n, const float *xq_dev, int k,
+                               const gb200_search_params *sp, float **D_all, int64_t **I_all_of_rank0, void *stream);
 
 /* ---- test hook (not used by the plugin): run the streaming top-R selection primitive the scan
  * kernels use (append + radix-select prune, one CTA of `threads`) on caller-provided 64-bit keys fed

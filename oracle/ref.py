@@ -50,6 +50,8 @@ def lib():
         _lib.oref_list_size.restype = C.c_long
         _lib.oref_list_size.argtypes = [C.c_void_p, C.c_long]
         _lib.oref_get_list.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        _lib.oref_opq_dims.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oref_get_opq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oref_coarse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.oref_set_trained.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oref_inject_postings.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -141,6 +143,16 @@ class RefIndex:
         out = np.empty((self.info("M"), self.info("ksub"), self.info("dsub")), np.float32)
         assert lib().oref_get_pq(self.h, out.ctypes.data) == 0
         return out
+
+    def opq(self):
+        """(A [d_out, d_in], b [d_out] or None) of the model's OPQ pre-transform, or None without one"""
+        di, do, hb = C.c_int(0), C.c_int(0), C.c_int(0)
+        if not lib().oref_opq_dims(self.h, C.byref(di), C.byref(do), C.byref(hb)):
+            return None
+        A = np.empty((do.value, di.value), np.float32)
+        b = np.empty(do.value, np.float32) if hb.value else None
+        assert lib().oref_get_opq(self.h, A.ctypes.data, b.ctypes.data if b is not None else None) == 0
+        return A, b
 
     def get_list(self, list_no):
         n = lib().oref_list_size(self.h, list_no)

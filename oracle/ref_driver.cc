@@ -33,6 +33,7 @@
 #include "vector/raw_vector_factory.h"
 
 #include <faiss/IndexFlat.h>
+#include <faiss/VectorTransform.h>
 
 INITIALIZE_EASYLOGGINGPP
 
@@ -201,6 +202,25 @@ int oref_get_pq(void *h, float *out) {
   OracleRef *o = (OracleRef *)h;
   const std::vector<float> &c = o->ivfpq->pq.centroids;  // [M][ksub][dsub]
   memcpy(out, c.data(), sizeof(float) * c.size());
+  return 0;
+}
+
+// OPQ pre-transform of the reference model (faiss::OPQMatrix : LinearTransform), if the index was created with "opq"
+int oref_opq_dims(void *h, int *d_in, int *d_out, int *have_bias) {
+  OracleRef *o = (OracleRef *)h;
+  faiss::LinearTransform *lt = o->ivfpq ? dynamic_cast<faiss::LinearTransform *>(o->ivfpq->opq_) : nullptr;
+  if (!lt) return 0;
+  *d_in = lt->d_in;
+  *d_out = lt->d_out;
+  *have_bias = lt->have_bias ? 1 : 0;
+  return 1;
+}
+int oref_get_opq(void *h, float *A, float *b) {
+  OracleRef *o = (OracleRef *)h;
+  faiss::LinearTransform *lt = o->ivfpq ? dynamic_cast<faiss::LinearTransform *>(o->ivfpq->opq_) : nullptr;
+  if (!lt) return -1;
+  memcpy(A, lt->A.data(), sizeof(float) * lt->A.size());
+  if (lt->have_bias && b) memcpy(b, lt->b.data(), sizeof(float) * lt->b.size());
   return 0;
 }
 

@@ -1,0 +1,74 @@
+"""Worker of tests/test_comm_gpu.py: one process per GPU.  argv: rank world tmpdir"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    import torch
+    from gamma_b200 import api, builder, synth
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda:%d" % rank)
+    N, d, nlist, M, n, k = 30000, 64, 64, 32, 96, 10
+    xb = synth.mixture(N, d, 7, n_clusters=64)
+    xq = synth.mixture(n * world, d, 8, n_clusters=64)
+    cache = os.path.join(tmp, "ix.npz")
+    if rank == 0:
+        coarse, pq, list_no, codes = builder.build_ivfpq(xb, nlist, M, device=str(dev))
+        np.savez(cache + ".tmp.npz", a=coarse, b=pq, c=list_no, d=codes)
+        os.replace(cache + ".tmp.npz", cache)
+    else:
+        while not os.path.exists(cache):
+            time.sleep(0.1)
+        time.sleep(0.2)
+        z = np.load(cache)
+        coarse, pq, list_no, codes = z["a"], z["b"], z["c"], z["d"]
+    ix = api.B200IVFPQ(rank)
+    assert ix.Init(json.dumps({"ncentroids": nlist, "nsubvector": M, "metric_type": "L2", "nprobe": 8}), d) == 0
+    ix.set_quantizers(coarse, pq)
+    assert ix.append(list_no, np.arange(N, dtype=np.int64), codes) == 0
+    ix.upload_raw(xb)
+    comm = api.Comm(rank, rank, world, n * k * 12)
+    with open(os.path.join(tmp, "h%d.tmp" % rank), "wb") as f:
+        f.write(comm.handle_bytes())
+    os.replace(os.path.join(tmp, "h%d.tmp" % rank), os.path.join(tmp, "h%d" % rank))
+    handles = []
+    for p in range(world):
+        path = os.path.join(tmp, "h%d" % p)
+        t0 = time.time()
+        while not os.path.exists(path):
+            assert time.time() - t0 < 120, "peer %d never published its handle" % p
+            time.sleep(0.05)
+        handles.append(open(path, "rb").read())
+    comm.connect(handles)
+    # the whole batch on this GPU alone = what the gathered result must equal
+    rc, D_full, I_full = ix.Search(xq, k, nprobe=8, recall_num=50, metric="L2", has_rank=True)
+    assert rc == 0
+    xq_d = torch.from_numpy(np.ascontiguousarray(xq[rank * n:(rank + 1) * n])).to(dev)
+    stream = torch.cuda.current_stream()
+    ok = True
+    for it in range(6):  # several epochs: both window buffers, flags running on
+        base = comm.search_sharded(ix, xq_d.data_ptr(), n, k, stream.cuda_stream, nprobe=8, recall_num=50, metric="L2")
+        torch.cuda.synchronize()
+        host = torch.empty(world * comm.slot_bytes, dtype=torch.uint8)
+        torch.cuda.cudart().cudaMemcpy(host.data_ptr(), base, world * comm.slot_bytes, 2)
+        for r in range(world):
+            blk = host[r * comm.slot_bytes:(r + 1) * comm.slot_bytes]
+            D = blk[:n * k * 4].view(torch.float32).numpy().reshape(n, k)
+            I = blk[n * k * 4:n * k * 12].view(torch.int64).numpy().reshape(n, k)
+            ok &= bool(np.array_equal(I, I_full[r * n:(r + 1) * n]) and np.array_equal(D, D_full[r * n:(r + 1) * n]))
+    st = comm.status()
+    print(json.dumps(dict(rank=rank, ok=ok, status=st)), flush=True)
+    comm.close()
+    return 0 if (ok and st == 0) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -115,20 +115,23 @@ class RefFixture:
     """A reference (oracle/_ref) IVFPQ index over seeded synthetic data + everything needed to
     mirror it into the device library."""
 
-    def __init__(self, N, d, nlist, M, metric, nq=64, n_clusters=64, seed_shift=0):
+    def __init__(self, N, d, nlist, M, metric, nq=64, n_clusters=64, seed_shift=0, extra_params=None):
         from gamma_b200 import synth
         from oracle import ref
         self.N, self.d, self.nlist, self.M, self.metric = N, d, nlist, M, metric
         normalize = metric != "L2"
         self.xb = synth.mixture(N, d, synth.SEED_BASE + seed_shift, n_clusters=n_clusters, normalize=normalize)
         self.xq = synth.mixture(nq, d, synth.SEED_QUERY + seed_shift, n_clusters=n_clusters, normalize=normalize)
-        self.model_json = json.dumps({"ncentroids": nlist, "nsubvector": M, "metric_type": metric, "nprobe": 8})
+        mp = {"ncentroids": nlist, "nsubvector": M, "metric_type": metric, "nprobe": 8}
+        mp.update(extra_params or {})
+        self.model_json = json.dumps(mp)
         self.ref = ref.RefIndex(d, "IVFPQ", self.model_json, indexing_size=N, bitmap_bits=max(N * 2, 1024))
         self.ref.add_raw(self.xb)
         self.ref.indexing()
         self.ref.add_to_index()
         self.centroids = self.ref.centroids()
         self.pq = self.ref.pq_centroids()
+        self.opq = self.ref.opq()  # (A, b) when the model was created with "opq"
         self.lists = self.ref.lists()
         self.deleted = []  # docs deleted in the (cached, shared) reference index; mirror() replays them
 
@@ -144,6 +147,8 @@ class RefFixture:
         ix = api.B200IVFPQ(device)
         assert ix.Init(self.model_json, self.d) == 0, api.lib().gb200_last_error()
         ix.set_quantizers(self.centroids, self.pq)
+        if self.opq is not None:
+            ix.set_opq(*self.opq)
         list_no = np.concatenate([np.full(len(ids), l, np.int32) for l, (ids, _) in enumerate(self.lists)])
         vids = np.concatenate([ids for ids, _ in self.lists])
         codes = np.concatenate([c for _, c in self.lists])

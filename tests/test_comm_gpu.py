@@ -1,0 +1,28 @@
+"""Multi-GPU result exchange behind the C-ABI (gb200_comm_*, gb200_ivfpq_search_sharded): one process per GPU, every
+rank searches its shard of the batch and pushes its top-k into every peer's window over NVLink; the gathered result on
+every rank must equal the single-GPU search of the whole batch.  Needs >= 2 GPUs (skipped on a one-GPU box; run with
+`gpurun --gpus 2`)."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_search_gathers_on_every_rank():
+    from gamma_b200 import api
+    world = min(api.lib().gb200_device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    tmp = tempfile.mkdtemp(prefix="gb200_comm_")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "comm_worker.py"), str(r), str(world), tmp],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for r, (p, (so, se)) in enumerate(zip(procs, outs)):
+        lines = [json.loads(l) for l in so.splitlines() if l.startswith("{")]
+        assert p.returncode == 0 and lines and lines[-1]["ok"] and lines[-1]["status"] == 0, (r, so[-2000:], se[-2000:])

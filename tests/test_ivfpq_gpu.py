@@ -341,3 +341,36 @@ def test_m64_default_kernel_parity(metric):
     rc, D, I = ix.Search(f.xq, 10, nprobe=16, recall_num=700, metric=metric, has_rank=True)
     assert rc == 0
     assert_rerank_parity(f, ix, f.xq, 10, 16, 700, metric, D, I)
+
+
+def test_opq_model_parity():
+    """Model parameter "opq": queries and added vectors go through the OPQ matrix before the quantizers, the re-rank keeps
+    the raw query (gamma_index_ivfpq.cc:158-165, 448-450, 547-555, 706).  The reference applies the matrix through sgemm,
+    the device with an fp32 FMA chain: ADC distances agree to 1e-4, re-ranked distances are bit-identical, encoded codes
+    agree except where the two roundings fall on different sides of a PQ cell boundary."""
+    f = get_ref_fixture("l2_m16_opq", N=20000, d=64, nlist=32, M=16, metric="L2", nq=48, n_clusters=32, seed_shift=9,
+                        extra_params={"opq": {"nsubvector": 16}})
+    assert f.opq is not None
+    ix = f.mirror()
+    nprobe, R, k = 8, 60, 10
+    cd_ref, k_ref = f.ref.coarse(f.xq @ f.opq[0].T + (0 if f.opq[1] is None else f.opq[1]), nprobe)
+    cd, kk = ix.coarse(f.xq, nprobe)
+    r = compare_topk(cd_ref, k_ref, cd, kk, rtol=1e-4, atol=1e-4)
+    assert r["n_id_mismatch_unexplained"] == 0 and r["max_rel_err"] <= 1e-4, r
+    D_ref, I_ref = f.ref.search(f.xq, R, rj(nprobe, R, "L2"), has_rank=False)
+    rc, D, I = ix.Search(f.xq, R, nprobe=nprobe, recall_num=R, metric="L2", has_rank=False)
+    assert rc == 0
+    assert_topk_parity(D_ref, I_ref, D, I, rtol=1e-4, atol=1e-5)
+    rc, D, I = ix.Search(f.xq, k, nprobe=nprobe, recall_num=R, metric="L2", has_rank=True)
+    assert rc == 0
+    assert assert_rerank_parity(f, ix, f.xq, k, nprobe, R, "L2", D, I) > 0.99
+    # encode through the same transform
+    ln, cd_ = ix.encode(f.xb[:4000])
+    ref_l = np.full(f.N, -1, np.int32)
+    ref_c = np.zeros((f.N, f.M), np.uint8)
+    for l, (ids, cds) in enumerate(f.lists):
+        ref_l[ids] = l
+        ref_c[ids] = cds
+    same = ln == ref_l[:4000]
+    assert same.mean() > 0.998
+    assert (cd_[same] == ref_c[:4000][same]).mean() > 0.999
