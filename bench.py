@@ -666,6 +666,9 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample of the batch for the CPU engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variants", default="", help="dev only: ';'-separated ENV=VAL[,ENV=VAL] sets to time after the main run")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: result exchange by peer stores over NVLink behind the C-ABI (gb200_ivfpq_search_sharded, "
+                         "default) or by an NCCL all-gather of the packed top-k")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -773,19 +776,36 @@ def main():
     out_bytes = out_d.numel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
+    comm = None
+    p2p = world > 1 and args.exchange == "p2p"
     if world > 1:
         import torch.distributed as dist
         out_all = torch.empty(world * out_bytes, dtype=torch.uint8, device=dev)  # rank r's block at r * out_bytes
+    if p2p:
+        # the exchange lives behind the C-ABI: every rank stores its top-k into every peer's window over NVLink; the
+        # host only carries the opaque IPC handles between the processes once
+        comm = api.Comm(local, rank, world, out_bytes)
+        hs = [None] * world
+        dist.all_gather_object(hs, comm.handle_bytes())
+        comm.connect(hs)
+    gathered = [0]  # device address of the gathered window of the last sharded search
 
-    def step_dev():
+    def step_plain():
         rc_ = ix.search_dev(xq_d.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
                             nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
         assert rc_ == 0, api.lib().gb200_last_error()
+
+    def step_dev():
+        if p2p:
+            gathered[0] = comm.search_sharded(ix, xq_d.data_ptr(), n, K_TOP, stream.cuda_stream, nprobe=w["nprobe"],
+                                              recall_num=RECALL_NUM, metric="L2", has_rank=True)
+            return
+        step_plain()
         if world > 1:
             dist.all_gather_into_tensor(out_all, out_d)
 
     # correctness side: recall@10 vs exact ground truth (and the raw result for the CPU cross-check)
-    step_dev()
+    step_plain()
     torch.cuda.synchronize()
     I_ours = I_d.cpu().numpy().copy()
     valid_mask = None
@@ -857,7 +877,7 @@ def main():
     load_for(400)
     clocks = sampler.stop(mark0, mark1)
     if world > 1:
-        launches += args.steps  # the NCCL all-gather per step
+        launches += args.steps  # the exchange kernel (or the NCCL all-gather) per step
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -925,6 +945,13 @@ def main():
         # N > 1: the whole query-sharded path — H2D of this rank's queries, search, the all-gather of every rank's top-k
         # over NVLink, D2H of the gathered result — so that e2e contains the exchange
         xq_stage.copy_(xq_pin, non_blocking=True)
+        if p2p:
+            base = comm.search_sharded(ix, xq_stage.data_ptr(), n, K_TOP, stream.cuda_stream, nprobe=w["nprobe"],
+                                       recall_num=RECALL_NUM, metric="L2", has_rank=True)
+            for r_ in range(world):  # rank r's block sits at r * slot_bytes in the window
+                comm.read(out_all_pin.data_ptr() + r_ * out_bytes, base + r_ * comm.slot_bytes, out_bytes,
+                          stream.cuda_stream, sync=(r_ == world - 1))
+            return
         rc_ = ix.search_dev(xq_stage.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
                             nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
         assert rc_ == 0, api.lib().gb200_last_error()
@@ -950,6 +977,11 @@ def main():
         mine = out_all_pin[rank * out_bytes:(rank + 1) * out_bytes][n * K_TOP * 4:].view(torch.int64).numpy().reshape(n, K_TOP)
         assert np.array_equal(mine, I_ours), "gathered result of this rank differs from its device-API result"
 
+    if comm is not None:
+        st_ = comm.status()
+        assert st_ == 0, "exchange: peer %d did not arrive" % (st_ - 1)
+        dist.barrier()
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -997,15 +1029,17 @@ def main():
                data="synthetic",
                config=dict(workload=w["desc"], N=N, nlist=nlist, M=w["M"], nprobe=w["nprobe"], batch_per_gpu=n,
                            global_batch=world * n, k=K_TOP, recall_num=RECALL_NUM, has_rank=True,
-                           parallelism="query-sharded x%d, index replicated, NCCL all-gather of top-k" % world,
+                           parallelism="query-sharded x%d, index replicated, %s" % (
+                               world, "top-k pushed into every peer's window over NVLink (gb200_ivfpq_search_sharded)" if p2p
+                               else "NCCL all-gather of top-k"),
                            l2="256 MB flush write between steps (untimed); per-step CUDA events",
                            ms_per_step_back_to_back_no_flush=ms_noflush, scaled_down=args.scale != 1.0),
                roofline=roofline, cpu_baseline=cpu,
                e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * w["d"] * 4),
                         d2h_bytes_per_step=int(n * K_TOP * 12 * (world if world > 1 else 1)),
                         path=("gb200_ivfpq_search (host C-ABI, pinned host buffers)" if world == 1 else
-                              "per rank: H2D queries, gb200_ivfpq_search_dev, NCCL all-gather of the packed top-k, D2H of "
-                              "the gathered result")),
+                              "per rank: H2D queries, search + exchange (%s), D2H of the gathered result" % (
+                                  "gb200_ivfpq_search_sharded" if p2p else "gb200_ivfpq_search_dev + NCCL all-gather"))),
                gpu_launches=int(launches), clocks=clocks, recall_at_10=rec_ours)
     print(json.dumps(out), flush=True)
     if world > 1:

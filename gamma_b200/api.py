@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status", "gb200_comm_read",
     "gb200_comm_buffers", "gb200_comm_exchange", "gb200_ivfpq_search_sharded",
 ]
 
@@ -104,6 +104,7 @@ def lib():
         L.gb200_comm_slot_bytes.argtypes = [C.c_void_p]
         L.gb200_comm_slot_bytes.restype = C.c_int64
         L.gb200_comm_status.argtypes = [C.c_void_p]
+        L.gb200_comm_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.gb200_comm_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gb200_comm_exchange.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.gb200_ivfpq_search_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
@@ -465,6 +466,9 @@ class Comm:
 
     def status(self):
         return int(lib().gb200_comm_status(self.h))
+
+    def read(self, dst_host_ptr, src_dev_ptr, nbytes, stream_ptr, sync=False):
+        _check(lib().gb200_comm_read(self.h, dst_host_ptr, src_dev_ptr, int(nbytes), stream_ptr, 1 if sync else 0), "comm_read")
 
     def close(self):
         if self.h:

@@ -261,11 +261,7 @@ __global__ void __launch_bounds__(CW_THREADS) coarse_select_row_kernel(const flo
 // one shared atomic each (rare), ranking as above.  The bisection fallback (survivors overflow the buffer,
 // e.g. thousands of equal distances) runs on the 64-bit keys so that it terminates on ties.
 // ---------------------------------------------------------------------------------------------
-// TIGHT (opt-in, GB200_COARSE_TIGHT=1, not yet validated on hardware): the threshold is the nprobe-th smallest of
-// G >= 2 * nprobe group minima instead of the largest of G >= nprobe ones — still an upper bound of the nprobe-th
-// smallest element (nprobe distinct elements lie at or below it) but it leaves ~1.5 * nprobe survivors instead of
-// ~G ln G, and the rank-by-counting over the survivors is half of this kernel's time (profiles/r01c).
-template <int V, bool TIGHT = false>
+template <int V>
 __global__ void __launch_bounds__(CW_THREADS, 2) coarse_select_reg_kernel(const float *__restrict__ dist, int nlist,
                                                                        int nprobe, int G, int *__restrict__ keys,
                                                                        float *__restrict__ coarse_dis) {
@@ -295,27 +291,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) coarse_select_reg_kernel(const 
   gminf[tid] = m;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  if (TIGHT) {
-    // G group minima (G = 64 / 128 / 256 >= 2 * nprobe), group g = threads g, g + G, ...; every thread of the first G
-    // ranks its group's minimum among the G (ties by group index) and the one of rank nprobe - 1 publishes it
-    __shared__ float gm_s[CW_THREADS];
-    if (tid == 0) s_tauf = INF;  // fewer than nprobe finite group minima: everything finite survives
-    if (tid < G) {
-      float gm = INF;
-      for (int j = tid; j < CW_THREADS; j += G) gm = fminf(gm, gminf[j]);
-      gm_s[tid] = gm;
-    }
-    __syncthreads();
-    if (tid < G) {
-      const float mine = gm_s[tid];
-      int r = 0;
-      for (int j = 0; j < G; j++) {
-        const float o = gm_s[j];
-        r += (o < mine) || (o == mine && j < tid);
-      }
-      if (r == nprobe - 1 && mine < INF) s_tauf = mine;
-    }
-  } else if (tid < 32) {  // fold the 256 thread minima into G group minima, tau0 = their maximum
+  if (tid < 32) {  // fold the 256 thread minima into G group minima, tau0 = their maximum
     float t = -INF;
     for (int g = tid; g < G; g += 32) {
       float gm = INF;
@@ -517,15 +493,10 @@ cudaError_t launch_coarse_select_cmin(const float *dist, const float *cmin, int 
 
 cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe, int *keys, float *coarse_dis,
                                  cudaStream_t st) {
-  if (nprobe <= 128 && !getenv("GB200_COARSE_SELECT_CTA")) {
+  if (nprobe <= 128) {
     const int G = nprobe <= 32 ? 32 : (nprobe <= 64 ? 64 : 128);
     const bool aligned = (nlist & 3) == 0 && ((uintptr_t)dist & 15) == 0;
-    if (aligned && nlist <= CW_THREADS * 4 * 16 && nlist >= nprobe && !getenv("GB200_COARSE_SELECT_ROW")) {
-      if (getenv("GB200_COARSE_TIGHT") && nlist > CW_THREADS * 4 * 4) {  // opt-in, large nlist only
-        const int G2 = nprobe <= 32 ? 64 : (nprobe <= 64 ? 128 : 256);
-        coarse_select_reg_kernel<16, true><<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G2, keys, coarse_dis);
-        return cudaGetLastError();
-      }
+    if (aligned && nlist <= CW_THREADS * 4 * 16 && nlist >= nprobe) {
       if (nlist <= CW_THREADS * 4 * 4)
         coarse_select_reg_kernel<4><<<n, CW_THREADS, 0, st>>>(dist, nlist, nprobe, G, keys, coarse_dis);
       else
@@ -543,11 +514,9 @@ cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe
   if (cap <= 4 * CS_THREADS) {
     coarse_select_kernel<4><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   } else {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {  // per device and cheap: no process-wide cache
       cudaError_t e = cudaFuncSetAttribute(coarse_select_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = smem;
     }
     coarse_select_kernel<16><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   }

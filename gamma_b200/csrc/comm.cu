@@ -188,6 +188,16 @@ int gb200_ivfpq_search_sharded(gb200_index *ix, gb200_comm *c, int n, const floa
 
 int64_t gb200_comm_slot_bytes(gb200_comm *c) { return c ? c->slot_bytes : 0; }
 
+// device -> host copy of (part of) the gathered window on `stream`; sync != 0 also waits for it
+int gb200_comm_read(gb200_comm *c, void *dst_host, const void *src_dev, int64_t bytes, void *stream, int sync) {
+  if (!c || !dst_host || !src_dev || bytes < 0) return GB200_EINVAL;
+  if (cudaSetDevice(c->device) != cudaSuccess) return GB200_ECUDA;
+  if (cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
+    return GB200_ECUDA;
+  if (sync && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return GB200_ECUDA;
+  return GB200_OK;
+}
+
 // 0 = every exchange so far saw all peers; 1 + p = peer p did not arrive within the time limit (synchronises the device)
 int gb200_comm_status(gb200_comm *c) {
   if (!c || !c->d_err) return 0;

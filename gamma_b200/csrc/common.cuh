@@ -295,6 +295,52 @@ struct BlockTopR {
 
 };
 
+// ---------------------------------------------------------------------------
+// Exact L2^2 / inner product in the summation order of faiss' AVX kernels (utils/distances_simd.cpp:366-431, as
+// compiled for the reference): 8 strided partial sums (mul then add, unfused), hi + lo halves, fused 4-wide and masked
+// tails, two horizontal adds — re-ranked and FLAT distances are bit-identical to the CPU engine's.
+// ---------------------------------------------------------------------------
+// 8 consecutive lanes (an "octet") cooperate on one candidate; returns the result in every lane of the octet
+template <bool IP>
+__device__ __forceinline__ float exact_distance_octet(const float *__restrict__ q, const float *__restrict__ y,
+                                                      int d, int sub /*0..7*/) {
+  float s = 0.f;
+  int d8 = d & ~7;
+  for (int i = sub; i < d8; i += 8) {
+    float a = q[i], b = __ldg(y + i);
+    if (IP) {
+      s = __fadd_rn(s, __fmul_rn(a, b));
+    } else {
+      float t = __fsub_rn(a, b);
+      s = __fadd_rn(s, __fmul_rn(t, t));
+    }
+  }
+  // msum2 = hi + lo
+  float other = __shfl_down_sync(GB_FULL, s, 4, 8);
+  float t4 = __fadd_rn(other, s);  // valid in sub 0..3
+  int rem = d - d8;
+  if (rem >= 4) {
+    if (sub < 4) {
+      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
+    }
+    d8 += 4;
+    rem -= 4;
+  }
+  if (rem > 0) {
+    if (sub < rem) {
+      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
+    }
+  }
+  // hadd, hadd: (t0 + t1) + (t2 + t3)
+  float n1 = __shfl_xor_sync(GB_FULL, t4, 1, 8);
+  float p = __fadd_rn(t4, n1);  // lanes 0,1: t0+t1 ; lanes 2,3: t2+t3
+  float n2 = __shfl_xor_sync(GB_FULL, p, 2, 8);
+  float r = __fadd_rn(p, n2);
+  return __shfl_sync(GB_FULL, r, 0, 8);
+}
+
 // In-place bitonic sort (ascending) of n = power of two u64 keys in shared memory. collective.
 __device__ __forceinline__ void block_bitonic_sort(u64 *a, int n) {
   for (int k = 2; k <= n; k <<= 1) {

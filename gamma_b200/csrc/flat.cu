@@ -16,42 +16,6 @@ constexpr int FL_THREADS = 256;
 constexpr int FL_OCT = FL_THREADS / 8;  // candidates per pass
 constexpr int FL_U = 4;                 // passes per round
 
-template <bool IP>
-__device__ __forceinline__ float exact_distance_octet_f(const float *__restrict__ q, const float *__restrict__ y,
-                                                        int d, int sub) {
-  float s = 0.f;
-  int d8 = d & ~7;
-  for (int i = sub; i < d8; i += 8) {
-    float a = q[i], b = __ldg(y + i);
-    if (IP) {
-      s = __fadd_rn(s, __fmul_rn(a, b));
-    } else {
-      float t = __fsub_rn(a, b);
-      s = __fadd_rn(s, __fmul_rn(t, t));
-    }
-  }
-  float other = __shfl_down_sync(GB_FULL, s, 4, 8);
-  float t4 = __fadd_rn(other, s);
-  int rem = d - d8;
-  if (rem >= 4) {
-    if (sub < 4) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-    }
-    d8 += 4;
-    rem -= 4;
-  }
-  if (rem > 0 && sub < rem) {
-    float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-    t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-  }
-  float n1 = __shfl_xor_sync(GB_FULL, t4, 1, 8);
-  float p = __fadd_rn(t4, n1);
-  float n2 = __shfl_xor_sync(GB_FULL, p, 2, 8);
-  float r = __fadd_rn(p, n2);
-  return __shfl_sync(GB_FULL, r, 0, 8);
-}
-
 template <bool IP, int PER>
 __global__ void __launch_bounds__(FL_THREADS) flat_exact_kernel(FlatParams P, int cap, int kpad) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -81,7 +45,7 @@ __global__ void __launch_bounds__(FL_THREADS) flat_exact_kernel(FlatParams P, in
       bool ok = vid < v1;
       if (ok && P.valid) ok = bitmap_test(P.valid, (int)vid);
       const float *y = P.raw + (size_t)(ok ? vid : v0) * P.d;
-      float dis = exact_distance_octet_f<IP>(qs, y, ok ? P.d : 0, sub);
+      float dis = exact_distance_octet<IP>(qs, y, ok ? P.d : 0, sub);
       ok = ok && dis <= P.max_score && dis >= P.min_score;
       u64 key = ((u64)dist_to_key32<IP>(dis) << 32) | (uint32_t)vid;
       bool pass = ok && sub == 0 && key < topr.threshold();

@@ -175,41 +175,6 @@ __global__ void __launch_bounds__(FT_THREADS) flat_chunk_select2_kernel(const fl
   for (int i = tid; i < Kp; i += FT_THREADS) st[i] = i < n_out ? buf[i] : GB_KEY_MAX;
 }
 
-// 8 lanes per candidate, faiss AVX summation order (see rerank.cu)
-template <bool IP>
-__device__ __forceinline__ float ft_exact_octet(const float *__restrict__ q, const float *__restrict__ y, int d, int sub) {
-  float s = 0.f;
-  int d8 = d & ~7;
-  for (int i = sub; i < d8; i += 8) {
-    float a = q[i], b = __ldg(y + i);
-    if (IP) {
-      s = __fadd_rn(s, __fmul_rn(a, b));
-    } else {
-      float t = __fsub_rn(a, b);
-      s = __fadd_rn(s, __fmul_rn(t, t));
-    }
-  }
-  float other = __shfl_down_sync(GB_FULL, s, 4, 8);
-  float t4 = __fadd_rn(other, s);
-  int rem = d - d8;
-  if (rem >= 4) {
-    if (sub < 4) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-    }
-    d8 += 4;
-    rem -= 4;
-  }
-  if (rem > 0 && sub < rem) {
-    float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-    t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-  }
-  float n1 = __shfl_xor_sync(GB_FULL, t4, 1, 8);
-  float p = __fadd_rn(t4, n1);
-  float n2 = __shfl_xor_sync(GB_FULL, p, 2, 8);
-  float r = __fadd_rn(p, n2);
-  return __shfl_sync(GB_FULL, r, 0, 8);
-}
 
 // exact re-score of the Kp candidates of every query, exact score window, k best in (distance, vid) order
 template <bool IP>
@@ -231,7 +196,7 @@ __global__ void __launch_bounds__(128) flat_rescore_kernel(const u64 *__restrict
     bool have = ck != GB_KEY_MAX;
     uint32_t vid = (uint32_t)ck;
     const float *y = raw + (size_t)(have ? vid : 0) * d;
-    float dis = ft_exact_octet<IP>(qs, y, have ? d : 0, sub);
+    float dis = exact_distance_octet<IP>(qs, y, have ? d : 0, sub);
     if (sub == 0 && i < Kp) {
       bool ok = have && dis <= max_score && dis >= min_score;  // IsSimilarScoreValid on the exact value
       keys[i] = ok ? (((u64)dist_to_key32<IP>(dis) << 32) | vid) : GB_KEY_MAX;
@@ -253,8 +218,7 @@ int flat_tc_candidates(int k) { return k + 64; }
 cudaError_t launch_flat_chunk_select(const float *dist, int ldo, int nc, long long chunk_base, const uint32_t *valid,
                                      float lo, float hi, int Kp, int first, u64 *state, int n, int is_ip,
                                      cudaStream_t st) {
-  if (Kp <= FT2_CAP - FT2_ROUND && (ldo & 3) == 0 && (nc & 3) == 0 && ((uintptr_t)dist & 15) == 0 &&
-      !getenv("GB200_FLAT_SELECT_V1")) {
+  if (Kp <= FT2_CAP - FT2_ROUND && (ldo & 3) == 0 && (nc & 3) == 0 && ((uintptr_t)dist & 15) == 0) {
     const size_t smem2 = (size_t)FT2_CAP * sizeof(u64) + (4 + 64) * sizeof(int);
     if (is_ip)
       flat_chunk_select2_kernel<true><<<n, FT_THREADS, smem2, st>>>(dist, ldo, nc, chunk_base, valid, lo, hi, Kp, first, state);

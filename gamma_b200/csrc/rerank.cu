@@ -16,47 +16,6 @@ namespace gb {
 
 constexpr int RR_THREADS = 128;
 
-// 8 consecutive lanes (an "octet") cooperate on one candidate; returns the result in every lane of the octet
-template <bool IP>
-__device__ __forceinline__ float exact_distance_octet(const float *__restrict__ q, const float *__restrict__ y,
-                                                      int d, int sub /*0..7*/) {
-  float s = 0.f;
-  int d8 = d & ~7;
-  for (int i = sub; i < d8; i += 8) {
-    float a = q[i], b = __ldg(y + i);
-    if (IP) {
-      s = __fadd_rn(s, __fmul_rn(a, b));
-    } else {
-      float t = __fsub_rn(a, b);
-      s = __fadd_rn(s, __fmul_rn(t, t));
-    }
-  }
-  // msum2 = hi + lo
-  float other = __shfl_down_sync(GB_FULL, s, 4, 8);
-  float t4 = __fadd_rn(other, s);  // valid in sub 0..3
-  int rem = d - d8;
-  if (rem >= 4) {
-    if (sub < 4) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-    }
-    d8 += 4;
-    rem -= 4;
-  }
-  if (rem > 0) {
-    if (sub < rem) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
-      t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
-    }
-  }
-  // hadd, hadd: (t0 + t1) + (t2 + t3)
-  float n1 = __shfl_xor_sync(GB_FULL, t4, 1, 8);
-  float p = __fadd_rn(t4, n1);  // lanes 0,1: t0+t1 ; lanes 2,3: t2+t3
-  float n2 = __shfl_xor_sync(GB_FULL, p, 2, 8);
-  float r = __fadd_rn(p, n2);
-  return __shfl_sync(GB_FULL, r, 0, 8);
-}
-
 template <bool IP>
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int p2_all, int p2_r) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -165,12 +124,10 @@ cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st) {
   int p2_all = next_pow2(P.S * P.R);
   int p2_r = next_pow2(P.R);
   size_t smem = (size_t)(p2_all + p2_r) * sizeof(u64) + (size_t)p2_r * sizeof(int) + (size_t)P.raw_d * sizeof(float);
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[P.is_ip]) {
+  if (smem > 48 * 1024) {  // per device and cheap: set on every such launch (an index may live on any device)
     cudaError_t e = P.is_ip ? cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[P.is_ip] = smem;
   }
   if (P.is_ip)
     rerank_kernel<true><<<P.n, RR_THREADS, smem, st>>>(P, p2_all, p2_r);

@@ -239,6 +239,8 @@ int gb200_comm_status(gb200_comm *c);
 /* device pointers for the NEXT exchange: where this rank's result goes ([n*k] f32 then [n*k] i64) and the start of the
  * gathered window (rank r's block at all_slots + r * slot_bytes)                                                       */
 int gb200_comm_buffers(gb200_comm *c, void **my_slot, void **all_slots);
+/* copy (part of) the gathered window to host memory on `stream`; sync != 0 also waits for the copy                     */
+int gb200_comm_read(gb200_comm *c, void *dst_host, const void *src_dev, int64_t bytes, void *stream, int sync);
 /* push the block written into my_slot to every peer and wait for theirs, all on `stream`                              */
 int gb200_comm_exchange(gb200_comm *c, int64_t bytes, void *stream);
 /* search this rank's n queries (device pointers) and exchange: afterwards (in stream order) rank r's distances are at

@@ -58,7 +58,7 @@ def main():
         base = comm.search_sharded(ix, xq_d.data_ptr(), n, k, stream.cuda_stream, nprobe=8, recall_num=50, metric="L2")
         torch.cuda.synchronize()
         host = torch.empty(world * comm.slot_bytes, dtype=torch.uint8)
-        torch.cuda.cudart().cudaMemcpy(host.data_ptr(), base, world * comm.slot_bytes, 2)
+        comm.read(host.data_ptr(), base, world * comm.slot_bytes, stream.cuda_stream, sync=True)
         for r in range(world):
             blk = host[r * comm.slot_bytes:(r + 1) * comm.slot_bytes]
             D = blk[:n * k * 4].view(torch.float32).numpy().reshape(n, k)
