@@ -45,7 +45,8 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status", "gb200_comm_read",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_ivfflat_create", "gb200_ivfflat_set_quantizer", "gb200_ivfflat_append",
+    "gb200_ivfflat_add_raw", "gb200_ivfflat_search", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status", "gb200_comm_read",
     "gb200_comm_buffers", "gb200_comm_exchange", "gb200_ivfpq_search_sharded",
 ]
 
@@ -109,6 +110,12 @@ def lib():
         L.gb200_comm_exchange.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.gb200_ivfpq_search_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_ivfflat_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.gb200_ivfflat_set_quantizer.argtypes = [C.c_void_p, C.c_void_p]
+        L.gb200_ivfflat_append.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.gb200_ivfflat_add_raw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.gb200_ivfflat_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_set_opq.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gb200_ivfpq_add_stored.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.gb200_last_scan_kernel_ms.argtypes = [C.c_void_p]
@@ -391,6 +398,52 @@ def _flat_search(obj, xq, k, metric, min_score, max_score, filters):
     rc = lib().gb200_flat_search(obj.h, n, xq.ctypes.data, k, C.byref(sp), C.cast(arr, C.c_void_p), len(filters),
                                  D.ctypes.data, I.ctypes.data)
     return rc, D, I
+
+
+class B200IVFFLAT(B200IVFPQ):
+    """Device mirror + search of the reference's "IVFFLAT" model (GammaIndexIVFFlat): lists of vids over the raw store."""
+
+    def Init(self, model_parameters, d, raw_d=None):
+        mp = json.loads(model_parameters) if isinstance(model_parameters, str) and model_parameters else \
+            (model_parameters or {})
+        self.d = self.raw_d = int(d)
+        self.nlist = int(mp.get("ncentroids", 2048))
+        self.M, self.nbits = 4, 8
+        self.metric = METRIC_L2 if str(mp.get("metric_type", "L2")).lower() == "l2" else METRIC_IP
+        self.nprobe = int(mp.get("nprobe", 80))
+        h = C.c_void_p()
+        rc = lib().gb200_ivfflat_create(self.device, self.d, self.nlist, self.metric, self.nprobe, C.byref(h))
+        if rc != 0:
+            return rc
+        self.h = h
+        return 0
+
+    def set_quantizer(self, coarse):
+        c = np.ascontiguousarray(coarse, dtype=np.float32)
+        assert c.shape == (self.nlist, self.d)
+        _check(lib().gb200_ivfflat_set_quantizer(self.h, c.ctypes.data), "ivfflat_set_quantizer")
+
+    def append_vids(self, list_no, vids):
+        ln = np.ascontiguousarray(list_no, dtype=np.int32)
+        v = np.ascontiguousarray(vids, dtype=np.int64)
+        return lib().gb200_ivfflat_append(self.h, ln.size, ln.ctypes.data, v.ctypes.data)
+
+    def add_raw(self, x, first_vid):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        ln = np.empty(x.shape[0], np.int32)
+        _check(lib().gb200_ivfflat_add_raw(self.h, int(first_vid), x.shape[0], x.ctypes.data, ln.ctypes.data), "ivfflat_add_raw")
+        return ln
+
+    def Search(self, xq, k, nprobe=-1, metric=None, min_score=-FLT_MAX, max_score=FLT_MAX, filters=()):
+        xq = np.ascontiguousarray(xq, dtype=np.float32)
+        n = xq.shape[0]
+        D = np.empty((n, k), np.float32)
+        I = np.empty((n, k), np.int64)
+        sp = self._sp(self.metric if metric is None else metric, nprobe, 0, False, min_score, max_score)
+        arr, keep = make_filters(filters)
+        rc = lib().gb200_ivfflat_search(self.h, n, xq.ctypes.data, k, C.byref(sp), C.cast(arr, C.c_void_p), len(filters),
+                                        D.ctypes.data, I.ctypes.data)
+        return rc, D, I
 
 
 class B200FLAT(_Base):

@@ -178,6 +178,7 @@ struct gb200_index {
   Tuning tune;
   gb200_ivfpq_params p{};
   int dsub = 0, chunk = 0, layout = 0, mode = 0;
+  bool flat_lists = false;  // IVFFLAT: the lists carry vids only (4 dummy code bytes), distances come from the raw store
   int smem_reserved = 0;  // cudaDevAttrReservedSharedMemoryPerBlock (the M = 32 / 64 kernels' LDS immediates assume 1024)
   int num_sms = 0;        // cudaDeviceProp::multiProcessorCount (grid sizing of the persistent scan, work plans)
 
@@ -1551,6 +1552,10 @@ static int ivfpq_search_impl(gb200_index *ix, SearchCtx &c, int n, const float *
                              bool use_installed_filter, const int64_t *keys_h, const float *cdis_h, int nprobe_pre,
                              float *D, int64_t *I, bool out_on_dev) {
   if (n == 0) return GB200_OK;
+  if (ix->flat_lists) {
+    set_err("this is an IVFFLAT index: use gb200_ivfflat_search");
+    return GB200_EINVAL;
+  }
   if (!ix->trained) {
     set_err("IVFPQ search on an untrained index");
     return GB200_ENOTTRAINED;
@@ -1800,6 +1805,160 @@ int gb200_ivfpq_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const flo
   // the raw rows first (re-rank and flat read them; the encode reads them from the device store)
   CKI(gb200_upload_raw(ix, first_vid, n, x));
   return gb200_ivfpq_add_stored(ix, first_vid, n, list_no, codes);
+}
+
+// ---- IVFFLAT ------------------------------------------------------------------------------------------
+int gb200_ivfflat_create(int device, int d, int nlist, int metric, int nprobe, gb200_index **out) {
+  if (!out || d <= 0 || nlist <= 0) return GB200_EINVAL;
+  if (d % 4) {
+    set_err("IVFFLAT: d = %d is not a multiple of 4 (not implemented)", d);
+    return GB200_EUNSUPPORTED;
+  }
+  gb200_ivfpq_params p;
+  memset(&p, 0, sizeof(p));
+  p.device = device;
+  p.d = d;
+  p.raw_d = d;
+  p.nlist = nlist;
+  p.nsubvector = 4;  // dummy codes: the posting machinery (blocks, growth, publication, compaction) is shared
+  p.nbits = 8;
+  p.metric = metric;
+  p.nprobe = nprobe;
+  p.store_raw = 1;
+  int rc = gb200_ivfpq_create(&p, out);
+  if (rc == GB200_OK) (*out)->flat_lists = true;
+  return rc;
+}
+
+int gb200_ivfflat_set_quantizer(gb200_index *ix, const float *coarse) {
+  if (!ix || ix->kind != 0 || !ix->flat_lists || !coarse) return GB200_EINVAL;
+  std::vector<float> pq((size_t)256 * ix->p.d, 0.f);
+  return gb200_ivfpq_set_quantizers(ix, coarse, pq.data());
+}
+
+int gb200_ivfflat_append(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids) {
+  if (!ix || ix->kind != 0 || !ix->flat_lists || n < 0) return GB200_EINVAL;
+  std::vector<uint8_t> codes((size_t)n * ix->p.nsubvector, 0);
+  return gb200_ivfpq_append(ix, n, list_no, vids, codes.data());
+}
+
+int gb200_ivfflat_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no) {
+  if (!ix || ix->kind != 0 || !ix->flat_lists || first_vid < 0 || n < 0 || (n > 0 && !x)) return GB200_EINVAL;
+  if (!ix->trained) return GB200_ENOTTRAINED;
+  if (n == 0) return GB200_OK;
+  CKI(gb200_upload_raw(ix, first_vid, n, x));
+  std::vector<int32_t> ln_own;
+  if (!list_no) {
+    ln_own.resize((size_t)n);
+    list_no = ln_own.data();
+  }
+  {
+    CKI(use_device(ix));
+    SearchScope s(ix);
+    if (!s.c) return GB200_ECUDA;
+    SearchCtx &c = *s.c;
+    const int d = ix->p.d;
+    const int64_t CH = 1 << 17;
+    for (int64_t s0 = 0; s0 < n; s0 += CH) {  // quantizer->assign = the coarse stage with nprobe = 1
+      const int m = (int)std::min<int64_t>(CH, n - s0);
+      CKI(c.ws_keys.ensure((size_t)m * sizeof(int)));
+      CKI(c.ws_cdis.ensure((size_t)m * sizeof(float)));
+      CKI(coarse_dev(ix, c, m, ix->d_raw + (size_t)(first_vid + s0) * d, 1, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
+      CK(cudaMemcpyAsync(list_no + s0, c.ws_keys.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      CK(cudaStreamSynchronize(c.stream));
+    }
+    ix->launches += c.launches;
+    c.launches = 0;
+  }
+  std::vector<int64_t> vids((size_t)n);
+  for (int64_t i = 0; i < n; i++) vids[i] = first_vid + i;
+  return gb200_ivfflat_append(ix, n, list_no, vids.data());
+}
+
+int gb200_ivfflat_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
+                         const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
+  CKI(check_search_args(ix, n, xq, k, sp, D, I));
+  if (ix->kind != 0 || !ix->flat_lists) return GB200_EINVAL;
+  if (n == 0) return GB200_OK;
+  if (!ix->trained) {
+    set_err("IVFFLAT search on an untrained index");
+    return GB200_ENOTTRAINED;
+  }
+  if (k > 2048) {
+    set_err("IVFFLAT k=%d > 2048 not implemented", k);
+    return GB200_EUNSUPPORTED;
+  }
+  CKI(use_device(ix));
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  SearchCtx &c = *s.c;
+  const int d = ix->p.d;
+  const int nprobe = resolve_nprobe(ix, sp, ix->p.nprobe > 0 ? ix->p.nprobe : 80);
+  const bool ip = sp->metric == GB200_METRIC_INNER_PRODUCT;
+  c.timed = ix->profiling;
+  CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
+  CK(cudaMemcpyAsync(c.ws_xq.p, xq, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  const float *d_xq = c.ws_xq.as<float>();
+  const uint32_t *d_valid = nullptr;
+  long long valid_bits = 0;
+  CKI(prepare_valid(ix, c, filters, n_filters, &d_valid, &valid_bits));
+  CKI(c.ws_keys.ensure((size_t)n * nprobe * sizeof(int)));
+  CKI(c.ws_cdis.ensure((size_t)n * nprobe * sizeof(float)));
+  if (c.timed) CK(cudaEventRecord(c.ev[0], c.stream));
+  CKI(coarse_dev(ix, c, n, d_xq, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
+  if (c.timed) CK(cudaEventRecord(c.ev[1], c.stream));
+  // splits: fill the machine when the batch is small (one CTA per (query, split), probes dealt round-robin)
+  int S = 1;
+  const int slots = ix->num_sms * 4;
+  while (S < 8 && S * 2 <= nprobe && (long long)n * S * 2 <= slots) S *= 2;
+  IvfFlatParams F;
+  memset(&F, 0, sizeof(F));
+  F.xq = d_xq;
+  F.keys = c.ws_keys.as<int>();
+  F.list_off = ix->d_off;
+  F.list_len = ix->d_len;
+  F.ids = ix->d_ids;
+  F.raw = ix->d_raw;
+  F.nraw = ix->raw_n.load();
+  F.valid = d_valid;
+  F.valid_bits = valid_bits;
+  F.scanned = c.d_scanned;
+  F.n = n, F.d = d, F.nlist = ix->p.nlist, F.nprobe = nprobe, F.S = S, F.R = k;
+  F.cap = ivfflat_buffer_cap(k);
+  F.is_ip = ip ? 1 : 0;
+  F.min_score = sp->min_score, F.max_score = sp->max_score;
+  CKI(c.ws_cand.ensure((size_t)n * S * k * sizeof(u64)));
+  F.cand = c.ws_cand.as<u64>();
+  CK(cudaMemsetAsync(c.d_scanned, 0, sizeof(unsigned long long), c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[4], c.stream));
+  CK(launch_ivfflat_scan(F, c.stream));
+  if (c.timed) {
+    CK(cudaEventRecord(c.ev[5], c.stream));
+    CK(cudaEventRecord(c.ev[2], c.stream));
+  }
+  CKI(c.ws_out_d.ensure((size_t)n * k * sizeof(float)));
+  CKI(c.ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+  RerankParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.cand = F.cand;
+  Q.keys = F.keys;
+  Q.list_off = ix->d_off;
+  Q.ids = ix->d_ids;
+  Q.xq = d_xq;
+  Q.raw = ix->d_raw;
+  Q.nraw = F.nraw;
+  Q.out_dist = c.ws_out_d.as<float>();
+  Q.out_ids = c.ws_out_i.as<long long>();
+  Q.n = n, Q.S = S, Q.R = k, Q.k = k, Q.nprobe = nprobe, Q.raw_d = d, Q.xq_stride = d;
+  Q.has_rank = 0;  // the scan's distances are exact already: merge the rows, resolve vids, first k
+  Q.is_ip = ip ? 1 : 0;
+  Q.min_score = sp->min_score, Q.max_score = sp->max_score;
+  CK(launch_rerank(Q, c.stream));
+  if (c.timed) CK(cudaEventRecord(c.ev[3], c.stream));
+  c.launches += 2;
+  CK(cudaMemcpyAsync(D, Q.out_dist, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaMemcpyAsync(I, Q.out_ids, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+  return finish_profile(ix, c);
 }
 
 // ---- flat ----------------------------------------------------------------------------------------

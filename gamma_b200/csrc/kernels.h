@@ -142,6 +142,25 @@ cudaError_t launch_coarse_select_cmin(const float *dist, const float *cmin, int 
 cudaError_t launch_pq_encode(const float *x, int x_stride, const int *keys, const float *centroids, const float *pq,
                              long long n, int d, int M, int dsub, int by_residual, uint8_t *codes, cudaStream_t st);
 
+// K7 — IVFFLAT scan (ivfflat.cu): exact distances over the probed lists (vids only; vectors come from the raw store)
+struct IvfFlatParams {
+  const float *xq;          // [n][d]
+  const int *keys;          // [n][nprobe]
+  const long long *list_off;
+  const int *list_len;
+  const int *ids;
+  const float *raw;         // [nraw][d]
+  long long nraw;
+  const uint32_t *valid;    // or nullptr
+  long long valid_bits;
+  u64 *cand;                // [n][S][R]
+  unsigned long long *scanned;
+  int n, d, nlist, nprobe, S, R, cap, is_ip;
+  float min_score, max_score;
+};
+int ivfflat_buffer_cap(int R);
+cudaError_t launch_ivfflat_scan(const IvfFlatParams &P, cudaStream_t st);
+
 // K3 — merge the per-split survivors, optional exact re-rank, score window, top-k
 struct RerankParams {
   const u64 *cand;          // [n][S][R]

@@ -220,6 +220,23 @@ int gb200_sync(gb200_index *ix);
  * them for an existing index (A/B runs in bench.py and the tests).                           */
 int gb200_reload_tuning(gb200_index *ix);
 
+/* ---- IVFFLAT: the reference's "IVFFLAT" model (index/impl/gamma_index_ivfflat.{h,cc}: GammaIndexIVFFlat — IVF over raw
+ * float lists, exact distances, no re-rank).  The device keeps one copy of every vector (the raw store, by vid) and
+ * the inverted lists hold vids, so Add = gb200_upload_raw + an assignment.  Realtime list maintenance, deleted
+ * bitmap, filters and the multi-GPU exchange are the IVFPQ model's (gb200_ivfpq_update is not meaningful here; use
+ * gb200_ivfpq_replace_list with any code bytes, gb200_ivfpq_compact, gb200_set_deleted, ...).                        */
+int gb200_ivfflat_create(int device, int d, int nlist, int metric, int nprobe, gb200_index **out);
+/* coarse centroids (IndexFlatL2 xb after train), nlist x d                                                           */
+int gb200_ivfflat_set_quantizer(gb200_index *ix, const float *coarse);
+/* RTInvertIndex::AddKeys for vectors already in the raw store: list_no n, vids n                                     */
+int gb200_ivfflat_append(gb200_index *ix, int64_t n, const int32_t *list_no, const int64_t *vids);
+/* GammaIndexIVFFlat::Add (gamma_index_ivfflat.cc:265-330): upload n x d rows as vids first_vid.., assign them with the
+ * tensor-core coarse stage (quantizer->assign) and append; list_no (may be NULL) returns the assignment               */
+int gb200_ivfflat_add_raw(gb200_index *ix, int64_t first_vid, int64_t n, const float *x, int32_t *list_no);
+/* GammaIndexIVFFlat::Search (:392-421) + search_preassigned (:423-560); sp->recall_num / has_rank are ignored          */
+int gb200_ivfflat_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
+                         const gb200_range_filter *filters, int n_filters, float *distances, int64_t *labels);
+
 /* ---- multi-GPU: one process per GPU, index replicated, batch sharded by query.  Replaces the host-side
  * merge of faiss IndexReplicas / IndexShards the reference's GPU model relies on (index/impl/gpu/gamma_gpu_cloner.cpp:
  * 209-212).  Every rank owns a result window in device memory; after its search it stores its [n][k] block into every

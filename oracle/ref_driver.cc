@@ -26,6 +26,7 @@
 
 #include "common/gamma_common_data.h"
 #include "index/impl/gamma_index_flat.h"
+#include "index/impl/gamma_index_ivfflat.h"
 #include "index/impl/gamma_index_ivfpq.h"
 #include "table/range_query_result.h"
 #include "util/bitmap_manager.h"
@@ -41,6 +42,12 @@ using namespace tig_gamma;
 
 namespace {
 
+// GammaIndexIVFFlat::Init insists on a RocksDB raw vector unless check_vector_ is off (gamma_index_ivfflat.cc:137-151;
+// the faiss-like facade index/gamma_index.cc turns it off the same way): the oracle runs it over MemoryRawVector
+struct OracleIVFFlat : GammaIndexIVFFlat {
+  OracleIVFFlat() { check_vector_ = false; }
+};
+
 struct OracleRef {
   int d = 0;
   bool is_ivfpq = false;
@@ -48,6 +55,7 @@ struct OracleRef {
   RawVector *raw = nullptr;
   GammaIVFPQIndex *ivfpq = nullptr;
   GammaFLATIndex *flat = nullptr;
+  GammaIndexIVFFlat *ivfflat = nullptr;
   RetrievalModel *model = nullptr;
 };
 
@@ -98,6 +106,9 @@ void *oref_open(const char *work_dir, int d, const char *retrieval_type,
     o->ivfpq = new GammaIVFPQIndex();
     o->model = o->ivfpq;
     o->is_ivfpq = true;
+  } else if (!strcmp(retrieval_type, "IVFFLAT")) {
+    o->ivfflat = new OracleIVFFlat();
+    o->model = o->ivfflat;
   } else {
     o->flat = new GammaFLATIndex();
     o->model = o->flat;
@@ -113,6 +124,7 @@ void oref_close(void *h) {
   if (!o) return;
   if (o->ivfpq) delete o->ivfpq;
   if (o->flat) delete o->flat;
+  if (o->ivfflat) delete o->ivfflat;
   if (o->raw) delete o->raw;
   if (o->docids_bitmap) delete o->docids_bitmap;
   delete o;
@@ -174,6 +186,13 @@ long oref_info(void *h, const char *key) {
   if (k == "d") return o->d;
   if (k == "nraw") return (long)o->raw->MetaInfo()->Size();
   if (k == "indexed") return o->model->indexed_count_;
+  if (o->ivfflat) {
+    if (k == "nlist") return (long)o->ivfflat->nlist;
+    if (k == "is_trained") return o->ivfflat->is_trained ? 1 : 0;
+    if (k == "code_size") return (long)o->ivfflat->code_size;
+    if (k == "nprobe") return (long)o->ivfflat->nprobe;
+    return -1;
+  }
   if (!o->ivfpq) return -1;
   GammaIVFPQIndex *ix = o->ivfpq;
   if (k == "nlist") return (long)ix->nlist;
@@ -192,7 +211,7 @@ long oref_info(void *h, const char *key) {
 
 int oref_get_centroids(void *h, float *out) {
   OracleRef *o = (OracleRef *)h;
-  faiss::IndexFlat *q = dynamic_cast<faiss::IndexFlat *>(o->ivfpq->quantizer);
+  faiss::IndexFlat *q = dynamic_cast<faiss::IndexFlat *>(o->ivfflat ? o->ivfflat->quantizer : o->ivfpq->quantizer);
   if (!q) return -1;
   memcpy(out, q->xb.data(), sizeof(float) * q->xb.size());
   return 0;
@@ -226,13 +245,20 @@ int oref_get_opq(void *h, float *A, float *b) {
 
 long oref_list_size(void *h, long list_no) {
   OracleRef *o = (OracleRef *)h;
-  return (long)o->ivfpq->invlists->list_size(list_no);
+  return (long)(o->ivfflat ? o->ivfflat->invlists : o->ivfpq->invlists)->list_size(list_no);
 }
 
 // raw view of one realtime inverted list: int64 ids WITH the kDelIdxMask bit
 // (realtime/realtime_mem_data.h:26) and code_size bytes per posting.
 int oref_get_list(void *h, long list_no, int64_t *ids, uint8_t *codes) {
   OracleRef *o = (OracleRef *)h;
+  if (o->ivfflat) {  // its RTInvertIndex is private: go through the faiss InvertedLists view of it (RTInvertedLists)
+    faiss::InvertedLists *il = o->ivfflat->invlists;
+    size_t n = il->list_size(list_no);
+    memcpy(ids, il->get_ids(list_no), n * sizeof(int64_t));
+    memcpy(codes, il->get_codes(list_no), n * o->ivfflat->code_size);
+    return 0;
+  }
   long *ivt = nullptr;
   size_t n = 0;
   uint8_t *cds = nullptr;
@@ -245,7 +271,7 @@ int oref_get_list(void *h, long list_no, int64_t *ids, uint8_t *codes) {
 // coarse quantiser exactly as GammaIVFPQIndex::Search calls it (gamma_index_ivfpq.cc:560)
 int oref_coarse(void *h, int n, const float *xq, int nprobe, float *cdis, int64_t *keys) {
   OracleRef *o = (OracleRef *)h;
-  o->ivfpq->quantizer->search(n, xq, nprobe, cdis, (faiss::Index::idx_t *)keys);
+  (o->ivfflat ? o->ivfflat->quantizer : o->ivfpq->quantizer)->search(n, xq, nprobe, cdis, (faiss::Index::idx_t *)keys);
   return 0;
 }
 
