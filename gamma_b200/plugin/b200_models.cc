@@ -15,6 +15,7 @@ namespace tig_gamma {
 
 REGISTER_MODEL(B200IVFPQ, B200IVFPQIndex)
 REGISTER_MODEL(B200FLAT, B200FLATIndex)
+REGISTER_MODEL(B200IVFFLAT, B200IVFFLATIndex)
 
 namespace {
 
@@ -342,6 +343,182 @@ int B200IVFPQIndex::Search(RetrievalContext *retrieval_context, int n, const uin
     rc = gb200_ivfpq_search(dev_, n, xq, k, &sp, filters.data(), (int)filters.size(), distances, labels);
   }
   if (rc) LOG(ERROR) << "gb200 search failed: " << rc << " " << gb200_last_error();
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------ IVFFLAT
+B200IVFFLATIndex::B200IVFFLATIndex() { check_vector_ = false; }  // any RawVector will do: the device reads its own copy
+B200IVFFLATIndex::~B200IVFFLATIndex() {
+  if (dev_) gb200_destroy(dev_);
+}
+
+int B200IVFFLATIndex::Init(const std::string &model_parameters, int indexing_size) {
+  int ret = GammaIndexIVFFlat::Init(model_parameters, indexing_size);
+  if (ret) return ret;
+  if (MultiVidStore(vector_)) {
+    LOG(ERROR) << "B200IVFFLAT: multi-vid vector fields are not supported (filters are applied by vid)";
+    return -1;
+  }
+  int metric = this->metric_type == faiss::METRIC_INNER_PRODUCT ? GB200_METRIC_INNER_PRODUCT : GB200_METRIC_L2;
+  if (gb200_ivfflat_create(DeviceOrdinal(), (int)this->d, (int)this->nlist, metric, (int)this->nprobe, &dev_)) {
+    LOG(ERROR) << "gb200_ivfflat_create failed: " << gb200_last_error();
+    return -1;
+  }
+  mirrored_len_.assign(this->nlist, 0);
+  return 0;
+}
+
+int B200IVFFLATIndex::PushQuantizer() {
+  faiss::IndexFlat *flat = dynamic_cast<faiss::IndexFlat *>(this->quantizer);
+  if (!flat || !this->is_trained) return -1;
+  int rc = gb200_ivfflat_set_quantizer(dev_, flat->xb.data());
+  if (rc == 0) quantizer_pushed_ = true;
+  return rc;
+}
+
+int B200IVFFLATIndex::Indexing() {
+  int ret = GammaIndexIVFFlat::Indexing();
+  if (ret) return ret;
+  B200RwLock::Shared dl(dev_mu_);
+  std::lock_guard<std::mutex> g(mirror_mu_);
+  return PushQuantizer() ? -1 : 0;
+}
+
+int B200IVFFLATIndex::MirrorRaw() {
+  RawVector *raw = dynamic_cast<RawVector *>(vector_);
+  long total = (long)raw->MetaInfo()->Size();
+  if (total <= raw_mirrored_) return 0;
+  int rc = UploadRawRange(dev_, raw, raw_mirrored_, total);
+  if (rc == 0) raw_mirrored_ = total;
+  return rc;
+}
+
+int B200IVFFLATIndex::SyncDeleted() {
+  RawVector *raw = dynamic_cast<RawVector *>(vector_);
+  bitmap::BitmapManager *bm = raw ? raw->Bitmap() : nullptr;
+  if (!bm) return 0;
+  return gb200_upload_deleted_bitmap(dev_, reinterpret_cast<const uint8_t *>(bm->Bitmap()), bm->BitSize());
+}
+
+// the model's RTInvertIndex is private: the lists are read through the faiss InvertedLists view of it (RTInvertedLists)
+int B200IVFFLATIndex::MirrorPostings() {
+  std::vector<int32_t> list_no;
+  std::vector<int64_t> vids;
+  for (size_t l = 0; l < this->nlist; l++) {
+    size_t len = this->invlists->list_size(l);
+    if (len <= mirrored_len_[l]) continue;
+    const faiss::Index::idx_t *ids = this->invlists->get_ids(l);
+    for (size_t j = mirrored_len_[l]; j < len; j++) {
+      list_no.push_back((int32_t)l);
+      vids.push_back(ids[j] & realtime::kRecoverIdxMask);
+    }
+    mirrored_len_[l] = len;
+  }
+  if (list_no.empty()) return 0;
+  return gb200_ivfflat_append(dev_, (int64_t)list_no.size(), list_no.data(), vids.data());
+}
+
+int B200IVFFLATIndex::MirrorList(int l) {
+  size_t len = this->invlists->list_size(l);
+  const faiss::Index::idx_t *ids = this->invlists->get_ids(l);
+  std::vector<uint8_t> codes(len * 4, 0);  // the device lists carry no codes: 4 dummy bytes per posting
+  int rc = gb200_ivfpq_replace_list(dev_, l, (int64_t)len, reinterpret_cast<const int64_t *>(ids), codes.data());
+  if (rc == 0) mirrored_len_[l] = len;
+  return rc;
+}
+
+bool B200IVFFLATIndex::Add(int n, const uint8_t *vec) {
+  if (!GammaIndexIVFFlat::Add(n, vec)) return false;  // quantizer->assign + AddKeys on the host
+  B200RwLock::Shared dl(dev_mu_);
+  std::lock_guard<std::mutex> g(mirror_mu_);
+  if (!quantizer_pushed_ && PushQuantizer()) return false;
+  if (MirrorRaw()) return false;  // the scan reads the vectors from the device raw store
+  return MirrorPostings() == 0;
+}
+
+int B200IVFFLATIndex::Update(const std::vector<int64_t> &ids, const std::vector<const uint8_t *> &vecs) {
+  int ret = GammaIndexIVFFlat::Update(ids, vecs);  // re-assign, RealTimeMemData::Update, CompactIfNeed
+  if (ret) return ret;
+  B200RwLock::Shared dl(dev_mu_);
+  std::lock_guard<std::mutex> g(mirror_mu_);
+  RawVector *raw = dynamic_cast<RawVector *>(vector_);
+  for (size_t i = 0; i < ids.size(); i++) {
+    ScopeVector sv;
+    raw->GetVector(ids[i], sv);
+    if (sv.Get() && gb200_upload_raw(dev_, ids[i], 1, reinterpret_cast<const float *>(sv.Get()))) return -1;
+  }
+  // RealTimeMemData::Update on the device: the old posting keeps its slot with the kDelIdxMask flag, the new one is
+  // appended to the list the quantizer assigns (same list: nothing moves — the vector itself lives in the raw store)
+  const uint8_t dummy[4] = {0, 0, 0, 0};
+  for (size_t i = 0; i < ids.size(); i++) {
+    faiss::Index::idx_t idx = -1;
+    quantizer->assign(1, reinterpret_cast<const float *>(vecs[i]), &idx);
+    if (idx < 0) continue;
+    if (gb200_ivfpq_update(dev_, ids[i], (int32_t)idx, dummy)) return -1;
+  }
+  // CompactIfNeed may have rewritten lists on the host: those whose length now differs from the device's are replaced
+  if (SyncDeleted()) return -1;
+  std::vector<int64_t> dev_len(this->nlist);
+  if (gb200_ivfpq_list_sizes(dev_, dev_len.data())) return -1;
+  for (size_t l = 0; l < this->nlist; l++) {
+    if ((int64_t)this->invlists->list_size(l) != dev_len[l]) {
+      if (MirrorList((int)l)) return -1;
+    } else {
+      mirrored_len_[l] = (size_t)dev_len[l];
+    }
+  }
+  return 0;
+}
+
+int B200IVFFLATIndex::Delete(const std::vector<int64_t> &ids) {
+  GammaIndexIVFFlat::Delete(ids);
+  B200RwLock::Shared dl(dev_mu_);
+  return gb200_set_deleted(dev_, ids.data(), (int64_t)ids.size(), 1) ? -1 : 0;
+}
+
+int B200IVFFLATIndex::Load(const std::string &index_dir) {
+  int ret = GammaIndexIVFFlat::Load(index_dir);
+  if (ret < 0) return ret;
+  B200RwLock::Exclusive dl(dev_mu_);
+  std::lock_guard<std::mutex> g(mirror_mu_);
+  if (!this->is_trained) return ret;
+  if (PushQuantizer() || MirrorRaw() || SyncDeleted()) return -1;
+  for (size_t l = 0; l < this->nlist; l++)
+    if (MirrorList((int)l)) return -1;
+  return ret;
+}
+
+long B200IVFFLATIndex::GetTotalMemBytes() { return dev_ ? gb200_mem_bytes(dev_) : 0; }
+
+int B200IVFFLATIndex::Search(RetrievalContext *retrieval_context, int n, const uint8_t *x, int k, float *distances,
+                             int64_t *labels) {
+  IVFFlatRetrievalParameters *rp = dynamic_cast<IVFFlatRetrievalParameters *>(retrieval_context->RetrievalParams());
+  GammaSearchCondition *cond = dynamic_cast<GammaSearchCondition *>(retrieval_context);
+  gb200_search_params sp;
+  memset(&sp, 0, sizeof(sp));
+  DistanceComputeType t = rp ? rp->GetDistanceComputeType()
+                             : (this->metric_type == faiss::METRIC_INNER_PRODUCT ? DistanceComputeType::INNER_PRODUCT
+                                                                                : DistanceComputeType::L2);
+  sp.metric = t == DistanceComputeType::INNER_PRODUCT ? GB200_METRIC_INNER_PRODUCT : GB200_METRIC_L2;
+  sp.nprobe = rp ? rp->Nprobe() : -1;  // <= 0: the model's nprobe
+  sp.min_score = cond ? cond->min_score : -std::numeric_limits<float>::max();
+  sp.max_score = cond ? cond->max_score : std::numeric_limits<float>::max();
+  if (k <= 0) return 0;
+  if (MatchesNothing(cond)) {
+    FillEmpty(n, k, sp.metric == GB200_METRIC_INNER_PRODUCT, distances, labels);
+    return 0;
+  }
+  B200RwLock::Shared dl(dev_mu_);
+  {
+    std::lock_guard<std::mutex> g(mirror_mu_);
+    if (MirrorRaw()) return -1;
+    if (SyncDeleted()) return -1;
+  }
+  std::vector<gb200_range_filter> filters;
+  CollectFilters(cond, &filters);
+  int rc = gb200_ivfflat_search(dev_, n, reinterpret_cast<const float *>(x), k, &sp, filters.data(), (int)filters.size(),
+                                distances, labels);
+  if (rc) LOG(ERROR) << "gb200 ivfflat search failed: " << rc << " " << gb200_last_error();
   return rc;
 }
 

@@ -2,6 +2,7 @@
 //
 //   REGISTER_MODEL(B200IVFPQ, B200IVFPQIndex)   retrieval_type "B200IVFPQ"
 //   REGISTER_MODEL(B200FLAT,  B200FLATIndex)    retrieval_type "B200FLAT"
+//   REGISTER_MODEL(B200IVFFLAT, B200IVFFLATIndex) retrieval_type "B200IVFFLAT"
 //
 // Same pattern as the reference's own GPU model (index/impl/gpu/gamma_index_ivfpq_gpu.cc:303-305,
 // 405-442): the CPU model is embedded for Init / Parse / Indexing (train) / Add (assign + PQ encode) /
@@ -18,6 +19,7 @@
 
 #include "gamma_b200.h"
 #include "index/impl/gamma_index_flat.h"
+#include "index/impl/gamma_index_ivfflat.h"
 #include "index/impl/gamma_index_ivfpq.h"
 
 namespace tig_gamma {
@@ -75,6 +77,36 @@ class B200IVFPQIndex : public GammaIVFPQIndex {
   long raw_mirrored_ = 0;
   long compacted_seen_ = 0;
   bool quantizers_pushed_ = false;
+};
+
+// IVFFLAT: the embedded CPU model keeps training, Add / Update and the list files; Search runs on the device over vid
+// lists + the raw store.  Unlike the reference model it does not insist on a RocksDB raw vector (check_vector_ off).
+class B200IVFFLATIndex : public GammaIndexIVFFlat {
+ public:
+  B200IVFFLATIndex();
+  ~B200IVFFLATIndex() override;
+  int Init(const std::string &model_parameters, int indexing_size) override;
+  int Indexing() override;
+  bool Add(int n, const uint8_t *vec) override;
+  int Update(const std::vector<int64_t> &ids, const std::vector<const uint8_t *> &vecs) override;
+  int Delete(const std::vector<int64_t> &ids);
+  int Search(RetrievalContext *retrieval_context, int n, const uint8_t *x, int k, float *distances,
+             int64_t *labels) override;
+  long GetTotalMemBytes() override;
+  int Load(const std::string &index_dir) override;
+
+ private:
+  int PushQuantizer();
+  int MirrorPostings();  // append what the host lists gained
+  int MirrorList(int l); // device copy of list l := the host list (RTInvertedLists view)
+  int MirrorRaw();
+  int SyncDeleted();
+  gb200_index *dev_ = nullptr;
+  B200RwLock dev_mu_;
+  std::mutex mirror_mu_;
+  std::vector<size_t> mirrored_len_;
+  long raw_mirrored_ = 0;
+  bool quantizer_pushed_ = false;
 };
 
 class B200FLATIndex : public GammaFLATIndex {

@@ -316,6 +316,78 @@ int main(int argc, char **argv) {
     delete cpu2;
   }
 
+  // ---- IVFFLAT: the reference model (over this MemoryRawVector: check_vector_ off, as its faiss-like facade does) against
+  // B200IVFFLAT from the same reflector — train, Add, filter + deletions, Update, 8 concurrent searches
+  {
+    struct RefIVFFlat : GammaIndexIVFFlat {
+      RefIVFFlat() { check_vector_ = false; }
+    };
+    RetrievalModel *cpu_if = new RefIVFFlat();
+    RetrievalModel *gpu_if = reflector().GetNewModel("B200IVFFLAT");
+    if (!gpu_if) {
+      printf("{\"error\":\"reflector did not return B200IVFFLAT\"}\n");
+      return 9;
+    }
+    cpu_if->vector_ = raw;
+    gpu_if->vector_ = raw;
+    const char *ij = "{\"ncentroids\":128,\"metric_type\":\"L2\",\"nprobe\":12}";
+    if (cpu_if->Init(ij, N) || gpu_if->Init(ij, N)) {
+      printf("{\"error\":\"IVFFLAT Init failed: %s\"}\n", gb200_last_error());
+      return 9;
+    }
+    if (cpu_if->Indexing()) {
+      printf("{\"error\":\"IVFFLAT Indexing failed\"}\n");
+      return 9;
+    }
+    {  // same trained quantizer on both sides
+      GammaIndexIVFFlat *c = dynamic_cast<GammaIndexIVFFlat *>(cpu_if), *g = dynamic_cast<GammaIndexIVFFlat *>(gpu_if);
+      faiss::IndexFlat *cf = dynamic_cast<faiss::IndexFlat *>(c->quantizer);
+      g->quantizer->reset();
+      g->quantizer->add(c->nlist, cf->xb.data());
+      g->quantizer->is_trained = true;
+      g->is_trained = true;
+    }
+    for (int s0 = 0; s0 < N; s0 += 1000) {
+      int nn = std::min(1000, N - s0);
+      ScopeVectors h;
+      std::vector<int> lens;
+      raw->GetVectorHeader(s0, nn, h, lens);
+      for (size_t j = 0; j < h.Size(); j++)
+        for (RetrievalModel *m : {cpu_if, gpu_if})
+          if (!m->Add(lens[j], h.Get(j))) {
+            printf("{\"error\":\"IVFFLAT Add failed: %s\"}\n", gb200_last_error());
+            return 9;
+          }
+    }
+    const char *irj = "{\"nprobe\":12,\"metric_type\":\"L2\"}";
+    search(cpu_if, irj, false, nullptr, -FMAX, FMAX, D0, I0);
+    search(gpu_if, irj, false, nullptr, -FMAX, FMAX, D1, I1);
+    report("ivfflat", 0.995, 0.0);
+    search(cpu_if, irj, false, &mr, -FMAX, FMAX, D0, I0);
+    search(gpu_if, irj, false, &mr, -FMAX, FMAX, D1, I1);
+    report("ivfflat_filter_deleted", 0.995, 0.0);
+    {
+      std::vector<int64_t> uids;
+      std::vector<const uint8_t *> uvecs;
+      for (int t = 0; t < 16; t++) {
+        int64_t id = 7000 + 173 * t;
+        if (bm->Test((uint32_t)id)) continue;
+        const float *nv = &xb[(size_t)((id * 11 + 5) % N) * d];
+        raw->UpdateToStore((int)id, (uint8_t *)nv, d * sizeof(float));
+        uids.push_back(id);
+        uvecs.push_back((const uint8_t *)nv);
+      }
+      for (RetrievalModel *m : {cpu_if, gpu_if, cpu, gpu, cpu_flat, gpu_flat})
+        if (m->Update(uids, uvecs)) {
+          printf("{\"error\":\"IVFFLAT Update failed: %s\"}\n", gb200_last_error());
+          return 9;
+        }
+    }
+    search(cpu_if, irj, false, nullptr, -FMAX, FMAX, D0, I0);
+    search(gpu_if, irj, false, nullptr, -FMAX, FMAX, D1, I1);
+    report("ivfflat_after_update", 0.995, 0.0);
+  }
+
   // ---- concurrent Search (the engine's normal mode, tests/test.h:1033-1062): 8 threads, results equal the serial ones
   {
     search(gpu, rj, true, nullptr, -FMAX, FMAX, D0, I0);

@@ -28,7 +28,8 @@ def test_plugin_matches_reference_models_through_the_reflector():
     # reference's file format in both directions, 8 concurrent searches
     for name in ("ivfpq_bitmap_only_delete", "flat_bitmap_only_delete", "ivfpq_rerank_after_update_and_compaction",
                  "ivfpq_adc_filter_after_compaction", "b200_loads_reference_dump", "reference_loads_b200_dump",
-                 "loaded_b200_equals_live_b200", "concurrent_search_8_threads"):
+                 "loaded_b200_equals_live_b200", "concurrent_search_8_threads", "ivfflat", "ivfflat_filter_deleted",
+                 "ivfflat_after_update"):
         assert cases[name]["ok"], cases[name]
     assert cases["loaded_b200_equals_live_b200"]["ids_identical"] == 1.0
     assert any(l.get("host_compacted_postings", 0) > 0 for l in lines)
