@@ -633,39 +633,51 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
   uint32_t parity = 0;
   uint32_t ring_epoch = 0;
   bool helper = false;
+  bool early = false;  // the tables of the query about to start were requested before the previous query's final select
+  // the next (query, candidate row) from the queue: fetched by one thread WHILE the current query is scanned (two
+  // dependent global atomics, ~2 us) and left in misc[74..75] for the next iteration
+  auto fetch_next = [&]() {
+    int qn = atomicAdd(P.v3_next_q, 1);
+    int rw = 0;
+    if (qn < P.n) rw = atomicAdd(P.v3_rows + qn, 1);
+    else qn = -1;
+    S.misc[74] = qn;
+    S.misc[75] = rw;
+  };
+  // the query's table [256][64] (lut_build_m32_kernel, L2 resident) and its probe block by bulk copies, one mbarrier each
+  auto request_tables = [&](int qq) {
+    const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)qq * 65536;
+    mbar_expect_tx(&S.mbar[0], pbytes);
+    tma_bulk_g2s(S.pinfo, P.probe_g + (size_t)qq * pbytes, pbytes, &S.mbar[0]);
+    mbar_expect_tx(&S.mbar[1], 65536u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[1]);
+  };
+  if (tid == 0) fetch_next();
+  __syncthreads();
   for (;;) {
     // ---- the next (query, candidate row) of this CTA
-    int q = -1, row = 0;
-    if (!helper) {
-      if (tid == 0) {
-        int qn = atomicAdd(P.v3_next_q, 1);
-        int rw = 0;
-        if (qn < P.n) rw = atomicAdd(P.v3_rows + qn, 1);
-        else qn = -1;
-        S.misc[72] = qn;
-        S.misc[73] = rw;
-      }
-      __syncthreads();
-      q = S.misc[72];
-      row = S.misc[73];
-      __syncthreads();  // misc[72..73] are rewritten by the victim search
-      if (q < 0) helper = true;
+    int q = S.misc[74], row = S.misc[75];
+    __syncthreads();  // everybody has read the pair before thread 0 replaces it with the one after
+    const bool from_queue = !helper && q >= 0;
+    if (!from_queue) {
+      helper = true;
+      if (!v3_pick_victim<THREADS>(P, S, q, row)) break;
     }
-    if (helper && !v3_pick_victim<THREADS>(P, S, q, row)) break;
-    if (row >= P.S) continue;  // every row of this query is taken: the CTAs holding them scan all of its items
-    // ---- the query's table [256][64] (lut_build_m32_kernel, L2 resident) and its probe table land in shared memory
-    // through one mbarrier; every warp is past its last table read of the previous query (barrier below)
+    if (row >= P.S) {  // every row of this query is taken: the CTAs holding them scan all of its items
+      if (from_queue) {
+        if (tid == 0) fetch_next();
+        __syncthreads();
+      }
+      continue;
+    }
     if (tid == 0) {
       *topr.cnt = 0;
       *topr.tau = GB_KEY_MAX;
       *topr.tau_f = IP ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);  // everything finite is admitted
       S.misc[68] = S.misc[69] = S.misc[70] = 0;
-      const char *src = reinterpret_cast<const char *>(P.lut_g) + (size_t)q * 65536;
-      mbar_expect_tx(&S.mbar[0], pbytes);
-      tma_bulk_g2s(S.pinfo, P.probe_g + (size_t)q * pbytes, pbytes, &S.mbar[0]);
-      mbar_expect_tx(&S.mbar[1], 65536u);
-#pragma unroll
-      for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[1]);
+      if (!early) request_tables(q);
+      if (from_queue) fetch_next();
     }
     __syncthreads();
     // every warp's first claim travels to L2 and back while the tables arrive
@@ -678,6 +690,14 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
     if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
     else scan_loop_m32_v3<IP, false, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
     parity ^= 1u;
+    // ---- every warp is past its last table / probe-block read (the loop's closing barrier): the NEXT query's tables
+    // start streaming in now, under the final select and the write-out
+    early = false;
+    if (from_queue) {
+      const int qn = S.misc[74], rn = S.misc[75];  // written before the barrier that opened this query's scan
+      early = qn >= 0 && rn < P.S;
+      if (early && tid == 0) request_tables(qn);
+    }
     // ---- survivors of this CTA -> cand[q][row][0..R)
     topr.prune_collective<PER>();
     const int n_out = min(*((volatile int *)topr.cnt), P.R);

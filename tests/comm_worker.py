@@ -1,4 +1,4 @@
-"""Worker of tests/test_comm_gpu.py: one process per GPU.  argv: rank world tmpdir"""
+"""Worker of tests/test_comm_gpu.py: one process per rank.  argv: rank world tmpdir device"""
 import json
 import os
 import sys
@@ -12,10 +12,11 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    device = int(sys.argv[4]) if len(sys.argv) > 4 else rank
     import torch
     from gamma_b200 import api, builder, synth
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda:%d" % rank)
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda:%d" % device)
     N, d, nlist, M, n, k = 30000, 64, 64, 32, 96, 10
     xb = synth.mixture(N, d, 7, n_clusters=64)
     xq = synth.mixture(n * world, d, 8, n_clusters=64)
@@ -30,12 +31,12 @@ def main():
         time.sleep(0.2)
         z = np.load(cache)
         coarse, pq, list_no, codes = z["a"], z["b"], z["c"], z["d"]
-    ix = api.B200IVFPQ(rank)
+    ix = api.B200IVFPQ(device)
     assert ix.Init(json.dumps({"ncentroids": nlist, "nsubvector": M, "metric_type": "L2", "nprobe": 8}), d) == 0
     ix.set_quantizers(coarse, pq)
     assert ix.append(list_no, np.arange(N, dtype=np.int64), codes) == 0
     ix.upload_raw(xb)
-    comm = api.Comm(rank, rank, world, n * k * 12)
+    comm = api.Comm(device, rank, world, n * k * 12)
     with open(os.path.join(tmp, "h%d.tmp" % rank), "wb") as f:
         f.write(comm.handle_bytes())
     os.replace(os.path.join(tmp, "h%d.tmp" % rank), os.path.join(tmp, "h%d" % rank))
