@@ -95,6 +95,9 @@ struct Tuning {
   int ch_blocks = 8;      // GB200_SCAN_CH: blocks per item (v3)
   int help_min = 8;       // GB200_SCAN_HELP_MIN: idle CTAs join a query that has >= this many unclaimed items (v3)
   int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
+  int v3_flags = 4;       // GB200_SCAN_FLAGS: M = 32 scan, bit 0: next query fetched inside the scan, bit 1: its tables
+                          // requested before the final select, bit 2: approximate in-loop prunes
+  int scan_cap = 0;       // GB200_SCAN_CAP: candidate buffer of the M = 32 scan in keys (0 = automatic)
   int v3_tma = 0;         // GB200_SCAN_TMA: v3 posting ring fed by bulk copies (1) or per-lane cp.async (0)
   int splits = 0;         // GB200_SCAN_SPLITS: M = 64 / generic: CTAs per query, 0 = automatic
   int tail = 0;           // GB200_SCAN_TAIL: M = 64 plan: splits of the last partial wave, 0 = automatic
@@ -116,6 +119,8 @@ struct Tuning {
     ch_blocks = std::max(1, geti("GB200_SCAN_CH", ch_blocks));
     help_min = std::max(1, geti("GB200_SCAN_HELP_MIN", help_min));
     v3_tma = geti("GB200_SCAN_TMA", v3_tma);
+    scan_cap = std::max(0, geti("GB200_SCAN_CAP", scan_cap));
+    v3_flags = geti("GB200_SCAN_FLAGS", v3_flags);
     max_rows = std::max(0, geti("GB200_SCAN_ROWS", 0));
     splits = std::max(0, geti("GB200_SCAN_SPLITS", 0));
     tail = std::max(0, geti("GB200_SCAN_TAIL", 0));
@@ -1349,7 +1354,9 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   int ctas_per_sm = 3;
   if (ix->mode == 1) {
     if (threads == 0) threads = 384;
-    if (cap > 1024) threads = 512;                 // R > 512: 2048 / 4096 keys (4 / 8 per thread in the select)
+    // tuning: a larger buffer means fewer in-loop selects per query (any multiple of 32 the 4-keys-per-thread select holds)
+    if (T.scan_cap && cap <= 1024 && T.scan_cap >= R + threads && T.scan_cap <= 4 * threads) cap = T.scan_cap & ~31;
+    if (cap > 4 * threads) threads = 512;          // R > 512: 2048 / 4096 keys (4 / 8 per thread in the select)
     if (threads == 512 && cap < 2048) cap = 2048;  // room for one block of each of the 16 warps
     ctas_per_sm = scan_v3_ctas_per_sm(threads, cap);
   } else if (ix->mode == 2) {
@@ -1408,6 +1415,7 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     P.ch_blocks = ch;
     P.help_min = T.help_min;
     P.v3_tma = T.v3_tma;
+    P.v3_flags = T.v3_flags;
     P.help_window = std::min(n, 4 * slots);
     P.max_np_s = nprobe;
   } else {

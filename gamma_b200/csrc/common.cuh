@@ -130,7 +130,11 @@ struct BlockTopR {
   // distance words fall through to a second stage on the scan-order word.  About a dozen barriers
   // and ~2 passes in practice, versus 64 barrier-separated bisection steps.  PER = keys held per thread: cap <= PER * blockDim.x
   // (the launchers pick 4 when the buffer has <= 4 keys per thread, else 16).
-  template <int PER>
+  // EXACT = false (in-loop prunes of the persistent scan): stop after the first histogram pass whose bin boundary leaves
+  // at most R + (cap - R) / 4 survivors — every key up to the upper edge of the bin that holds the R-th one is kept, tau
+  // becomes that edge.  The R best are all among the survivors, the threshold is only slightly looser than the exact one,
+  // and the brute-force ranking and its barriers are skipped; the query's final select runs with EXACT = true.
+  template <int PER, bool EXACT = true>
   __device__ __forceinline__ void prune_collective() {
     __syncthreads();
     const int n = min(*((volatile int *)cnt), cap);
@@ -246,6 +250,11 @@ struct BlockTopR {
       lo = nlo;
       hi = nhi;
       __syncthreads();  // scratch is reused by the next pass / the gather
+      if (!EXACT && stage == 0 && base + cb <= R + ((cap - R) >> 2)) {  // uniform: good enough for an in-loop prune
+        tstar = ((u64)hi << 32) | 0xffffffffu;
+        resolved = true;
+        break;
+      }
       if (cb <= 64) break;
     }
     if (!resolved) {

@@ -366,6 +366,17 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
       claim_pending = false;
       const int it = __shfl_sync(GB_FULL, it_next, 0);
       nx_valid = it < n_items;
+      // the query has no unclaimed item left: what remains are the items other warps are inside.  The first warp to
+      // notice fetches the CTA's NEXT (query, row) from the queue now — late enough not to reserve work a faster CTA
+      // could take, early enough for the two dependent atomics to be back before the query's last barrier
+      if (!nx_valid && lane == 0 && S.misc[77] && atomicExch(&S.misc[76], 1) == 0) {
+        int qn = atomicAdd(P.v3_next_q, 1);
+        int rw = 0;
+        if (qn < P.n) rw = atomicAdd(P.v3_rows + qn, 1);
+        else qn = -1;
+        S.misc[74] = qn;
+        S.misc[75] = rw;
+      }
       if (nx_valid) {
         if (it < P.v3_max_items) {  // the item table gives list and blocks directly
           const uint2 e = S.itab[it];
@@ -551,7 +562,10 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
     const int v = flags[slot];
     if (threadIdx.x == 0) flags[(round + 2) % 3] = 0;  // used two sync points from now; nobody touches it before
     round++;
-    if (v & 1) topr.prune_collective<PER>();
+    if (v & 1) {  // in-loop prune: approximate (keeps a few more than R, far fewer barriers) when enabled
+      if (P.v3_flags & 4) topr.prune_collective<PER, false>();
+      else topr.prune_collective<PER, true>();
+    }
     if (!(v & 2)) break;
   }
   if (TMA) {  // nothing is in flight here (a warp requests only blocks it consumes); drain anyway so the phases stay in step
@@ -653,31 +667,30 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
 #pragma unroll
     for (int i = 0; i < 4; i++) tma_bulk_g2s(gb_scan_smem + i * 16384, src + i * 16384, 16384u, &S.mbar[1]);
   };
-  if (tid == 0) fetch_next();
-  __syncthreads();
+  bool prefetched = false;  // misc[74..75] already hold the next (query, row): fetched inside the previous scan
   for (;;) {
     // ---- the next (query, candidate row) of this CTA
+    if (!helper && !prefetched) {
+      if (tid == 0) fetch_next();
+      __syncthreads();
+    }
     int q = S.misc[74], row = S.misc[75];
-    __syncthreads();  // everybody has read the pair before thread 0 replaces it with the one after
+    __syncthreads();  // everybody has read the pair before it is replaced
+    prefetched = false;
     const bool from_queue = !helper && q >= 0;
     if (!from_queue) {
       helper = true;
       if (!v3_pick_victim<THREADS>(P, S, q, row)) break;
     }
-    if (row >= P.S) {  // every row of this query is taken: the CTAs holding them scan all of its items
-      if (from_queue) {
-        if (tid == 0) fetch_next();
-        __syncthreads();
-      }
-      continue;
-    }
+    if (row >= P.S) continue;  // every row of this query is taken: the CTAs holding them scan all of its items
     if (tid == 0) {
       *topr.cnt = 0;
       *topr.tau = GB_KEY_MAX;
       *topr.tau_f = IP ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);  // everything finite is admitted
       S.misc[68] = S.misc[69] = S.misc[70] = 0;
+      S.misc[76] = 0;                                        // nobody has fetched the next query yet
+      S.misc[77] = (from_queue && (P.v3_flags & 1)) ? 1 : 0;  // ... and whether a warp of the scan should
       if (!early) request_tables(q);
-      if (from_queue) fetch_next();
     }
     __syncthreads();
     // every warp's first claim travels to L2 and back while the tables arrive
@@ -690,12 +703,14 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
     if (P.valid) scan_loop_m32_v3<IP, true, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
     else scan_loop_m32_v3<IP, false, WARPS, PER, RING, TMA>(P, S, topr, q, it_first, ring_epoch, parity);
     parity ^= 1u;
-    // ---- every warp is past its last table / probe-block read (the loop's closing barrier): the NEXT query's tables
-    // start streaming in now, under the final select and the write-out
+    // ---- every warp is past its last table / probe-block read (the loop's closing barrier).  If the next query is
+    // known already (fetched inside the scan) its tables can start streaming in under the final select (optional:
+    // measured slower — the 64 KB of bulk-copy writes collide with the select's shared-memory traffic)
     early = false;
-    if (from_queue) {
-      const int qn = S.misc[74], rn = S.misc[75];  // written before the barrier that opened this query's scan
-      early = qn >= 0 && rn < P.S;
+    if (from_queue && (P.v3_flags & 1)) {
+      prefetched = true;  // every warp ends on a failed claim, so one of them fetched
+      const int qn = S.misc[74], rn = S.misc[75];
+      early = (P.v3_flags & 2) && qn >= 0 && rn < P.S;
       if (early && tid == 0) request_tables(qn);
     }
     // ---- survivors of this CTA -> cand[q][row][0..R)
@@ -734,7 +749,7 @@ static cudaError_t launch_v3_shape(const ScanParams &P, int grid, cudaStream_t s
 //   320 x 2, ring 3: 20 warps per SM, 4 blocks in flight per warp
 //   256 x 2, ring 4: 16 warps per SM, 5 blocks in flight per warp
 //   512 x 1, ring 2: recall_num > 512 (candidate buffers of 2048 / 4096 keys, 4 / 8 keys per thread in the select)
-int scan_v3_ctas_per_sm(int threads, int cap) { return (threads >= 512 || cap > 1024) ? 1 : 2; }
+int scan_v3_ctas_per_sm(int threads, int cap) { return (threads >= 512 || cap > 4 * threads) ? 1 : 2; }
 size_t scan_v3_smem_bytes_for(int nprobe, int max_items, int cap, int threads) {
   const int ring = threads == 320 ? 3 : threads == 256 ? 4 : 2;
   return scan_v3_smem_bytes(nprobe, max_items, cap, threads / 32, ring);

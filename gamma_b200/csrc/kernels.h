@@ -50,6 +50,8 @@ struct ScanParams {
   int v3_zero;              // always 0 (keeps the claim address opaque to the compiler, see scan_loop_m32_v3)
   int help_min;             // an idle CTA joins a running query that still has >= help_min unclaimed items ...
   int help_window;          // ... looking at the last help_window queries
+  int v3_flags;             // bit 0: next query fetched inside the scan, bit 1: its tables requested before the final select,
+                            // bit 2: approximate in-loop prunes
   int v3_max_items;         // capacity of the per-query item table (host bound: nprobe x items of the longest list)
   int v3_tma;               // posting ring fed by bulk copies (cp.async.bulk, one elected lane) instead of per-lane cp.async
 };
