@@ -97,6 +97,8 @@ struct Tuning {
   int max_rows = 0;       // GB200_SCAN_ROWS: candidate rows per query (v3), 0 = automatic
   int v3_flags = 4;       // GB200_SCAN_FLAGS: M = 32 scan, bit 0: next query fetched inside the scan, bit 1: its tables
                           // requested before the final select, bit 2: approximate in-loop prunes
+  int rerank_no_stage = 1;  // GB200_RERANK_STAGE=1: re-rank stages the raw rows in shared memory by cp.async (validated, slower:
+                            // 70 us against 42 — three CTAs per SM instead of sixteen) instead of L2 prefetch + load on use
   int scan_cap = 0;       // GB200_SCAN_CAP: candidate buffer of the M = 32 scan in keys (0 = automatic)
   int v3_tma = 0;         // GB200_SCAN_TMA: v3 posting ring fed by bulk copies (1) or per-lane cp.async (0)
   int splits = 0;         // GB200_SCAN_SPLITS: M = 64 / generic: CTAs per query, 0 = automatic
@@ -121,6 +123,7 @@ struct Tuning {
     v3_tma = geti("GB200_SCAN_TMA", v3_tma);
     scan_cap = std::max(0, geti("GB200_SCAN_CAP", scan_cap));
     v3_flags = geti("GB200_SCAN_FLAGS", v3_flags);
+    rerank_no_stage = geti("GB200_RERANK_STAGE", 0) ? 0 : 1;
     max_rows = std::max(0, geti("GB200_SCAN_ROWS", 0));
     splits = std::max(0, geti("GB200_SCAN_SPLITS", 0));
     tail = std::max(0, geti("GB200_SCAN_TAIL", 0));
@@ -1497,6 +1500,8 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   if (c.timed) CK(cudaEventRecord(c.ev[5], c.stream));
   if (c.timed) CK(cudaEventRecord(c.ev[2], c.stream));
   RerankParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.no_stage = T.rerank_no_stage;
   Q.cand = P.cand;
   Q.keys = d_keys;
   Q.list_off = ix->d_off;

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(CM_THREADS) coarse_select_cmin_kernel(const fl
                                                                         float *__restrict__ coarse_dis) {
   __shared__ u64 cand[CM_CAP];
   __shared__ int chunk_list[CM_CHUNKS];
-  __shared__ float gm_s[CM_THREADS];
+  __shared__ __align__(16) float gm_s[CM_THREADS];
   __shared__ float s_tauf;
   __shared__ int s_cnt, s_nch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -388,9 +388,21 @@ __global__ void __launch_bounds__(CM_THREADS) coarse_select_cmin_kernel(const fl
   const int E = (((cmin_pitch + CM_THREADS - 1) / CM_THREADS) + 3) & ~3;
   const int c_lo = tid * E, c_hi = min(c_lo + E, cmin_pitch);
   float gm = INF;
-  for (int c = c_lo; c < c_hi; c += 4) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(cm + c));
+  // a thread's chunk minima stay in registers when there are at most 16 of them (nlist <= 65536): the candidate pass
+  // below needs them again and must not wait for a second round trip
+  constexpr int KEEP = 16;
+  float kept[KEEP];
+#pragma unroll
+  for (int i = 0; i < KEEP; i += 4) {
+    const int c = c_lo + i;
+    float4 v = make_float4(INF, INF, INF, INF);
+    if (i < E && c < c_hi) v = __ldg(reinterpret_cast<const float4 *>(cm + c));
+    kept[i] = v.x, kept[i + 1] = v.y, kept[i + 2] = v.z, kept[i + 3] = v.w;
     gm = fminf(gm, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));  // fminf drops NaN (a chunk of nothing but NaN)
+  }
+  for (int c = c_lo + KEEP; c < c_hi; c += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(cm + c));
+    gm = fminf(gm, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
   }
   gm = gm < INF ? gm : INF;
   gm_s[tid] = gm;
@@ -402,9 +414,13 @@ __global__ void __launch_bounds__(CM_THREADS) coarse_select_cmin_kernel(const fl
   __syncthreads();
   {
     int r = 0;
-    for (int j = 0; j < CM_THREADS; j++) {
-      const float o = gm_s[j];
-      r += (o < gm) || (o == gm && j < tid);
+#pragma unroll 8
+    for (int j = 0; j < CM_THREADS; j += 4) {  // broadcast 128-bit reads
+      const float4 o = *reinterpret_cast<const float4 *>(gm_s + j);
+      r += (o.x < gm) || (o.x == gm && j < tid);
+      r += (o.y < gm) || (o.y == gm && j + 1 < tid);
+      r += (o.z < gm) || (o.z == gm && j + 2 < tid);
+      r += (o.w < gm) || (o.w == gm && j + 3 < tid);
     }
     if (r == nprobe - 1 && gm < INF) s_tauf = gm;
   }
@@ -412,7 +428,14 @@ __global__ void __launch_bounds__(CM_THREADS) coarse_select_cmin_kernel(const fl
   const float tauf = s_tauf;
   bool slow = !(tauf < INF);
   if (!slow) {
-    for (int c = c_lo; c < c_hi; c++) {
+#pragma unroll
+    for (int i = 0; i < KEEP; i++) {
+      if (kept[i] <= tauf) {  // +inf beyond the thread's share
+        const int slot = atomicAdd(&s_nch, 1);
+        if (slot < CM_CHUNKS) chunk_list[slot] = c_lo + i;
+      }
+    }
+    for (int c = c_lo + KEEP; c < c_hi; c++) {
       if (cm[c] <= tauf) {
         const int slot = atomicAdd(&s_nch, 1);
         if (slot < CM_CHUNKS) chunk_list[slot] = c;

@@ -310,18 +310,31 @@ struct BlockTopR {
 // tails, two horizontal adds — re-ranked and FLAT distances are bit-identical to the CPU engine's.
 // ---------------------------------------------------------------------------
 // 8 consecutive lanes (an "octet") cooperate on one candidate; returns the result in every lane of the octet
-template <bool IP>
+// YS: y points into shared memory (rows staged by the caller) instead of global memory
+template <bool IP, bool YS = false>
 __device__ __forceinline__ float exact_distance_octet(const float *__restrict__ q, const float *__restrict__ y,
                                                       int d, int sub /*0..7*/) {
   float s = 0.f;
   int d8 = d & ~7;
-  for (int i = sub; i < d8; i += 8) {
-    float a = q[i], b = __ldg(y + i);
-    if (IP) {
-      s = __fadd_rn(s, __fmul_rn(a, b));
-    } else {
-      float t = __fsub_rn(a, b);
-      s = __fadd_rn(s, __fmul_rn(t, t));
+  // 16 strided elements of the row per lane are requested before the first one is used (profiles/r02_rerank: with
+  // two loads in flight 41 % of the kernel's warp time sat on the first FADD after each load); the arithmetic and its
+  // order are unchanged
+  constexpr int U = 16;
+  for (int i0 = sub; i0 < d8; i0 += 8 * U) {
+    float yv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) yv[u] = (i0 + 8 * u < d8) ? (YS ? y[i0 + 8 * u] : __ldg(y + i0 + 8 * u)) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (i0 + 8 * u < d8) {
+        const float a = q[i0 + 8 * u], b = yv[u];
+        if (IP) {
+          s = __fadd_rn(s, __fmul_rn(a, b));
+        } else {
+          float t = __fsub_rn(a, b);
+          s = __fadd_rn(s, __fmul_rn(t, t));
+        }
+      }
     }
   }
   // msum2 = hi + lo
@@ -330,7 +343,7 @@ __device__ __forceinline__ float exact_distance_octet(const float *__restrict__ 
   int rem = d - d8;
   if (rem >= 4) {
     if (sub < 4) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      float a = q[d8 + sub], b = YS ? y[d8 + sub] : __ldg(y + d8 + sub);
       t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
     }
     d8 += 4;
@@ -338,7 +351,7 @@ __device__ __forceinline__ float exact_distance_octet(const float *__restrict__ 
   }
   if (rem > 0) {
     if (sub < rem) {
-      float a = q[d8 + sub], b = __ldg(y + d8 + sub);
+      float a = q[d8 + sub], b = YS ? y[d8 + sub] : __ldg(y + d8 + sub);
       t4 = IP ? __fmaf_rn(a, b, t4) : __fmaf_rn(__fsub_rn(a, b), __fsub_rn(a, b), t4);
     }
   }

@@ -176,6 +176,8 @@ struct RerankParams {
   long long *out_ids;       // [n][k]
   int n, S, R, k, nprobe, raw_d, xq_stride, has_rank, is_ip;
   float min_score, max_score;
+  int stage_rows, stage_off;  // set by launch_rerank: raw rows staged in shared memory per chunk / their offset (0 = off)
+  int no_stage;             // tuning: 1 = the L2-prefetch + load-on-use path
   const int *nsplit;        // optional [n]: candidate rows the query really has (<= S); nullptr = S ...
   int n_full;               // ... or, when > 0 (positional plan), 1 row for q < n_full and S rows otherwise
 };

@@ -9,6 +9,8 @@
 // (faiss utils/distances_simd.cpp:366-431): 8 strided partial sums (mul then add, unfused),
 // hi/lo halves added, optional 4-wide and masked tails (fused), then two horizontal adds —
 // so re-ranked distances are bit-identical to the CPU engine built with the same flags.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
     vids[i] = vid;
   }
   __syncthreads();
-  if (P.has_rank) {  // pull the candidates' raw rows towards L2 now; the distance loop below then runs on L2 latency
+  if (P.has_rank && P.stage_rows <= 0) {  // unstaged path: pull the candidates' raw rows towards L2 now
     const int lines = (P.raw_d * 4 + 127) >> 7;
     const int nr = min(P.R, p2_r);
     for (int i = tid; i < nr * lines; i += RR_THREADS) {
@@ -68,15 +70,54 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
     // exact distances, 8 lanes per candidate
     const int sub = tid & 7, oct = tid >> 3;
     const int n_oct = RR_THREADS / 8;
-    for (int base = 0; base < p2_r; base += n_oct) {
-      int i = base + oct;
-      int vid = i < p2_r ? vids[i] : -1;
-      bool have = vid >= 0 && (long long)vid < P.nraw;
-      const float *y = P.raw + (size_t)(have ? vid : 0) * P.raw_d;
-      float dis = exact_distance_octet<IP>(qs, y, have ? P.raw_d : 0, sub);
-      if (sub == 0 && i < p2_r) {
-        bool ok = have && dis <= P.max_score && dis >= P.min_score;  // IsSimilarScoreValid
-        keys2[i] = ok ? (((u64)dist_to_key32<IP>(dis) << 32) | (uint32_t)i) : GB_KEY_MAX;
+    if (P.stage_rows > 0) {
+      // The candidates' raw rows (random 4 * raw_d-byte rows of a multi-GB table) are pulled into shared memory with
+      // cp.async, every row of a chunk requested before the first one is used: hundreds of DRAM lines in flight per CTA
+      // instead of the handful the L2-prefetch + load-on-use scheme sustained (profiles/r02: 1.4 TB/s, long-scoreboard
+      // stall 8.5 per issue).  Rows are padded by 8 floats so the four octets of a warp read different banks.
+      const int pitch = P.raw_d + 8;
+      float *rows = reinterpret_cast<float *>(smem + P.stage_off);
+      const int nr = min(P.R, p2_r), lane = tid & 31, warp = tid >> 5;
+      for (int i = tid; i < p2_r; i += RR_THREADS) keys2[i] = GB_KEY_MAX;
+      for (int c0 = 0; c0 < nr; c0 += P.stage_rows) {
+        const int ncur = min(P.stage_rows, nr - c0);
+        for (int c = warp; c < ncur; c += RR_THREADS / 32) {
+          const int vid = vids[c0 + c];
+          if (vid >= 0 && (long long)vid < P.nraw) {
+            const float *src = P.raw + (size_t)vid * P.raw_d;
+            for (int off = lane * 4; off < P.raw_d; off += 128)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(
+                               rows + (size_t)c * pitch + off)),
+                           "l"(src + off)
+                           : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        for (int base = 0; base < ncur; base += n_oct) {
+          const int c = base + oct, i = c0 + c;
+          const int vid = c < ncur ? vids[i] : -1;
+          const bool have = vid >= 0 && (long long)vid < P.nraw;
+          const float dis = exact_distance_octet<IP, true>(qs, rows + (size_t)(have ? c : 0) * pitch, have ? P.raw_d : 0, sub);
+          if (sub == 0 && c < ncur) {
+            const bool ok = have && dis <= P.max_score && dis >= P.min_score;  // IsSimilarScoreValid
+            keys2[i] = ok ? (((u64)dist_to_key32<IP>(dis) << 32) | (uint32_t)i) : GB_KEY_MAX;
+          }
+        }
+        __syncthreads();  // the next chunk overwrites the rows
+      }
+    } else {
+      for (int base = 0; base < p2_r; base += n_oct) {
+        int i = base + oct;
+        int vid = i < p2_r ? vids[i] : -1;
+        bool have = vid >= 0 && (long long)vid < P.nraw;
+        const float *y = P.raw + (size_t)(have ? vid : 0) * P.raw_d;
+        float dis = exact_distance_octet<IP>(qs, y, have ? P.raw_d : 0, sub);
+        if (sub == 0 && i < p2_r) {
+          bool ok = have && dis <= P.max_score && dis >= P.min_score;  // IsSimilarScoreValid
+          keys2[i] = ok ? (((u64)dist_to_key32<IP>(dis) << 32) | (uint32_t)i) : GB_KEY_MAX;
+        }
       }
     }
     __syncthreads();
@@ -120,10 +161,25 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
   }
 }
 
-cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st) {
+cudaError_t launch_rerank(const RerankParams &P_in, cudaStream_t st) {
+  RerankParams P = P_in;
   int p2_all = next_pow2(P.S * P.R);
   int p2_r = next_pow2(P.R);
   size_t smem = (size_t)(p2_all + p2_r) * sizeof(u64) + (size_t)p2_r * sizeof(int) + (size_t)P.raw_d * sizeof(float);
+  // row staging for the exact re-rank: as many 16-candidate rounds as fit in ~64 KB
+  P.stage_rows = 0;
+  P.stage_off = 0;
+  if (P.has_rank && (P.raw_d & 3) == 0 && !P.no_stage) {
+    const size_t row_bytes = (size_t)(P.raw_d + 8) * sizeof(float);
+    int rows = (int)((64 * 1024) / row_bytes) & ~15;
+    const int want = (std::min(P.R, p2_r) + 15) & ~15;
+    if (rows > want) rows = want;
+    if (rows >= 16) {
+      P.stage_off = (int)((smem + 15) & ~(size_t)15);
+      P.stage_rows = rows;
+      smem = (size_t)P.stage_off + (size_t)rows * row_bytes;
+    }
+  }
   if (smem > 48 * 1024) {  // per device and cheap: set on every such launch (an index may live on any device)
     cudaError_t e = P.is_ip ? cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
