@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgamma_b200.so")
-SOURCES = ["capi.cu", "ivfpq_scan.cu", "ivfpq_scan_v3.cu", "postings.cu", "coarse.cu", "rerank.cu", "flat.cu", "selftest.cu", "tc_gemm.cu", "flat_tc.cu", "encode.cu", "comm.cu", "ivfflat.cu"]
+SOURCES = ["capi.cu", "ivfpq_scan.cu", "ivfpq_scan_v3.cu", "postings.cu", "coarse.cu", "rerank.cu", "flat.cu", "selftest.cu", "tc_gemm.cu", "flat_tc.cu", "encode.cu", "comm.cu", "ivfflat.cu", "launch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -22,7 +22,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <thread>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -109,6 +111,12 @@ struct Tuning {
   int lut_inline = 0;     // GB200_LUT_INLINE: build the tables on the main stream
   int flat_mode = 0;      // GB200_FLAT: 0 automatic, 1 = exact (per-query scan), 2 = tc (tensor-core path for any batch)
   int max_contexts = 8;   // GB200_MAX_CONTEXTS: Search calls in flight per index (each owns streams + workspaces)
+  int coalesce = 3;       // GB200_COALESCE: concurrent host-buffer IVFPQ searches with equal parameters are merged into one
+                          // device batch once this many merged batches are already in flight (0 = never merge)
+  int coalesce_max = 2048;  // GB200_COALESCE_MAX: queries per merged batch (calls of at least half this size are not merged)
+  int coalesce_wait_us = 60;  // GB200_COALESCE_WAIT_US: while another batch keeps the device busy, a starting batch waits up
+                              // to this long for the callers it expects (recent concurrency / coalesce); 0 = never waits
+  int coalesce_balance = 1;   // GB200_COALESCE_BALANCE: a batch takes at most its share (recent concurrency / coalesce)
   long long flat_chunk_rows = 0;  // GB200_FLAT_CHUNK_ROWS: database rows per tensor-core chunk (tests: force many chunks)
   void read() {
     *this = Tuning();
@@ -131,6 +139,10 @@ struct Tuning {
     lut_inline = geti("GB200_LUT_INLINE", 0);
     coarse_full_select = geti("GB200_COARSE_FULL_SELECT", 0);
     max_contexts = std::max(1, std::min(64, geti("GB200_MAX_CONTEXTS", max_contexts)));
+    coalesce = std::max(0, std::min(max_contexts, geti("GB200_COALESCE", coalesce)));
+    coalesce_max = std::max(2, geti("GB200_COALESCE_MAX", coalesce_max));
+    coalesce_wait_us = std::max(0, std::min(1000, geti("GB200_COALESCE_WAIT_US", coalesce_wait_us)));
+    coalesce_balance = geti("GB200_COALESCE_BALANCE", coalesce_balance);
     if (const char *e = getenv("GB200_COARSE")) coarse_simt = !strcmp(e, "simt");
     if (const char *e = getenv("GB200_FLAT")) flat_mode = !strcmp(e, "exact") ? 1 : !strcmp(e, "tc") ? 2 : 0;
     if (const char *e = getenv("GB200_FLAT_CHUNK_ROWS")) flat_chunk_rows = atoll(e);
@@ -148,7 +160,10 @@ struct SearchCtx {
       ws_ctl, ws_cmin, ws_xt;
   DevBuf valid_filt, filt_bytes, filt_desc;  // per-call range filters -> validity bitmap
   unsigned long long *d_scanned = nullptr;
+  void *h_stage = nullptr;  // pinned: results of a merged batch before they are handed to their callers
+  size_t h_stage_cap = 0;
   int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
+  int zero_req = 0, zeroed_for = 0;  // scan control words: queries the coarse stage should zero them for / did
   long long launches = 0;
   bool timed = false;  // the events of the last call were recorded
 
@@ -169,6 +184,7 @@ struct SearchCtx {
                       &ws_lut, &ws_xs, &ws_fstate, &ws_probe, &ws_ctl,  &valid_filt, &filt_bytes, &filt_desc, &ws_cmin, &ws_xt};
     for (DevBuf *b : bufs) b->release();
     if (d_scanned) cudaFree(d_scanned);
+    if (h_stage) cudaFreeHost(h_stage);
     for (int i = 0; i < 6; i++)
       if (ev[i]) cudaEventDestroy(ev[i]);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -195,6 +211,24 @@ struct gb200_index {
   std::mutex writer_mu;
   std::mutex ctx_mu;
   std::condition_variable ctx_cv;
+  // concurrent small searches waiting to be merged into one device batch (search_coalesced)
+  struct PendingSearch {
+    int n, k;
+    const float *xq;
+    float *D;
+    int64_t *I;
+    gb200_search_params sp;
+    int rc = GB200_OK;
+    bool taken = false, done = false;  // travelling in another caller's batch / that batch has finished
+    std::string err;
+  };
+  std::mutex co_mu;
+  std::condition_variable co_cv;
+  std::vector<PendingSearch *> co_waiting;
+  int co_leaders = 0;   // batches being formed or running (<= tune.coalesce)
+  int co_running = 0;   // batches on the device
+  int co_inflight = 0;  // callers travelling in them
+  int co_peak = 0;      // recent number of concurrent callers (in flight + waiting), decays by one per batch
   std::vector<SearchCtx *> ctx_all, ctx_free;
   SearchCtx *last_ctx = nullptr;  // most recently used context (gb200_sync / profiling read-out)
   std::mutex stats_mu;
@@ -1264,7 +1298,13 @@ static int coarse_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_xq, i
   const bool use_tc = !ix->tune.coarse_simt && (d % 4 == 0) && (nlist % 4 == 0);
   if (use_tc) {
     CKI(c.ws_xs.ensure((size_t)n * d * sizeof(float)));
-    CK(launch_rows_prep(d_xq, n, d, c.ws_xn.as<float>(), c.ws_xs.as<float>(), c.stream));
+    if (c.zero_req == n && c.ws_ctl.p) {  // the scan's control words and counter ride on this launch (no memset nodes)
+      CK(launch_rows_prep(d_xq, n, d, c.ws_xn.as<float>(), c.ws_xs.as<float>(), c.stream, c.ws_ctl.as<int>(), 4 + 2 * n,
+                          c.d_scanned));
+      c.zeroed_for = n;
+    } else {
+      CK(launch_rows_prep(d_xq, n, d, c.ws_xn.as<float>(), c.ws_xs.as<float>(), c.stream));
+    }
   } else {
     CK(launch_row_norms(d_xq, n, d, c.ws_xn.as<float>(), c.stream));
   }
@@ -1452,7 +1492,9 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     set_err("scan needs %zu B shared memory (M=%d recall_num=%d nprobe=%d): not implemented", smem_need, M, R, nprobe);
     return GB200_EUNSUPPORTED;
   }
-  CK(cudaMemsetAsync(c.d_scanned, 0, sizeof(unsigned long long), c.stream));
+  const bool pre_zeroed = c.zeroed_for == n && variant == 3;
+  c.zeroed_for = 0;
+  if (!pre_zeroed) CK(cudaMemsetAsync(c.d_scanned, 0, sizeof(unsigned long long), c.stream));
   if (c.timed) CK(cudaEventRecord(c.ev[1], c.stream));
   const int *d_rows = nullptr;
   if (ix->mode == 1 || ix->mode == 2) {
@@ -1473,7 +1515,7 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
     if (variant == 3) {
       // control words [next_q, pad x3][claim x n][rows x n], zeroed; per-query probe tables
       CKI(c.ws_ctl.ensure((size_t)(4 + 2 * (size_t)n) * sizeof(int)));
-      CK(cudaMemsetAsync(c.ws_ctl.p, 0, (size_t)(4 + 2 * (size_t)n) * sizeof(int), c.stream));
+      if (!pre_zeroed) CK(cudaMemsetAsync(c.ws_ctl.p, 0, (size_t)(4 + 2 * (size_t)n) * sizeof(int), c.stream));
       P.v3_next_q = c.ws_ctl.as<int>();
       P.v3_claim = c.ws_ctl.as<int>() + 4;
       P.v3_rows = c.ws_ctl.as<int>() + 4 + n;
@@ -1624,7 +1666,13 @@ static int ivfpq_search_impl(gb200_index *ix, SearchCtx &c, int n, const float *
     CK(cudaMemcpyAsync(c.ws_cdis.p, cdis_h, (size_t)n * nprobe * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     CK(cudaStreamSynchronize(c.stream));
   } else {
+    c.zero_req = 0;
+    if (ix->mode == 1) {  // the persistent scan's control words are zeroed by the coarse stage's first launch
+      CKI(c.ws_ctl.ensure((size_t)(4 + 2 * (size_t)n) * sizeof(int)));
+      c.zero_req = n;
+    }
     CKI(coarse_dev(ix, c, n, d_xq, nprobe, c.ws_keys.as<int>(), c.ws_cdis.as<float>()));
+    c.zero_req = 0;
   }
   float *d_D = D;
   long long *d_I = reinterpret_cast<long long *>(I);
@@ -1656,11 +1704,138 @@ static int release_to_user_stream(SearchCtx &c, cudaStream_t cs) {
   return GB200_OK;
 }
 
+// One device batch for a group of callers: their queries are copied into one workspace, one search runs, each caller
+// gets its rows back.  A query's result does not depend on the batch it travels in (every stage works per query row).
+static int run_merged(gb200_index *ix, const std::vector<gb200_index::PendingSearch *> &grp) {
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  SearchCtx &c = *s.c;
+  const int d = ix->p.d, k = grp[0]->k;
+  int n = 0;
+  for (auto *r : grp) n += r->n;
+  CKI(c.ws_xq.ensure((size_t)n * d * sizeof(float)));
+  CKI(c.ws_out_d.ensure((size_t)n * k * sizeof(float)));
+  CKI(c.ws_out_i.ensure((size_t)n * k * sizeof(long long)));
+  const size_t out_bytes = (size_t)n * k * (sizeof(float) + sizeof(long long));
+  if (c.h_stage_cap < out_bytes) {
+    if (c.h_stage) CK(cudaFreeHost(c.h_stage));
+    c.h_stage = nullptr, c.h_stage_cap = 0;
+    CK(cudaMallocHost(&c.h_stage, out_bytes * 2));
+    c.h_stage_cap = out_bytes * 2;
+  }
+  size_t row = 0;
+  for (auto *r : grp) {
+    CK(cudaMemcpyAsync(c.ws_xq.as<float>() + row * d, r->xq, (size_t)r->n * d * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    row += r->n;
+  }
+  CKI(ivfpq_search_impl(ix, c, n, c.ws_xq.as<float>(), true, k, &grp[0]->sp, nullptr, 0, false, nullptr, nullptr, 0,
+                        c.ws_out_d.as<float>(), reinterpret_cast<int64_t *>(c.ws_out_i.p), true));
+  long long *h_I = static_cast<long long *>(c.h_stage);
+  float *h_D = reinterpret_cast<float *>(h_I + (size_t)n * k);
+  CK(cudaMemcpyAsync(h_I, c.ws_out_i.p, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaMemcpyAsync(h_D, c.ws_out_d.p, (size_t)n * k * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  CKI(finish_profile(ix, c));
+  row = 0;
+  for (auto *r : grp) {
+    memcpy(r->I, h_I + row * k, (size_t)r->n * k * sizeof(long long));
+    memcpy(r->D, h_D + row * k, (size_t)r->n * k * sizeof(float));
+    row += r->n;
+  }
+  return GB200_OK;
+}
+
+static bool same_search(const gb200_index::PendingSearch &a, const gb200_index::PendingSearch &b) {
+  return a.k == b.k && a.sp.metric == b.sp.metric && a.sp.nprobe == b.sp.nprobe && a.sp.recall_num == b.sp.recall_num &&
+         a.sp.has_rank == b.sp.has_rank && a.sp.min_score == b.sp.min_score && a.sp.max_score == b.sp.max_score;
+}
+
+// Group commit for concurrent callers (reference: one Search per request thread, tests/test.h:1033-1062).  Up to
+// tune.coalesce batches are in flight at once, each on its own context, so the device always has the next batch queued
+// behind the running one.  A caller that arrives while that many are in flight waits, and the next batch to start takes
+// the waiting requests with the same parameters along.  A batch that starts while the device is busy anyway first waits
+// (at most coalesce_wait_us, spinning) until its share of the recent callers has arrived: threads released by one batch
+// come back within microseconds of one another and would otherwise each start a batch of their own.  A lone caller, or
+// any caller that finds the device idle, starts at once.
+static int search_coalesced(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp, float *D, int64_t *I) {
+  gb200_index::PendingSearch me;
+  me.n = n, me.k = k, me.xq = xq, me.D = D, me.I = I, me.sp = *sp;
+  std::vector<gb200_index::PendingSearch *> grp;
+  const Tuning &T = ix->tune;
+  {
+    std::unique_lock<std::mutex> g(ix->co_mu);
+    auto &w = ix->co_waiting;
+    w.push_back(&me);
+    ix->co_cv.wait(g, [&] { return me.done || (!me.taken && ix->co_leaders < T.coalesce); });
+    if (me.done) {
+      if (me.rc != GB200_OK) set_err("%s", me.err.c_str());
+      return me.rc;
+    }
+    ix->co_leaders++;
+    auto share = [&] {
+      ix->co_peak = std::max(ix->co_peak, ix->co_inflight + (int)w.size());
+      return std::max(1, (ix->co_peak + T.coalesce - 1) / T.coalesce);
+    };
+    if (T.coalesce_wait_us > 0 && ix->co_running > 0) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (;;) {
+        const int want = std::min(share(), std::max(1, ix->co_peak - ix->co_inflight));
+        if ((int)w.size() >= want || ix->co_running == 0) break;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(T.coalesce_wait_us)) break;
+        g.unlock();
+        std::this_thread::yield();
+        g.lock();
+      }
+    }
+    const int max_reqs = T.coalesce_balance ? share() : (1 << 30);
+    int total = me.n;
+    grp.push_back(&me);
+    size_t keep = 0;
+    for (size_t i = 0; i < w.size(); i++) {
+      gb200_index::PendingSearch *r = w[i];
+      if (r == &me) continue;
+      if ((int)grp.size() < max_reqs && same_search(*r, me) && total + r->n <= T.coalesce_max) {
+        grp.push_back(r);
+        r->taken = true;
+        total += r->n;
+      } else {
+        w[keep++] = r;
+      }
+    }
+    w.resize(keep);
+    ix->co_peak = std::max(ix->co_inflight + (int)grp.size() + (int)w.size(), ix->co_peak - 1);
+    ix->co_running++;
+    ix->co_inflight += (int)grp.size();
+  }
+  int rc;
+  if (grp.size() == 1) {  // nobody to take along: the plain path, results straight into the caller's buffers
+    SearchScope s(ix);
+    rc = !s.c ? GB200_ECUDA : ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, nullptr, 0, false, nullptr, nullptr, 0, D, I, false);
+  } else {
+    rc = run_merged(ix, grp);
+  }
+  {
+    std::lock_guard<std::mutex> g(ix->co_mu);
+    ix->co_leaders--;
+    ix->co_running--;
+    ix->co_inflight -= (int)grp.size();
+    for (size_t i = 1; i < grp.size(); i++) {
+      grp[i]->rc = rc;
+      if (rc != GB200_OK) grp[i]->err = g_err;
+      grp[i]->done = true;
+    }
+  }
+  ix->co_cv.notify_all();
+  return rc;
+}
+
 int gb200_ivfpq_search(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp,
                        const gb200_range_filter *filters, int n_filters, float *D, int64_t *I) {
   CKI(check_search_args(ix, n, xq, k, sp, D, I));
   if (ix->kind != 0) return GB200_EINVAL;
   CKI(use_device(ix));
+  if (ix->tune.coalesce > 0 && n > 0 && n_filters == 0 && 2 * n <= ix->tune.coalesce_max && !ix->profiling && !ix->flat_lists &&
+      ix->trained)
+    return search_coalesced(ix, n, xq, k, sp, D, I);
   SearchScope s(ix);
   if (!s.c) return GB200_ECUDA;
   return ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, filters, n_filters, false, nullptr, nullptr, 0, D, I, false);

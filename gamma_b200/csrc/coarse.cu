@@ -537,10 +537,8 @@ cudaError_t launch_coarse_select(const float *dist, int n, int nlist, int nprobe
   if (cap <= 4 * CS_THREADS) {
     coarse_select_kernel<4><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   } else {
-    if (smem > 48 * 1024) {  // per device and cheap: no process-wide cache
-      cudaError_t e = cudaFuncSetAttribute(coarse_select_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(coarse_select_kernel<16>, smem);
+    if (e != cudaSuccess) return e;
     coarse_select_kernel<16><<<n, CS_THREADS, smem, st>>>(dist, nlist, nprobe, cap, keys, coarse_dis);
   }
   return cudaGetLastError();

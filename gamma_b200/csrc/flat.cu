@@ -101,14 +101,10 @@ cudaError_t launch_flat_exact(const FlatParams &P, cudaStream_t st) {
   if (smem > 200 * 1024 || smem2 > 200 * 1024) return cudaErrorInvalidValue;
   auto run = [&](auto exact, auto merge) -> cudaError_t {
     cudaError_t e;
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e) return e;
-    }
-    if (smem2 > 48 * 1024) {
-      e = cudaFuncSetAttribute(merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      if (e) return e;
-    }
+    e = ensure_dynamic_smem(exact, smem);
+    if (e) return e;
+    e = ensure_dynamic_smem(merge, smem2);
+    if (e) return e;
     exact<<<dim3(P.nsplit, P.n), FL_THREADS, smem, st>>>(P, cap, kpad);
     merge<<<P.n, 256, smem2, st>>>(P, kpad, p2);
     return cudaGetLastError();

@@ -231,10 +231,8 @@ cudaError_t launch_flat_chunk_select(const float *dist, int ldo, int nc, long lo
   while (cap < need) cap <<= 1;
   size_t smem = (size_t)cap * sizeof(u64) + (4 + 64) * sizeof(int);
   auto go = [&](auto kern) -> cudaError_t {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
+    if (e) return e;
     kern<<<n, FT_THREADS, smem, st>>>(dist, ldo, nc, chunk_base, valid, lo, hi, Kp, cap, first, state);
     return cudaGetLastError();
   };
@@ -249,16 +247,12 @@ cudaError_t launch_flat_rescore(const u64 *state, int Kp, const float *xq, const
   int p2 = next_pow2(Kp > k ? Kp : k);
   size_t smem = (size_t)p2 * sizeof(u64) + (size_t)d * sizeof(float);
   if (is_ip) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(flat_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(flat_rescore_kernel<true>, smem);
+    if (e) return e;
     flat_rescore_kernel<true><<<n, 128, smem, st>>>(state, Kp, p2, xq, raw, d, min_score, max_score, k, out_d, out_i);
   } else {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(flat_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(flat_rescore_kernel<false>, smem);
+    if (e) return e;
     flat_rescore_kernel<false><<<n, 128, smem, st>>>(state, Kp, p2, xq, raw, d, min_score, max_score, k, out_d, out_i);
   }
   return cudaGetLastError();

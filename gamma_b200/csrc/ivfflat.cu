@@ -84,10 +84,8 @@ cudaError_t launch_ivfflat_scan(const IvfFlatParams &P, cudaStream_t st) {
   const size_t smem = (size_t)P.cap * sizeof(u64) + (4 + 64) * sizeof(int) + (size_t)P.d * sizeof(float);
   dim3 grid(P.S, P.n);
   auto go = [&](auto kern) -> cudaError_t {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
+    if (e != cudaSuccess) return e;
     kern<<<grid, IF_THREADS, smem, st>>>(P);
     return cudaGetLastError();
   };

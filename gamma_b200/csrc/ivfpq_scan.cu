@@ -379,11 +379,9 @@ template <typename K>
 static cudaError_t launch_kernel(K kernel, const ScanParams &P, int mode, int threads, size_t *configured,
                                  cudaStream_t st) {
   size_t smem = scan_smem_bytes(P, mode);
-  {  // the attribute is per device and setting it is cheap: no process-wide cache (an index may live on any device)
-    (void)configured;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
+  (void)configured;
+  cudaError_t e = ensure_dynamic_smem(kernel, smem);
+  if (e != cudaSuccess) return e;
   dim3 grid(P.S, P.n);
   if (P.n_items > 0) grid = dim3(P.n_items, 1);
   kernel<<<grid, threads, smem, st>>>(P);

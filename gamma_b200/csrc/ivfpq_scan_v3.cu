@@ -722,12 +722,9 @@ __global__ void __launch_bounds__(THREADS, MINB) ivfpq_scan_m32_v3_kernel(ScanPa
   }
 }
 
-// cudaFuncSetAttribute is per device and cheap: called on every launch instead of caching per process (an index may live
-// on any device)
 template <bool IP, int T, int MINB, int PER, int RING, bool TMA>
 static cudaError_t launch_v3_one(const ScanParams &P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(ivfpq_scan_m32_v3_kernel<IP, T, MINB, PER, RING, TMA>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(ivfpq_scan_m32_v3_kernel<IP, T, MINB, PER, RING, TMA>, smem);
   if (e != cudaSuccess) return e;
   ivfpq_scan_m32_v3_kernel<IP, T, MINB, PER, RING, TMA><<<grid, T, smem, st>>>(P);
   return cudaGetLastError();

@@ -121,7 +121,17 @@ cudaError_t launch_row_norms(const float *x, int rows, int d, float *out, cudaSt
 cudaError_t launch_linear_apply(const float *x, int x_stride, int rows, int d_in, const float *At, const float *b,
                                 int d_out, float *y, cudaStream_t st);
 // |x|^2 and x - tf32(x) of every row in one pass (the query side of the tensor-core distance producer)
-cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st);
+// permission for a launch with `smem` bytes of dynamic shared memory (> 48 KB needs the opt-in attribute): grows the
+// attribute of (func, current device) monotonically, safe against concurrent launches with other sizes (launch.cu)
+cudaError_t ensure_dynamic_smem(const void *func, size_t smem);
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K *kernel, size_t smem) {
+  return ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), smem);
+}
+
+// zero_words / zero_u64 (optional): control words of a later kernel of the same search, zeroed by this launch
+cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st,
+                             int *zero_words = nullptr, int n_zero = 0, unsigned long long *zero_u64 = nullptr);
 cudaError_t launch_coarse_dist(const float *xq, const float *xq_norm, const float *cent,
                                const float *cent_norm, int n, int nlist, int d, float *dist,
                                cudaStream_t st);

@@ -243,7 +243,11 @@ __global__ void row_norms_kernel(const float *x, int rows, int d, float *out) {
 }
 // |x|^2 (same summation order as row_norms_kernel) and x - tf32(x) of every row in ONE pass: the two operands the
 // tensor-core distance producer needs next to the rows themselves (one launch instead of two on the search path)
-__global__ void rows_prep_kernel(const float *x, int rows, int d, float *norms, float *small) {
+__global__ void rows_prep_kernel(const float *x, int rows, int d, float *norms, float *small, int *zero_words, int n_zero,
+                                 unsigned long long *zero_u64) {
+  // optional: control words of a later kernel of the same search, zeroed here instead of by separate memset nodes
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_words[i] = 0;
+  if (zero_u64 && blockIdx.x == 0 && threadIdx.x == 0) *zero_u64 = 0ull;
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   int lane = threadIdx.x & 31;
@@ -258,9 +262,10 @@ __global__ void rows_prep_kernel(const float *x, int rows, int d, float *norms, 
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(GB_FULL, s, o);
   if (lane == 0) norms[r] = s;
 }
-cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st) {
+cudaError_t launch_rows_prep(const float *x, int rows, int d, float *norms, float *small, cudaStream_t st, int *zero_words,
+                             int n_zero, unsigned long long *zero_u64) {
   if (rows <= 0) return cudaSuccess;
-  rows_prep_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, d, norms, small);
+  rows_prep_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, d, norms, small, zero_words, zero_words ? n_zero : 0, zero_u64);
   return cudaGetLastError();
 }
 

@@ -180,9 +180,8 @@ cudaError_t launch_rerank(const RerankParams &P_in, cudaStream_t st) {
       smem = (size_t)P.stage_off + (size_t)rows * row_bytes;
     }
   }
-  if (smem > 48 * 1024) {  // per device and cheap: set on every such launch (an index may live on any device)
-    cudaError_t e = P.is_ip ? cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = P.is_ip ? ensure_dynamic_smem(rerank_kernel<true>, smem) : ensure_dynamic_smem(rerank_kernel<false>, smem);
     if (e != cudaSuccess) return e;
   }
   if (P.is_ip)

@@ -45,11 +45,11 @@ cudaError_t launch_select_selftest(const u64 *keys, int n, int R, int cap, int b
   size_t smem = (size_t)cap * sizeof(u64) + (4 + 64) * sizeof(int);
   cudaError_t e;
   if (cap <= 4 * threads) {
-    e = cudaFuncSetAttribute(select_selftest_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(select_selftest_kernel<4>, smem);
     if (e) return e;
     select_selftest_kernel<4><<<1, threads, smem, st>>>(keys, n, R, cap, batch, out, out_n);
   } else {
-    e = cudaFuncSetAttribute(select_selftest_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(select_selftest_kernel<16>, smem);
     if (e) return e;
     select_selftest_kernel<16><<<1, threads, smem, st>>>(keys, n, R, cap, batch, out, out_n);
   }

@@ -351,8 +351,8 @@ cudaError_t launch_tc_gemm(const float *a, const float *a_small, const float *a_
     return cudaErrorNotSupported;
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 4) * sizeof(uint64_t) + 16 +
                       TC_EPI_WARPS * TC_TR_FLOATS * sizeof(float) + 1024;
-  {  // per device and cheap: set on every launch (an index may live on any device)
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dynamic_smem(tc_gemm_tf32x3_kernel, smem);
     if (e != cudaSuccess) return e;
   }
   if (cmin && (!l2 || cmin_pitch < ((N + TC_BN - 1) / TC_BN) * (TC_BN / 32))) return cudaErrorInvalidValue;

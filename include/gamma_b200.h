@@ -166,6 +166,8 @@ int gb200_upload_deleted_bitmap(gb200_index *ix, const uint8_t *bitmap, int64_t 
  * stream and workspaces (up to GB200_MAX_CONTEXTS calls in flight per index, further callers wait for a free one);
  * appends / updates / deletes / raw uploads are serialised among themselves and do not block searches except for
  * the moment a device array has to be re-allocated.  A search sees a list either before or after an append.
+ * Concurrent gb200_ivfpq_search calls with equal parameters and no range filter may travel in one device batch
+ * (GB200_COALESCE); each caller's rows are bit-identical to a call of its own.
  * GammaIVFPQIndex::Search (gamma_index_ivfpq.cc:514-566): coarse quantizer, ADC scan of
  * the nprobe lists with the validity filter inside the scan, recall_num selection,
  * optional exact re-rank, score window, top-k.  xq: n x d f32; out: n x k.             */

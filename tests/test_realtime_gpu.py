@@ -201,3 +201,43 @@ def test_concurrent_searches_and_a_writer():
         th.join()
     for rc_, D_, I_ in outs:
         assert rc_ == 0 and np.array_equal(I_, I_full) and np.array_equal(D_, D_full)
+
+
+def test_merged_batches_equal_serial_calls():
+    """Concurrent callers with equal parameters travel in one device batch (capi.cu search_coalesced); callers with
+    different parameters do not.  Every caller's rows equal the rows of its own serial call, bit for bit."""
+    f = own_fixture(9)
+    ix = f.mirror()
+    variants = [dict(k=10, nprobe=8, recall_num=50), dict(k=7, nprobe=4, recall_num=30), dict(k=10, nprobe=8, recall_num=50, has_rank=False)]
+    plans = []
+    for t in range(12):
+        v = dict(variants[t % 3])
+        lo, hi = (t * 5) % 16, (t * 5) % 16 + 3 + t  # ragged batch sizes 3..14
+        plans.append((v, f.xq[lo:hi]))
+    serial = []
+    for v, xq in plans:
+        v = dict(v)
+        rc, D, I = ix.Search(xq, v.pop("k"), metric="L2", has_rank=v.pop("has_rank", True), **v)
+        assert rc == 0
+        serial.append((D, I))
+    errors = []
+
+    def caller(t):
+        try:
+            v, xq = plans[t]
+            for _ in range(25):
+                vv = dict(v)
+                rc, D, I = ix.Search(xq, vv.pop("k"), metric="L2", has_rank=vv.pop("has_rank", True), **vv)
+                if rc != 0 or not np.array_equal(I, serial[t][1]) or not np.array_equal(D, serial[t][0]):
+                    from gamma_b200 import api
+                    errors.append((t, rc, api.lib().gb200_last_error()))
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=caller, args=(t,)) for t in range(12)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
