@@ -666,9 +666,10 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample of the batch for the CPU engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variants", default="", help="dev only: ';'-separated ENV=VAL[,ENV=VAL] sets to time after the main run")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: result exchange by peer stores over NVLink behind the C-ABI (gb200_ivfpq_search_sharded, "
-                         "default) or by an NCCL all-gather of the packed top-k")
+    ap.add_argument("--exchange", default="p2p-deferred", choices=["p2p", "p2p-deferred", "nccl"],
+                    help="N > 1: result exchange by peer stores over NVLink behind the C-ABI — p2p-deferred (default): a "
+                         "step waits for the peers' results of the step before it (gb200_ivfpq_search_sharded_deferred), "
+                         "p2p: for this step's (gb200_ivfpq_search_sharded) — or by an NCCL all-gather of the packed top-k")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -777,7 +778,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
     comm = None
-    p2p = world > 1 and args.exchange == "p2p"
+    p2p = world > 1 and args.exchange in ("p2p", "p2p-deferred")
+    deferred = p2p and args.exchange == "p2p-deferred"  # a step waits for the peers' results of the step before it
     if world > 1:
         import torch.distributed as dist
         out_all = torch.empty(world * out_bytes, dtype=torch.uint8, device=dev)  # rank r's block at r * out_bytes
@@ -798,7 +800,7 @@ def main():
     def step_dev():
         if p2p:
             gathered[0] = comm.search_sharded(ix, xq_d.data_ptr(), n, K_TOP, stream.cuda_stream, nprobe=w["nprobe"],
-                                              recall_num=RECALL_NUM, metric="L2", has_rank=True)
+                                              recall_num=RECALL_NUM, metric="L2", has_rank=True, deferred=deferred)
             return
         step_plain()
         if world > 1:
@@ -925,6 +927,7 @@ def main():
         ix.reload_tuning()
 
     # ---- e2e: public host call, pinned host buffers, H2D + D2H inside the timed region
+    ix.set_profiling(False)  # no per-stage events on the path a user runs
     xq_pin = torch.from_numpy(xq).pin_memory()
     D_pin = torch.empty(n, K_TOP, dtype=torch.float32).pin_memory()
     I_pin = torch.empty(n, K_TOP, dtype=torch.int64).pin_memory()
@@ -934,6 +937,14 @@ def main():
     if world > 1:
         out_all_pin = torch.empty(world * out_bytes, dtype=torch.uint8).pin_memory()
         xq_stage = torch.empty_like(xq_d)
+
+    def read_gathered(base):
+        if base is None:
+            stream.synchronize()
+            return
+        for r_ in range(world):  # rank r's block sits at r * slot_bytes in the window
+            comm.read(out_all_pin.data_ptr() + r_ * out_bytes, base + r_ * comm.slot_bytes, out_bytes,
+                      stream.cuda_stream, sync=(r_ == world - 1))
 
     def step_host():
         if world == 1:
@@ -947,10 +958,8 @@ def main():
         xq_stage.copy_(xq_pin, non_blocking=True)
         if p2p:
             base = comm.search_sharded(ix, xq_stage.data_ptr(), n, K_TOP, stream.cuda_stream, nprobe=w["nprobe"],
-                                       recall_num=RECALL_NUM, metric="L2", has_rank=True)
-            for r_ in range(world):  # rank r's block sits at r * slot_bytes in the window
-                comm.read(out_all_pin.data_ptr() + r_ * out_bytes, base + r_ * comm.slot_bytes, out_bytes,
-                          stream.cuda_stream, sync=(r_ == world - 1))
+                                       recall_num=RECALL_NUM, metric="L2", has_rank=True, deferred=deferred)
+            read_gathered(base)  # deferred: the gathered result of the step before this one
             return
         rc_ = ix.search_dev(xq_stage.data_ptr(), n, K_TOP, D_d.data_ptr(), I_d.data_ptr(), stream.cuda_stream,
                             nprobe=w["nprobe"], recall_num=RECALL_NUM, metric="L2", has_rank=True)
@@ -966,6 +975,8 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_host()
+    if deferred:  # the last step's gathered result: wait for it and read it inside the timed region
+        read_gathered(comm.flush(stream.cuda_stream))
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -976,6 +987,33 @@ def main():
     else:
         mine = out_all_pin[rank * out_bytes:(rank + 1) * out_bytes][n * K_TOP * 4:].view(torch.int64).numpy().reshape(n, K_TOP)
         assert np.array_equal(mine, I_ours), "gathered result of this rank differs from its device-API result"
+
+    # informational: the same host call from two request threads (the reference's usage: one Search per request thread,
+    # tests/test.h:1033-1062), each with its own pinned buffers — transfers of one call overlap the other's kernels
+    e2e_two = None
+    if world == 1:
+        try:
+            import threading
+            bufs = [(xq_pin, D_pin, I_pin), (xq_pin.clone().pin_memory(), torch.empty_like(D_pin).pin_memory(),
+                                             torch.empty_like(I_pin).pin_memory())]
+
+            def caller(b):
+                for _ in range(args.steps + args.warmup):
+                    r_ = api.lib().gb200_ivfpq_search(ix.h, n, b[0].data_ptr(), K_TOP, ctypes.byref(sp),
+                                                      ctypes.cast(farr, ctypes.c_void_p), len(filters), b[1].data_ptr(),
+                                                      b[2].data_ptr())
+                    assert r_ == 0
+
+            th = [threading.Thread(target=caller, args=(b,)) for b in bufs]
+            t0 = time.perf_counter()
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            e2e_two = 2 * n * (args.steps + args.warmup) / (time.perf_counter() - t0)
+            assert np.array_equal(bufs[1][2].numpy(), I_ours)
+        except Exception as e:  # noqa: BLE001
+            log("two-caller e2e failed: %r" % (e,))
 
     if comm is not None:
         st_ = comm.status()
@@ -1030,16 +1068,21 @@ def main():
                config=dict(workload=w["desc"], N=N, nlist=nlist, M=w["M"], nprobe=w["nprobe"], batch_per_gpu=n,
                            global_batch=world * n, k=K_TOP, recall_num=RECALL_NUM, has_rank=True,
                            parallelism="query-sharded x%d, index replicated, %s" % (
-                               world, "top-k pushed into every peer's window over NVLink (gb200_ivfpq_search_sharded)" if p2p
+                               world, ("top-k pushed into every peer's window over NVLink, a step waits for the peers' results "
+                                       "of the step before it (gb200_ivfpq_search_sharded_deferred)") if deferred else
+                               "top-k pushed into every peer's window over NVLink (gb200_ivfpq_search_sharded)" if p2p
                                else "NCCL all-gather of top-k"),
                            l2="256 MB flush write between steps (untimed); per-step CUDA events",
                            ms_per_step_back_to_back_no_flush=ms_noflush, scaled_down=args.scale != 1.0),
                roofline=roofline, cpu_baseline=cpu,
                e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * w["d"] * 4),
                         d2h_bytes_per_step=int(n * K_TOP * 12 * (world if world > 1 else 1)),
+                        two_request_threads_value=e2e_two,
                         path=("gb200_ivfpq_search (host C-ABI, pinned host buffers)" if world == 1 else
                               "per rank: H2D queries, search + exchange (%s), D2H of the gathered result" % (
-                                  "gb200_ivfpq_search_sharded" if p2p else "gb200_ivfpq_search_dev + NCCL all-gather"))),
+                                  "gb200_ivfpq_search_sharded_deferred, result read one step late, last one after gb200_comm_flush"
+                                  if deferred else "gb200_ivfpq_search_sharded" if p2p else
+                                  "gb200_ivfpq_search_dev + NCCL all-gather"))),
                gpu_launches=int(launches), clocks=clocks, recall_at_10=rec_ours)
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -45,7 +45,7 @@ EXPORTS = [
     "gb200_upload_deleted_bitmap", "gb200_ivfpq_search", "gb200_ivfpq_search_preassigned", "gb200_ivfpq_coarse",
     "gb200_flat_search", "gb200_ivfpq_search_dev", "gb200_flat_search_dev", "gb200_set_filters", "gb200_mem_bytes",
     "gb200_last_scanned_postings", "gb200_launch_count", "gb200_last_stage_ms", "gb200_set_profiling", "gb200_last_scan_kernel_ms", "gb200_sync",
-    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_ivfflat_create", "gb200_ivfflat_set_quantizer", "gb200_ivfflat_append",
+    "gb200_debug_select", "gb200_debug_plan", "gb200_reload_tuning", "gb200_ivfpq_search_sharded_deferred", "gb200_comm_flush", "gb200_ivfpq_compact", "gb200_ivfpq_replace_list", "gb200_ivfpq_encode", "gb200_ivfpq_add_raw", "gb200_ivfpq_add_stored", "gb200_ivfpq_set_opq", "gb200_ivfflat_create", "gb200_ivfflat_set_quantizer", "gb200_ivfflat_append",
     "gb200_ivfflat_add_raw", "gb200_ivfflat_search", "gb200_comm_create", "gb200_comm_connect", "gb200_comm_destroy", "gb200_comm_slot_bytes", "gb200_comm_status", "gb200_comm_read",
     "gb200_comm_buffers", "gb200_comm_exchange", "gb200_ivfpq_search_sharded",
 ]
@@ -110,6 +110,8 @@ def lib():
         L.gb200_comm_exchange.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.gb200_ivfpq_search_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gb200_ivfpq_search_sharded_deferred.argtypes = L.gb200_ivfpq_search_sharded.argtypes
+        L.gb200_comm_flush.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gb200_ivfflat_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gb200_ivfflat_set_quantizer.argtypes = [C.c_void_p, C.c_void_p]
         L.gb200_ivfflat_append.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -509,13 +511,21 @@ class Comm:
     def exchange(self, nbytes, stream_ptr):
         _check(lib().gb200_comm_exchange(self.h, int(nbytes), stream_ptr), "comm_exchange")
 
-    def search_sharded(self, ix, xq_ptr, n, k, stream_ptr, nprobe=-1, recall_num=100, metric=None, has_rank=True):
-        """returns the device address of the gathered window: rank r's block ([n*k] f32, [n*k] i64) at + r * slot_bytes"""
+    def search_sharded(self, ix, xq_ptr, n, k, stream_ptr, nprobe=-1, recall_num=100, metric=None, has_rank=True,
+                       deferred=False):
+        """returns the device address of the gathered window: rank r's block ([n*k] f32, [n*k] i64) at + r * slot_bytes.
+        deferred=True: the window of the PREVIOUS call (None on the first one); flush() gives the last one."""
         sp = ix._sp(ix.metric if metric is None else metric, nprobe, recall_num, has_rank, -FLT_MAX, FLT_MAX)
         D_all = C.c_void_p()
-        _check(lib().gb200_ivfpq_search_sharded(ix.h, self.h, n, xq_ptr, k, C.byref(sp), C.byref(D_all), None, stream_ptr),
-               "search_sharded")
+        fn = lib().gb200_ivfpq_search_sharded_deferred if deferred else lib().gb200_ivfpq_search_sharded
+        _check(fn(ix.h, self.h, n, xq_ptr, k, C.byref(sp), C.byref(D_all), None, stream_ptr), "search_sharded")
         return D_all.value
+
+    def flush(self, stream_ptr):
+        """wait on the stream for the peers' results of the last exchange; returns that window's device address"""
+        allp = C.c_void_p()
+        _check(lib().gb200_comm_flush(self.h, C.byref(allp), stream_ptr), "comm_flush")
+        return allp.value
 
     def status(self):
         return int(lib().gb200_comm_status(self.h))

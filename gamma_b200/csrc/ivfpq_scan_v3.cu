@@ -89,6 +89,12 @@ __device__ __forceinline__ float lds_ctl_f32(uint32_t base) {
   asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF));
   return v;
 }
+// two adjacent control words with one load (8-byte aligned offset)
+template <int OFF>
+__device__ __forceinline__ void lds_ctl_s32_f32(uint32_t base, int &a, float &b) {
+  static_assert(OFF % 8 == 0, "v2 load");
+  asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(a), "=f"(b) : "r"(base), "n"(OFF));
+}
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
   asm volatile("" : "+r"(v));
   return v;
@@ -534,8 +540,9 @@ __device__ __forceinline__ void scan_loop_m32_v3(const ScanParams &P, const V3Sm
         // ---- pre-test, admission.  Every warp reads the counter once per block so that all of them notice a
         // wanted prune within one block, whether or not they append anything themselves.  The pre-test is one float
         // compare against the float image of tau's distance word (NaN fails it, as in the reference's heap compare).
-        const float tau_f = lds_ctl_f32<12>(ctl);
-        const int cnt_now = lds_ctl_s32<8>(ctl);
+        float tau_f;  // misc[3]
+        int cnt_now;  // misc[2]: one 8-byte load for both
+        lds_ctl_s32_f32<8>(ctl, cnt_now, tau_f);
         float s0, s1, s2, s3;
         f2_unpack(s01, s0, s1);
         f2_unpack(s23, s2, s3);

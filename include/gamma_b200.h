@@ -266,6 +266,14 @@ int gb200_comm_exchange(gb200_comm *c, int64_t bytes, void *stream);
  * *D_all + r * slot_bytes / 4 ... — see gb200_comm_buffers for the layout                                             */
 int gb200_ivfpq_search_sharded(gb200_index *ix, gb200_comm *c, int n, const float *xq_dev, int k,
                                const gb200_search_params *sp, float **D_all, int64_t **I_all_of_rank0, void *stream);
+/* the pipelined form: search, push this rank's result to the peers, and wait only for the peers' results of the PREVIOUS
+ * call — *D_all_prev is that call's gathered window (NULL on the first call).  No rank idles for the slowest rank of the
+ * current step; a server consumes gathered results one call late.  gb200_comm_flush waits (on `stream`) for the last
+ * call's results and returns their window.  Both forms may be mixed on one gb200_comm.                                */
+int gb200_ivfpq_search_sharded_deferred(gb200_index *ix, gb200_comm *c, int n, const float *xq_dev, int k,
+                                        const gb200_search_params *sp, float **D_all_prev, int64_t **I_all_prev_of_rank0,
+                                        void *stream);
+int gb200_comm_flush(gb200_comm *c, void **all_slots, void *stream);
 
 /* ---- test hook (not used by the plugin): run the streaming top-R selection primitive the scan
  * kernels use (append + radix-select prune, one CTA of `threads`) on caller-provided 64-bit keys fed

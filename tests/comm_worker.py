@@ -65,6 +65,39 @@ def main():
             D = blk[:n * k * 4].view(torch.float32).numpy().reshape(n, k)
             I = blk[n * k * 4:n * k * 12].view(torch.int64).numpy().reshape(n, k)
             ok &= bool(np.array_equal(I, I_full[r * n:(r + 1) * n]) and np.array_equal(D, D_full[r * n:(r + 1) * n]))
+    # pipelined form: call i hands back the gathered result of call i - 1; the batches alternate so that a stale or
+    # early window would be noticed; mixed with the immediate form on the same comm
+    xq2 = synth.mixture(n * world, d, 9, n_clusters=64)
+    rc, D_full2, I_full2 = ix.Search(xq2, k, nprobe=8, recall_num=50, metric="L2", has_rank=True)
+    assert rc == 0
+    xq2_d = torch.from_numpy(np.ascontiguousarray(xq2[rank * n:(rank + 1) * n])).to(dev)
+    expect = [(D_full, I_full), (D_full2, I_full2)]
+
+    def check(base, which):
+        host = torch.empty(world * comm.slot_bytes, dtype=torch.uint8)
+        comm.read(host.data_ptr(), base, world * comm.slot_bytes, stream.cuda_stream, sync=True)
+        good = True
+        for r in range(world):
+            blk = host[r * comm.slot_bytes:(r + 1) * comm.slot_bytes]
+            D = blk[:n * k * 4].view(torch.float32).numpy().reshape(n, k)
+            I = blk[n * k * 4:n * k * 12].view(torch.int64).numpy().reshape(n, k)
+            good &= bool(np.array_equal(I, expect[which][1][r * n:(r + 1) * n]) and
+                         np.array_equal(D, expect[which][0][r * n:(r + 1) * n]))
+        return good
+
+    prev = None
+    for it in range(9):  # every window buffer more than twice
+        which = it & 1
+        base = comm.search_sharded(ix, (xq2_d if which else xq_d).data_ptr(), n, k, stream.cuda_stream, nprobe=8,
+                                   recall_num=50, metric="L2", deferred=True)
+        if it == 0:
+            ok &= base is not None  # an immediate exchange ran before: its window is the "previous" one
+        if base is not None and prev is not None:
+            ok &= check(base, prev)
+        prev = which
+    ok &= check(comm.flush(stream.cuda_stream), prev)
+    base = comm.search_sharded(ix, xq_d.data_ptr(), n, k, stream.cuda_stream, nprobe=8, recall_num=50, metric="L2")
+    ok &= check(base, 0)
     st = comm.status()
     print(json.dumps(dict(rank=rank, ok=ok, status=st)), flush=True)
     comm.close()
