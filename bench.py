@@ -878,8 +878,8 @@ def main():
         dist.barrier()
     load_for(400)
     clocks = sampler.stop(mark0, mark1)
-    if world > 1:
-        launches += args.steps  # the exchange kernel (or the NCCL all-gather) per step
+    if world > 1 and not p2p:
+        launches += args.steps  # the NCCL all-gather per step (p2p: the re-rank kernel itself feeds the peers)
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -988,33 +988,6 @@ def main():
         mine = out_all_pin[rank * out_bytes:(rank + 1) * out_bytes][n * K_TOP * 4:].view(torch.int64).numpy().reshape(n, K_TOP)
         assert np.array_equal(mine, I_ours), "gathered result of this rank differs from its device-API result"
 
-    # informational: the same host call from two request threads (the reference's usage: one Search per request thread,
-    # tests/test.h:1033-1062), each with its own pinned buffers — transfers of one call overlap the other's kernels
-    e2e_two = None
-    if world == 1:
-        try:
-            import threading
-            bufs = [(xq_pin, D_pin, I_pin), (xq_pin.clone().pin_memory(), torch.empty_like(D_pin).pin_memory(),
-                                             torch.empty_like(I_pin).pin_memory())]
-
-            def caller(b):
-                for _ in range(args.steps + args.warmup):
-                    r_ = api.lib().gb200_ivfpq_search(ix.h, n, b[0].data_ptr(), K_TOP, ctypes.byref(sp),
-                                                      ctypes.cast(farr, ctypes.c_void_p), len(filters), b[1].data_ptr(),
-                                                      b[2].data_ptr())
-                    assert r_ == 0
-
-            th = [threading.Thread(target=caller, args=(b,)) for b in bufs]
-            t0 = time.perf_counter()
-            for t_ in th:
-                t_.start()
-            for t_ in th:
-                t_.join()
-            e2e_two = 2 * n * (args.steps + args.warmup) / (time.perf_counter() - t0)
-            assert np.array_equal(bufs[1][2].numpy(), I_ours)
-        except Exception as e:  # noqa: BLE001
-            log("two-caller e2e failed: %r" % (e,))
-
     if comm is not None:
         st_ = comm.status()
         assert st_ == 0, "exchange: peer %d did not arrive" % (st_ - 1)
@@ -1077,7 +1050,6 @@ def main():
                roofline=roofline, cpu_baseline=cpu,
                e2e=dict(value=e2e_qps, unit="queries/s", h2d_bytes_per_step=int(n * w["d"] * 4),
                         d2h_bytes_per_step=int(n * K_TOP * 12 * (world if world > 1 else 1)),
-                        two_request_threads_value=e2e_two,
                         path=("gb200_ivfpq_search (host C-ABI, pinned host buffers)" if world == 1 else
                               "per rank: H2D queries, search + exchange (%s), D2H of the gathered result" % (
                                   "gb200_ivfpq_search_sharded_deferred, result read one step late, last one after gb200_comm_flush"

@@ -164,6 +164,8 @@ struct SearchCtx {
   size_t h_stage_cap = 0;
   int lut_built_n = 0, lut_built_ip = -1;  // the side stream holds tables for this many queries of the current search
   int zero_req = 0, zeroed_for = 0;  // scan control words: queries the coarse stage should zero them for / did
+  const gb::PeerSink *sink = nullptr;  // multi-GPU: the final kernel of this search also feeds the peers (comm.cu)
+  bool sink_used = false;
   long long launches = 0;
   bool timed = false;  // the events of the last call were recorded
 
@@ -1566,6 +1568,10 @@ static int scan_rerank_dev(gb200_index *ix, SearchCtx &c, int n, const float *d_
   Q.max_score = sp->max_score;
   Q.nsplit = d_rows;  // v3: rows handed out per query (clamped to S by the kernel)
   Q.n_full = P.n_items > 0 ? P.n_full : 0;
+  if (c.sink) {
+    Q.sink = *c.sink;
+    c.sink_used = true;
+  }
   CK(launch_rerank(Q, c.stream));
   if (c.timed) CK(cudaEventRecord(c.ev[3], c.stream));
   c.launches += 2;
@@ -1771,15 +1777,18 @@ static int search_coalesced(gb200_index *ix, int n, const float *xq, int k, cons
       return me.rc;
     }
     ix->co_leaders++;
+    // from here on this request belongs to its own batch: out of the waiting list BEFORE the lock is dropped below, or a
+    // second batch forming meanwhile would take it along as well
+    w.erase(std::find(w.begin(), w.end(), &me));
     auto share = [&] {
-      ix->co_peak = std::max(ix->co_peak, ix->co_inflight + (int)w.size());
+      ix->co_peak = std::max(ix->co_peak, ix->co_inflight + 1 + (int)w.size());
       return std::max(1, (ix->co_peak + T.coalesce - 1) / T.coalesce);
     };
     if (T.coalesce_wait_us > 0 && ix->co_running > 0) {
       const auto t0 = std::chrono::steady_clock::now();
       for (;;) {
         const int want = std::min(share(), std::max(1, ix->co_peak - ix->co_inflight));
-        if ((int)w.size() >= want || ix->co_running == 0) break;
+        if (1 + (int)w.size() >= want || ix->co_running == 0) break;
         if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(T.coalesce_wait_us)) break;
         g.unlock();
         std::this_thread::yield();
@@ -1792,7 +1801,6 @@ static int search_coalesced(gb200_index *ix, int n, const float *xq, int k, cons
     size_t keep = 0;
     for (size_t i = 0; i < w.size(); i++) {
       gb200_index::PendingSearch *r = w[i];
-      if (r == &me) continue;
       if ((int)grp.size() < max_reqs && same_search(*r, me) && total + r->n <= T.coalesce_max) {
         grp.push_back(r);
         r->taken = true;
@@ -1854,17 +1862,7 @@ int gb200_ivfpq_search_preassigned(gb200_index *ix, int n, const float *xq, int 
 
 int gb200_ivfpq_search_dev(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp,
                            float *D_dev, int64_t *I_dev, void *stream) {
-  CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
-  if (ix->kind != 0) return GB200_EINVAL;
-  CKI(use_device(ix));
-  SearchScope s(ix);
-  if (!s.c) return GB200_ECUDA;
-  // order after the caller's stream, run on the context's, and make the caller's stream wait for the result
-  cudaStream_t cs = (cudaStream_t)stream;
-  CKI(join_user_stream(*s.c, cs));
-  int rc = ivfpq_search_impl(ix, *s.c, n, xq_dev, true, k, sp, nullptr, 0, true, nullptr, nullptr, 0, D_dev, I_dev, true);
-  if (rc == GB200_OK) CKI(release_to_user_stream(*s.c, cs));
-  return rc;
+  return gb_ivfpq_search_dev_sink(ix, n, xq_dev, k, sp, D_dev, I_dev, stream, nullptr, nullptr);
 }
 
 int gb200_ivfpq_coarse(gb200_index *ix, int n, const float *xq, int nprobe, float *coarse_dis, int64_t *keys) {
@@ -2413,3 +2411,24 @@ int gb200_reload_tuning(gb200_index *ix) {
 }
 
 }  // extern "C"
+
+// gb200_ivfpq_search_dev, optionally with a multi-GPU sink on its final kernel (kernels.h; called by comm.cu)
+int gb_ivfpq_search_dev_sink(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp, float *D_dev,
+                             int64_t *I_dev, void *stream, const gb::PeerSink *sink, int *sink_used) {
+  if (sink_used) *sink_used = 0;
+  CKI(check_search_args(ix, n, xq_dev, k, sp, D_dev, I_dev));
+  if (ix->kind != 0) return GB200_EINVAL;
+  CKI(use_device(ix));
+  SearchScope s(ix);
+  if (!s.c) return GB200_ECUDA;
+  // order after the caller's stream, run on the context's, and make the caller's stream wait for the result
+  cudaStream_t cs = (cudaStream_t)stream;
+  CKI(join_user_stream(*s.c, cs));
+  s.c->sink = sink;
+  s.c->sink_used = false;
+  int rc = ivfpq_search_impl(ix, *s.c, n, xq_dev, true, k, sp, nullptr, 0, true, nullptr, nullptr, 0, D_dev, I_dev, true);
+  s.c->sink = nullptr;
+  if (sink_used) *sink_used = s.c->sink_used ? 1 : 0;
+  if (rc == GB200_OK) CKI(release_to_user_stream(*s.c, cs));
+  return rc;
+}

@@ -7,6 +7,11 @@
 //   window (per rank, four buffers, buffer = epoch % 4):  [4][world][slot_bytes] results + [4][world] u32 flags
 //   exchange kernel, CTA p: copy my slot -> peer p's window (16-byte stores), __threadfence_system, flag[p's view of me]
 //                           = epoch (release, system scope); then spin on MY flag from peer p (acquire, system scope).
+// Fused form (what gb200_ivfpq_search_sharded* normally run): there is no exchange kernel at all — the search's final
+// kernel (rerank_kernel, one CTA per query) stores each query's k results into every peer's window right where it
+// writes them locally, every CTA fences at system scope and counts itself done, and the last CTA raises the flags and
+// does the wait (kernels.h PeerSink, rerank.cu).  The separate kernel below serves gb200_comm_exchange and searches that
+// end in another kernel.
 // Two ways to wait:
 //   * gb200_ivfpq_search_sharded waits for the peers' flags of THIS epoch: the gathered result of this call is readable
 //     when the stream gets past the kernel;
@@ -80,6 +85,7 @@ struct gb200_comm {
   uint4 **d_peer_slot = nullptr;      // [NBUF][world] where MY slot lives in every peer's window
   uint32_t **d_peer_flag = nullptr;   // [NBUF][world] MY flag in every peer's window
   unsigned int *d_err = nullptr;      // set by the exchange kernel when a peer did not arrive in time
+  unsigned int *d_done = nullptr;     // CTA counter of the fused form (the search's final kernel feeds the peers itself)
   uint32_t epoch = 0;
   bool connected = false;
   static constexpr int NBUF = 4;
@@ -143,9 +149,10 @@ int gb200_comm_connect(gb200_comm *c, const uint8_t *handles) {
     }
   if (cudaMalloc(&c->d_peer_slot, slots.size() * sizeof(uint4 *)) != cudaSuccess ||
       cudaMalloc(&c->d_peer_flag, flags.size() * sizeof(uint32_t *)) != cudaSuccess ||
-      cudaMalloc(&c->d_err, sizeof(unsigned int)) != cudaSuccess)
+      cudaMalloc(&c->d_err, sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&c->d_done, sizeof(unsigned int)) != cudaSuccess)
     return GB200_ENOMEM;
   cudaMemset(c->d_err, 0, sizeof(unsigned int));
+  cudaMemset(c->d_done, 0, sizeof(unsigned int));
   cudaMemcpy(c->d_peer_slot, slots.data(), slots.size() * sizeof(uint4 *), cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_peer_flag, flags.data(), flags.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice);
   c->connected = true;
@@ -161,6 +168,7 @@ int gb200_comm_destroy(gb200_comm *c) {
   if (c->d_peer_slot) cudaFree(c->d_peer_slot);
   if (c->d_peer_flag) cudaFree(c->d_peer_flag);
   if (c->d_err) cudaFree(c->d_err);
+  if (c->d_done) cudaFree(c->d_done);
   if (c->win) cudaFree(c->win);
   delete c;
   return GB200_OK;
@@ -206,10 +214,39 @@ static int search_sharded(gb200_index *ix, gb200_comm *c, int n, const float *xq
   gb200_comm_buffers(c, &mine, &all);
   float *D = static_cast<float *>(mine);
   int64_t *I = reinterpret_cast<int64_t *>(static_cast<unsigned char *>(mine) + (size_t)n * k * 4);
-  int rc = gb200_ivfpq_search_dev(ix, n, xq_dev, k, sp, D, I, stream);
+  // Fused form: the search's final kernel stores each query's k results into every peer's window as it produces them,
+  // its last CTA raises this rank's flags and does the wait — the exchange costs no launch and no second pass over the
+  // results.  (Searches that end in another kernel, or more peers than the sink holds: the separate exchange kernel.)
+  gb::PeerSink sk;
+  memset(&sk, 0, sizeof(sk));
+  const uint32_t e = c->epoch + 1, wait_epoch = deferred ? e - 1 : e;
+  const int buf = (int)(e % gb200_comm::NBUF);
+  const bool fuse = c->connected && c->world > 1 && c->world - 1 <= gb::GB_MAX_PEERS && ((long long)n * k) % 2 == 0;
+  if (fuse) {
+    for (int p = 0; p < c->world; p++) {
+      if (p == c->rank) continue;
+      unsigned char *slot = c->slot_of(c->peer[p], buf, c->rank);
+      const int i = sk.n_peers++;
+      sk.dist[i] = reinterpret_cast<float *>(slot);
+      sk.ids[i] = reinterpret_cast<long long *>(slot + (size_t)n * k * 4);
+      sk.flag[i] = c->flags_of(c->peer[p], buf) + c->rank;
+      sk.wait[i] = wait_epoch ? c->flags_of(c->win, (int)(wait_epoch % gb200_comm::NBUF)) + p : nullptr;
+      sk.peer_rank[i] = p;
+    }
+    sk.epoch = e;
+    sk.wait_epoch = wait_epoch;
+    sk.done = c->d_done;
+    sk.err = c->d_err;
+  }
+  int used = 0;
+  int rc = gb_ivfpq_search_dev_sink(ix, n, xq_dev, k, sp, D, I, stream, fuse ? &sk : nullptr, &used);
   if (rc != GB200_OK) return rc;
-  rc = comm_exchange(c, per, stream, deferred);
-  if (rc != GB200_OK) return rc;
+  if (used) {
+    c->epoch = e;  // pushed, flagged and awaited by the search's final kernel
+  } else {
+    rc = comm_exchange(c, per, stream, deferred);
+    if (rc != GB200_OK) return rc;
+  }
   if (deferred)  // the window of the epoch before the one just pushed (nullptr on the first call)
     all = c->epoch >= 2 ? c->slot_of(c->win, (int)((c->epoch - 1) % gb200_comm::NBUF), 0) : nullptr;
   // rank r's block: [n*k] f32 distances then [n*k] i64 ids at all + r * slot_bytes

@@ -174,6 +174,22 @@ int ivfflat_buffer_cap(int R);
 cudaError_t launch_ivfflat_scan(const IvfFlatParams &P, cudaStream_t st);
 
 // K3 — merge the per-split survivors, optional exact re-rank, score window, top-k
+// Multi-GPU result sink of the final kernel of a search (comm.cu): the kernel stores every query's k results into each
+// peer's result window as well (peer memory over NVLink), and its last CTA raises this rank's flag there — the exchange
+// rides on the kernel that produces the results.
+constexpr int GB_MAX_PEERS = 15;
+struct PeerSink {
+  int n_peers;                        // 0 = none
+  float *dist[GB_MAX_PEERS];          // [n][k] in peer p's window
+  long long *ids[GB_MAX_PEERS];       // [n][k]
+  uint32_t *flag[GB_MAX_PEERS];       // this rank's flag in peer p's window (release store of `epoch`)
+  const uint32_t *wait[GB_MAX_PEERS]; // peer p's flag in MY window to wait for (>= wait_epoch), or nullptr
+  uint32_t epoch, wait_epoch;
+  unsigned int *done;                 // CTA counter (zero between launches)
+  unsigned int *err;                  // set to 1 + p when peer p did not arrive in time
+  int peer_rank[GB_MAX_PEERS];
+};
+
 struct RerankParams {
   const u64 *cand;          // [n][S][R]
   const int *keys;          // [n][nprobe]
@@ -190,6 +206,7 @@ struct RerankParams {
   int no_stage;             // tuning: 1 = the L2-prefetch + load-on-use path
   const int *nsplit;        // optional [n]: candidate rows the query really has (<= S); nullptr = S ...
   int n_full;               // ... or, when > 0 (positional plan), 1 row for q < n_full and S rows otherwise
+  PeerSink sink;            // multi-GPU: also store the results into the peers' windows (n_peers = 0: off)
 };
 cudaError_t launch_rerank(const RerankParams &P, cudaStream_t st);
 
@@ -231,3 +248,10 @@ cudaError_t launch_build_valid(const uint32_t *live, long long live_bits, const 
                                int n_filters, uint32_t *valid, long long nbits, cudaStream_t st);
 
 }  // namespace gb
+
+// internal (capi.cu, used by comm.cu): gb200_ivfpq_search_dev whose final kernel also stores the results into the peers'
+// windows and raises / awaits the exchange flags (sink); *sink_used = 0 when the search took a path without that kernel
+struct gb200_index;
+struct gb200_search_params;
+int gb_ivfpq_search_dev_sink(gb200_index *ix, int n, const float *xq_dev, int k, const gb200_search_params *sp, float *D_dev,
+                             int64_t *I_dev, void *stream, const gb::PeerSink *sink, int *sink_used);

@@ -124,12 +124,17 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
     block_bitonic_sort(keys2, p2_r);
     for (int j = tid; j < P.k; j += RR_THREADS) {
       u64 k = j < p2_r ? keys2[j] : GB_KEY_MAX;
+      float dv = neutral;
+      long long iv = -1;
       if (k != GB_KEY_MAX) {
-        od[j] = key32_to_dist<IP>((uint32_t)(k >> 32));
-        oi[j] = vids[(uint32_t)k];
-      } else {
-        od[j] = neutral;
-        oi[j] = -1;
+        dv = key32_to_dist<IP>((uint32_t)(k >> 32));
+        iv = vids[(uint32_t)k];
+      }
+      od[j] = dv;
+      oi[j] = iv;
+      for (int p = 0; p < P.sink.n_peers; p++) {  // multi-GPU: the same row into every peer's window (NVLink stores)
+        P.sink.dist[p][(size_t)q * P.k + j] = dv;
+        P.sink.ids[p][(size_t)q * P.k + j] = iv;
       }
     }
   } else {
@@ -156,6 +161,46 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
       for (int j = filled + tid; j < P.k; j += 32) {
         od[j] = neutral;
         oi[j] = -1;
+      }
+      if (P.sink.n_peers) {  // multi-GPU: copy the finished row (this warp wrote all of it)
+        __syncwarp();
+        for (int j = tid; j < P.k; j += 32) {
+          const float dv = od[j];
+          const long long iv = oi[j];
+          for (int p = 0; p < P.sink.n_peers; p++) {
+            P.sink.dist[p][(size_t)q * P.k + j] = dv;
+            P.sink.ids[p][(size_t)q * P.k + j] = iv;
+          }
+        }
+      }
+    }
+  }
+  if (P.sink.n_peers) {
+    // Every thread that stored into a peer's window fences its stores at system scope; the CTA then counts itself done.
+    // The last CTA of the grid has (through the counter) observed every other CTA's fence, so the flags it raises with
+    // release stores become visible at the peers after all rows of this rank.  It also does this exchange's wait: for
+    // the peers' flags of wait_epoch (deferred form: the previous exchange, normally long there).
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(P.sink.done, 1u);
+      if (prev == gridDim.x - 1) {
+        *P.sink.done = 0u;  // for the next launch (stream order)
+        __threadfence_system();
+        for (int p = 0; p < P.sink.n_peers; p++)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.sink.flag[p]), "r"(P.sink.epoch) : "memory");
+        for (int p = 0; p < P.sink.n_peers; p++) {
+          if (P.sink.wait[p] == nullptr) continue;
+          uint32_t v;
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(P.sink.wait[p]) : "memory");
+            if (clock64() - t0 > 8000000000LL) {  // ~4 s: the peer failed or was never called — do not hang
+              atomicExch(P.sink.err, 1u + (unsigned)P.sink.peer_rank[p]);
+              break;
+            }
+          } while ((int32_t)(v - P.sink.wait_epoch) < 0);
+        }
       }
     }
   }

@@ -225,7 +225,7 @@ def test_merged_batches_equal_serial_calls():
     def caller(t):
         try:
             v, xq = plans[t]
-            for _ in range(25):
+            for _ in range(60):
                 vv = dict(v)
                 rc, D, I = ix.Search(xq, vv.pop("k"), metric="L2", has_rank=vv.pop("has_rank", True), **vv)
                 if rc != 0 or not np.array_equal(I, serial[t][1]) or not np.array_equal(D, serial[t][0]):
