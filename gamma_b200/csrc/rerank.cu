@@ -176,13 +176,14 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams P, int 
     }
   }
   if (P.sink.n_peers) {
-    // Every thread that stored into a peer's window fences its stores at system scope; the CTA then counts itself done.
-    // The last CTA of the grid has (through the counter) observed every other CTA's fence, so the flags it raises with
+    // The CTA's stores into the peers' windows are ordered before thread 0's system-scope fence by the barrier (the
+    // pattern of a collective's "store, barrier, one thread fences and signals"); the CTA then counts itself done.  The
+    // last CTA of the grid has (through the counter) observed every other CTA's fence, so the flags it raises with
     // release stores become visible at the peers after all rows of this rank.  It also does this exchange's wait: for
     // the peers' flags of wait_epoch (deferred form: the previous exchange, normally long there).
-    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+      __threadfence_system();
       const unsigned int prev = atomicAdd(P.sink.done, 1u);
       if (prev == gridDim.x - 1) {
         *P.sink.done = 0u;  // for the next launch (stream order)
