@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "../../include/gamma_b200.h"
+#include "coalesce.h"
 #include "kernels.h"
 
 using namespace gb;
@@ -213,24 +214,19 @@ struct gb200_index {
   std::mutex writer_mu;
   std::mutex ctx_mu;
   std::condition_variable ctx_cv;
-  // concurrent small searches waiting to be merged into one device batch (search_coalesced)
+  // concurrent small searches waiting to be merged into one device batch (search_coalesced, coalesce.h)
   struct PendingSearch {
     int n, k;
     const float *xq;
     float *D;
     int64_t *I;
     gb200_search_params sp;
-    int rc = GB200_OK;
-    bool taken = false, done = false;  // travelling in another caller's batch / that batch has finished
-    std::string err;
+    bool same(const PendingSearch &b) const {
+      return k == b.k && sp.metric == b.sp.metric && sp.nprobe == b.sp.nprobe && sp.recall_num == b.sp.recall_num &&
+             sp.has_rank == b.sp.has_rank && sp.min_score == b.sp.min_score && sp.max_score == b.sp.max_score;
+    }
   };
-  std::mutex co_mu;
-  std::condition_variable co_cv;
-  std::vector<PendingSearch *> co_waiting;
-  int co_leaders = 0;   // batches being formed or running (<= tune.coalesce)
-  int co_running = 0;   // batches on the device
-  int co_inflight = 0;  // callers travelling in them
-  int co_peak = 0;      // recent number of concurrent callers (in flight + waiting), decays by one per batch
+  gb::Coalescer<PendingSearch> coalescer;
   std::vector<SearchCtx *> ctx_all, ctx_free;
   SearchCtx *last_ctx = nullptr;  // most recently used context (gb200_sync / profiling read-out)
   std::mutex stats_mu;
@@ -1750,89 +1746,33 @@ static int run_merged(gb200_index *ix, const std::vector<gb200_index::PendingSea
   return GB200_OK;
 }
 
-static bool same_search(const gb200_index::PendingSearch &a, const gb200_index::PendingSearch &b) {
-  return a.k == b.k && a.sp.metric == b.sp.metric && a.sp.nprobe == b.sp.nprobe && a.sp.recall_num == b.sp.recall_num &&
-         a.sp.has_rank == b.sp.has_rank && a.sp.min_score == b.sp.min_score && a.sp.max_score == b.sp.max_score;
-}
-
-// Group commit for concurrent callers (reference: one Search per request thread, tests/test.h:1033-1062).  Up to
-// tune.coalesce batches are in flight at once, each on its own context, so the device always has the next batch queued
-// behind the running one.  A caller that arrives while that many are in flight waits, and the next batch to start takes
-// the waiting requests with the same parameters along.  A batch that starts while the device is busy anyway first waits
-// (at most coalesce_wait_us, spinning) until its share of the recent callers has arrived: threads released by one batch
-// come back within microseconds of one another and would otherwise each start a batch of their own.  A lone caller, or
-// any caller that finds the device idle, starts at once.
+// Group commit for concurrent callers: the policy lives in coalesce.h (host-only, stress-tested under ThreadSanitizer by
+// tests/test_coalesce_cpu.py); here only what a batch of requests runs.
 static int search_coalesced(gb200_index *ix, int n, const float *xq, int k, const gb200_search_params *sp, float *D, int64_t *I) {
   gb200_index::PendingSearch me;
   me.n = n, me.k = k, me.xq = xq, me.D = D, me.I = I, me.sp = *sp;
-  std::vector<gb200_index::PendingSearch *> grp;
-  const Tuning &T = ix->tune;
-  {
-    std::unique_lock<std::mutex> g(ix->co_mu);
-    auto &w = ix->co_waiting;
-    w.push_back(&me);
-    ix->co_cv.wait(g, [&] { return me.done || (!me.taken && ix->co_leaders < T.coalesce); });
-    if (me.done) {
-      if (me.rc != GB200_OK) set_err("%s", me.err.c_str());
-      return me.rc;
-    }
-    ix->co_leaders++;
-    // from here on this request belongs to its own batch: out of the waiting list BEFORE the lock is dropped below, or a
-    // second batch forming meanwhile would take it along as well
-    w.erase(std::find(w.begin(), w.end(), &me));
-    auto share = [&] {
-      ix->co_peak = std::max(ix->co_peak, ix->co_inflight + 1 + (int)w.size());
-      return std::max(1, (ix->co_peak + T.coalesce - 1) / T.coalesce);
-    };
-    if (T.coalesce_wait_us > 0 && ix->co_running > 0) {
-      const auto t0 = std::chrono::steady_clock::now();
-      for (;;) {
-        const int want = std::min(share(), std::max(1, ix->co_peak - ix->co_inflight));
-        if (1 + (int)w.size() >= want || ix->co_running == 0) break;
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(T.coalesce_wait_us)) break;
-        g.unlock();
-        std::this_thread::yield();
-        g.lock();
-      }
-    }
-    const int max_reqs = T.coalesce_balance ? share() : (1 << 30);
-    int total = me.n;
-    grp.push_back(&me);
-    size_t keep = 0;
-    for (size_t i = 0; i < w.size(); i++) {
-      gb200_index::PendingSearch *r = w[i];
-      if ((int)grp.size() < max_reqs && same_search(*r, me) && total + r->n <= T.coalesce_max) {
-        grp.push_back(r);
-        r->taken = true;
-        total += r->n;
-      } else {
-        w[keep++] = r;
-      }
-    }
-    w.resize(keep);
-    ix->co_peak = std::max(ix->co_inflight + (int)grp.size() + (int)w.size(), ix->co_peak - 1);
-    ix->co_running++;
-    ix->co_inflight += (int)grp.size();
-  }
-  int rc;
-  if (grp.size() == 1) {  // nobody to take along: the plain path, results straight into the caller's buffers
-    SearchScope s(ix);
-    rc = !s.c ? GB200_ECUDA : ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, nullptr, 0, false, nullptr, nullptr, 0, D, I, false);
-  } else {
-    rc = run_merged(ix, grp);
-  }
-  {
-    std::lock_guard<std::mutex> g(ix->co_mu);
-    ix->co_leaders--;
-    ix->co_running--;
-    ix->co_inflight -= (int)grp.size();
-    for (size_t i = 1; i < grp.size(); i++) {
-      grp[i]->rc = rc;
-      if (rc != GB200_OK) grp[i]->err = g_err;
-      grp[i]->done = true;
-    }
-  }
-  ix->co_cv.notify_all();
+  gb::CoalescePolicy pol;
+  pol.slots = ix->tune.coalesce;
+  pol.max_queries = ix->tune.coalesce_max;
+  pol.wait_us = ix->tune.coalesce_wait_us;
+  pol.balance = ix->tune.coalesce_balance;
+  std::string err;
+  const int rc = ix->coalescer.submit(
+      me, pol,
+      [&](const std::vector<gb200_index::PendingSearch *> &grp, std::string &e) {
+        int r;
+        if (grp.size() == 1) {  // nobody to take along: the plain path, results straight into the caller's buffers
+          SearchScope s(ix);
+          r = !s.c ? GB200_ECUDA
+                   : ivfpq_search_impl(ix, *s.c, n, xq, false, k, sp, nullptr, 0, false, nullptr, nullptr, 0, D, I, false);
+        } else {
+          r = run_merged(ix, grp);
+        }
+        if (r != GB200_OK) e = g_err;
+        return r;
+      },
+      &err);
+  if (rc != GB200_OK && !err.empty()) set_err("%s", err.c_str());  // this request travelled in another caller's batch
   return rc;
 }
 
