@@ -4,19 +4,23 @@
 metric  : QPS @ recall@10 (d=128, 10M vecs, nprobe=32, batch=1024) — BASELINE.json
 workload: IVFPQ d=128 nlist=16384 PQ32x8, 10M synthetic vectors, nprobe=32, recall_num=100,
           exact re-rank on, k=10, L2 (SURVEY.md §8d "headline shape").  `--workload c3` = PQ64x8 +
-          range-filter bitmap + 1 % deletions, `--workload c2` = 1M/nlist 4096/nprobe 16/batch 256.
+          range-filter bitmap + 1 % deletions, `--workload c2` = 1M/nlist 4096/nprobe 16/batch 256, `--workload c4` =
+          FLAT inner product d=768 5M batch 512, `--workload c5` = 100M/nlist 65536/nprobe 64/batch 4096 built on the
+          device (BASELINE.json configs).
 step    : one Search of one batch (coarse quantiser + ADC scan + select + re-rank + top-k).
 value   : device-timed (CUDA events), queries resident in HBM, L2 flushed between steps.
 e2e     : the same Search through the public host C-ABI call with pinned HOST buffers
-          (H2D of the queries and D2H of the results inside the timed region).
+          (H2D of the queries and D2H of the results inside the timed region; N > 1: also the exchange and the D2H of
+          the gathered result).
 roofline: ADC scan kernel, algorithmic bytes = scanned postings x (code_size + 4)  (SURVEY §8d).
 cpu_baseline / --impl reference: the reference's own CPU engine (oracle/_ref = unmodified
           GammaIVFPQIndex over faiss 1.7.1, compiled by oracle/Makefile) searching the SAME index on
           the host cores, on a bounded sample of the batch.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torch.distributed.run
-(one rank per GPU, index replicated, queries sharded: every rank searches its own batch, then an
-NCCL all-gather of the per-rank top-k — weak scaling, global batch = N x 1024).
+(one rank per GPU, index replicated, queries sharded: every rank searches its own batch and its re-rank kernel stores
+the top-k into every peer's result window over NVLink — gb200_ivfpq_search_sharded[_deferred], `--exchange`; weak
+scaling, global batch = N x 1024; torch.distributed carries only the IPC handles and the timing reductions).
 """
 import argparse
 import ctypes
